@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.json by running the UNMODIFIED reference (CPU, torch eager).
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container, where /root/reference is
+mounted read-only:
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py [--only NAME] [--full-c1]
+
+The reference cannot travel to the GPU box, so the vectors it produces are
+committed.  fp32 values are stored as uint32 bit patterns so that comparisons are
+exact.  `semantics="reference"` is the shipped code; `semantics="lorentz"` is the
+shipped code with the three functions of SURVEY.md Appendix B monkey-patched in
+(distance / batch_distance / log_map) -- nothing else is touched.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import random
+import sys
+import warnings
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+warnings.filterwarnings("ignore")
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+import torch  # noqa: E402
+
+import embedding.lorentz_model as RL  # noqa: E402
+import tokenizer.hyperbolic_merge as RH  # noqa: E402
+import tokenizer.fast_hyperbolic_merge as RF  # noqa: E402
+import tokenizer.frequency_aware_hyperbolic_merge as RQ  # noqa: E402
+import tqdm as _tqdm  # noqa: E402
+
+# silence progress bars
+for _m in (RH, RF, RQ):
+    if hasattr(_m, "tqdm"):
+        _m.tqdm = lambda it, **kw: _Quiet(it)
+
+
+class _Quiet:
+    def __init__(self, it):
+        self.it = it
+
+    def __iter__(self):
+        return iter(self.it)
+
+    def set_postfix(self, *a, **k):
+        pass
+
+
+_tqdm.tqdm = lambda it=None, **kw: _Quiet(it)
+
+
+def bits(t) -> list:
+    a = t.detach().cpu().contiguous().numpy() if isinstance(t, torch.Tensor) else np.asarray(t, dtype=np.float32)
+    return a.astype(np.float32).view(np.uint32).reshape(-1).tolist()
+
+
+def fbits(x: float) -> int:
+    return int(np.array([x], dtype=np.float32).view(np.uint32)[0])
+
+
+# ---- Appendix B patch ---------------------------------------------------------------------
+def _lz_distance(x, y, c=1.0):
+    u = torch.clamp(RL.minkowski_dot(x, y), min=1.0 + 1e-8)
+    return torch.acosh(u) / torch.sqrt(torch.tensor(c, device=x.device, dtype=x.dtype))
+
+
+def _lz_batch_distance(x, y, c=1.0):
+    xr, yr = x.unsqueeze(1), y.unsqueeze(0)
+    t = xr[..., 0] * yr[..., 0]
+    s = torch.sum(xr[..., 1:] * yr[..., 1:], dim=-1)
+    u = torch.clamp(t - s, min=1.0 + 1e-8)
+    return torch.acosh(u) / torch.sqrt(torch.tensor(c, device=x.device, dtype=x.dtype))
+
+
+def _lz_log_map(x, y, c=1.0):
+    m = RL.minkowski_dot(x, y)
+    u = torch.clamp(m, min=1.0 + 1e-8)
+    coef = torch.clamp(torch.acosh(u) / torch.sqrt(u * u - 1), max=1e4)
+    coef = torch.where(torch.isnan(coef) | (coef > 1e4), torch.ones_like(coef), coef)
+    return coef.unsqueeze(-1) * (y - m.unsqueeze(-1) * x)
+
+
+_PATCH = {"distance": _lz_distance, "batch_distance": _lz_batch_distance, "log_map": _lz_log_map,
+          "distance_compiled": _lz_distance, "batch_distance_compiled": _lz_batch_distance}
+
+
+@contextlib.contextmanager
+def semantics(name: str):
+    saved = []
+    if name == "lorentz":
+        for mod in (RL, RH, RF, RQ):
+            for k, fn in _PATCH.items():
+                if hasattr(mod, k):
+                    saved.append((mod, k, getattr(mod, k)))
+                    setattr(mod, k, fn)
+    try:
+        yield
+    finally:
+        for mod, k, fn in saved:
+            setattr(mod, k, fn)
+
+
+# ---- synthetic inputs --------------------------------------------------------
+def synth_words(n=2000, seed=0):
+    rng = random.Random(seed)
+    return ["".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(2, 10))) for _ in range(n)]
+
+
+def c1_vocab():
+    chars = sorted(set("".join(synth_words())))
+    return ["<pad>", "<bos>", "<eos>", "<unk>"] + chars
+
+
+def set_seeds(seed=42):
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def ref_init(n, d, scale=0.01, c=1.0):
+    """scripts/train_hyperbolic_tokenizer.py:64-109 with the 0.01 made a parameter
+    (the script itself is not importable here: it needs typer)."""
+    tangent = torch.zeros((n, d + 1), dtype=torch.float32)
+    tangent[:, 1:] = torch.randn((n, d), dtype=torch.float32) * scale
+    origin = torch.zeros(d + 1, dtype=torch.float32)
+    origin[0] = 1.0
+    emb = torch.zeros((n, d + 1), dtype=torch.float32)
+    for i, t in enumerate(tangent):
+        emb[i] = RL.exp_map(origin, t, c)
+    return RL.project_to_hyperboloid(emb, c)
+
+
+def dump(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name)
+    with open(path, "w") as f:
+        json.dump(obj, f, separators=(",", ":"))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+# ---- 1. pointwise / all-pairs known answers ---------------------------------------------------
+def gen_lorentz_ops():
+    cases = []
+    for d in (3, 5, 50, 100):
+        for scale in (0.01, 0.5):
+            for c in (1.0, 0.7):
+                set_seeds(1000 + d)
+                n = 7
+                X = ref_init(n, d, scale, c)
+                case = {"d": d, "scale": scale, "c": c, "n": n, "X": bits(X)}
+                P = torch.randn(n, d + 1)
+                case["P"] = bits(P)
+                case["project"] = bits(RL.project_to_hyperboloid(P, c))
+                case["project_row"] = bits(RL.project_to_hyperboloid(P[2], c))
+                case["mdot"] = bits(RL.minkowski_dot(X.unsqueeze(1), X.unsqueeze(0)))
+                case["mnorm"] = bits(RL.minkowski_norm(X))
+                ia = torch.tensor([0, 1, 2, 3, 4, 5, 0, 6])
+                ib = torch.tensor([1, 2, 3, 4, 5, 6, 6, 6])
+                case["ia"], case["ib"] = ia.tolist(), ib.tolist()
+                for sem in ("reference", "lorentz"):
+                    with semantics(sem):
+                        r = {}
+                        r["distance"] = bits(RL.distance(X[ia], X[ib], c))
+                        r["batch_distance"] = bits(RL.batch_distance(X, X, c))
+                        lg = RL.log_map(X[ia], X[ib], c)
+                        r["log_map"] = bits(lg)
+                        # midpoint exactly as tokenizer/hyperbolic_merge.py:323-340 (len 1 + len 3)
+                        rows = []
+                        for a, b in zip(ia.tolist(), ib.tolist()):
+                            v = RL.log_map(X[a].unsqueeze(0), X[b].unsqueeze(0), c) * (3 / (1 + 3))
+                            m = RL.exp_map(X[a].unsqueeze(0), v, c)[0]
+                            rows.append(RL.project_to_hyperboloid(m, c))
+                        r["midpoint_1_3"] = bits(torch.stack(rows))
+                        case[sem] = r
+                with semantics("lorentz"):
+                    V = RL.log_map(X[ia], X[ib], c) * 0.4
+                case["V"] = bits(V)
+                case["exp_map"] = bits(RL.exp_map(X[ia], V, c))
+                cases.append(case)
+    dump("lorentz_ops.json", {"cases": cases})
+
+
+# ---- 2. traces ----------------------------------------------------------------------------------
+def trace_of(tok, merges_before=0):
+    """(i, j) of each merge recovered from merge_history is ambiguous (duplicate strings),
+    so traces are recorded by wrapping _merge_tokens."""
+    raise NotImplementedError
+
+
+def record_merges(tok):
+    rec = []
+    orig = tok._merge_tokens
+
+    def wrapped(i, j):
+        rec.append([int(i), int(j)])
+        return orig(i, j)
+
+    tok._merge_tokens = wrapped
+    return rec
+
+
+def run_base_loop(tok, steps, script_loop=False, target=None):
+    """Either HyperbolicTokenizer.optimize_merges (hyperbolic_merge.py:357-412) or the loop of
+    scripts/train_hyperbolic_tokenizer.py:236-283 (log callback omitted), driven from outside so
+    the chosen distance and the candidate count are captured."""
+    out = []
+    for step in range(steps):
+        if script_loop and target is not None and len(tok.vocab) >= target:
+            break
+        cands = tok._find_merge_candidates()
+        if not cands:
+            break
+        ncand = len(cands)
+        cands.sort(key=lambda x: x[2])
+        i, j, d = cands[0]
+        tok._merge_tokens(i, j)
+        out.append([int(i), int(j), fbits(d), ncand])
+        if script_loop and step > 0 and step % 1000 == 0:
+            tok.merge_threshold *= 1.05
+    return out
+
+
+def tok_state(tok):
+    n = tok.current_vocab_size
+    return {"n": n, "vocab": list(tok.vocab), "merges": [list(m) for m in tok.merge_history],
+            "embeddings": bits(tok.embeddings[:n]), "merge_threshold": tok.merge_threshold}
+
+
+def gen_trace_test9():
+    """tests/test_hyperbolic_tokenizer.py:24-63 fixture (9 tokens, d=5, seed 42, thr 0.5)."""
+    out = {}
+    for sem in ("reference", "lorentz"):
+        torch.manual_seed(42)
+        vocab = ["<pad>", "<bos>", "<eos>", "<unk>", "a", "b", "c", "d", "e"]
+        d = 5
+        tangent = torch.randn((len(vocab), d), dtype=torch.float32) * 0.01
+        origin = torch.zeros(d + 1)
+        origin[0] = 1.0
+        emb = torch.zeros((len(vocab), d + 1))
+        for i, t in enumerate(tangent):
+            emb[i] = RL.exp_map(origin.unsqueeze(0), torch.cat([torch.zeros(1), t]).unsqueeze(0))[0]
+        emb = RL.project_to_hyperboloid(emb)
+        with semantics(sem):
+            tok = RH.HyperbolicTokenizer(vocab, torch.nn.Parameter(emb.clone()), curvature=1.0,
+                                         merge_threshold=0.5, lr=1e-3, device=torch.device("cpu"), max_vocab_size=64)
+            tok.merge_threshold = 10.0
+            cands = tok._find_merge_candidates()
+            tok.merge_threshold = 0.5
+            trace = run_base_loop(tok, 12)
+        out[sem] = {"init": bits(emb), "d": d, "vocab0": vocab,
+                    "candidates_thr10": [[i, j, fbits(x)] for i, j, x in cands],
+                    "trace": trace, "final": tok_state(tok)}
+    dump("trace_test9.json", out)
+
+
+def gen_trace_c1(target=330, scales=(0.01, 0.3), name="trace_c1.json", sems=("reference", "lorentz")):
+    """Config 1 generator: 30-token char vocab, d=50, thr 0.1, script loop."""
+    vocab = c1_vocab()
+    out = {"vocab0": vocab, "d": 50, "runs": []}
+    for scale in scales:
+        for sem in sems:
+            set_seeds(42)
+            emb = ref_init(len(vocab), 50, scale)
+            thr = 0.1 if scale == 0.01 else 3.0
+            with semantics(sem):
+                tok = RH.HyperbolicTokenizer(vocab, torch.nn.Parameter(emb.clone()), curvature=1.0, merge_threshold=thr,
+                                             lr=1e-3, device=torch.device("cpu"), max_vocab_size=1000)
+                trace = run_base_loop(tok, 100000, script_loop=True, target=target)
+            run = {"semantics": sem, "scale": scale, "threshold": thr, "target": target, "init": bits(emb),
+                   "trace": trace, "final": tok_state(tok)}
+            if target > 400:      # keep the big fixture small: the trace is what matters
+                run["final"].pop("embeddings")
+                run["final_embeddings_tail"] = bits(tok.embeddings[tok.current_vocab_size - 4:tok.current_vocab_size])
+            out["runs"].append(run)
+            print("c1", sem, scale, "merges", len(trace), "first", trace[:7])
+    dump(name, out)
+
+
+def gen_trace_fast():
+    """FastHyperbolicTokenizer, 300 tokens, d=16, 250 steps, no FAISS."""
+    out = {"runs": []}
+    for sem, scale, thr in (("reference", 0.01, 0.1), ("lorentz", 0.01, 0.1), ("lorentz", 0.3, 5.0)):
+        set_seeds(42)
+        vocab = [f"w{k}" for k in range(300)]
+        emb = ref_init(300, 16, scale)
+        with semantics(sem):
+            tok = RF.FastHyperbolicTokenizer(vocab, torch.nn.Parameter(emb.clone()), curvature=1.0, merge_threshold=thr,
+                                             device=torch.device("cpu"), max_vocab_size=1024,
+                                             use_approximate_search=False)
+            rec = record_merges(tok)
+            tok.optimize_merges(steps=250, log_every=1000)
+        out["runs"].append({"semantics": sem, "scale": scale, "threshold0": thr, "init": bits(emb), "d": 16,
+                            "merges_ij": rec, "final": tok_state(tok),
+                            "cache_stats": {k: (float(v) if isinstance(v, float) else v)
+                                            for k, v in tok.cache.get_stats().items()}})
+        print("fast", sem, scale, len(rec), rec[:6])
+    dump("trace_fast300.json", out)
+
+
+def synth_corpus_lines(n_lines=400, seed=7):
+    rng = random.Random(seed)
+    alpha = "abcdefghijklmnopqrstuvwxyz"
+    lines = []
+    for k in range(n_lines):
+        words = ["".join(rng.choice(alpha) for _ in range(rng.randint(1, 9))) for _ in range(rng.randint(0, 20))]
+        line = " ".join(words)
+        if k % 7 == 0:
+            line = "  \t" + line + "   "
+        if k % 11 == 0:
+            line = line + " café über naïve 中文 \U0001F600"
+        if k % 13 == 0:
+            line = ""
+        lines.append(line)
+    return lines
+
+
+def gen_pair_counts(tmpdir="/tmp"):
+    lines = synth_corpus_lines()
+    path = os.path.join(tmpdir, "hyp_golden_corpus.txt")
+    with open(path, "w", encoding="utf-8") as f:
+        f.write("\n".join(lines) + "\n")
+    vocab = c1_vocab()
+    set_seeds(42)
+    emb = ref_init(len(vocab), 8)
+    tok = RQ.FrequencyAwareHyperbolicTokenizer(vocab, torch.nn.Parameter(emb), corpus_path=path,
+                                               device=torch.device("cpu"), max_vocab_size=256)
+    counts = [[a, b, n] for (a, b), n in tok.pair_frequencies.items()]
+    dump("pair_counts.json", {"lines": lines, "counts": counts})
+
+
+def gen_trace_freq(tmpdir="/tmp"):
+    """FrequencyAwareHyperbolicTokenizer.optimize_merges (:236-313), small."""
+    lines = synth_corpus_lines(120, seed=3)
+    path = os.path.join(tmpdir, "hyp_golden_corpus2.txt")
+    with open(path, "w", encoding="utf-8") as f:
+        f.write("\n".join(lines) + "\n")
+    vocab = c1_vocab()
+    out = {"lines": lines, "vocab0": vocab, "d": 8, "runs": []}
+    for sem, scale, thr in (("reference", 0.01, 1.0), ("lorentz", 0.01, 0.03), ("lorentz", 0.3, 1.0)):
+        set_seeds(42)
+        emb = ref_init(len(vocab), 8, scale)
+        with semantics(sem):
+            tok = RQ.FrequencyAwareHyperbolicTokenizer(vocab, torch.nn.Parameter(emb.clone()), corpus_path=path,
+                                                       merge_threshold=thr, device=torch.device("cpu"),
+                                                       max_vocab_size=256)
+            rec = record_merges(tok)
+            torch.manual_seed(123)
+            scores = []
+            orig = tok._find_merge_candidates
+
+            def spy():
+                c = orig()
+                scores.append([len(c), (float(c[0][2]) if c else None)])
+                return c
+
+            tok._find_merge_candidates = spy
+            tok.optimize_merges(steps=8, log_every=10 ** 9)
+        out["runs"].append({"semantics": sem, "scale": scale, "threshold0": thr, "init": bits(emb),
+                            "merges_ij": rec, "best_neg_score": [[n, (None if s is None or s != s else s)] for n, s in scores],
+                            "final": tok_state(tok)})
+        print("freq", sem, scale, rec)
+    dump("trace_freq.json", out)
+
+
+GENS = {"lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
+        "trace_fast": gen_trace_fast, "pair_counts": gen_pair_counts, "trace_freq": gen_trace_freq}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--full-c1", action="store_true",
+                    help="also write trace_c1_full.json: config 1 at full size (30 -> 1000), slow in lorentz semantics")
+    a = ap.parse_args()
+    torch.set_num_threads(8)
+    if a.full_c1:
+        gen_trace_c1(target=1000, scales=(0.01,), name="trace_c1_full.json")
+    else:
+        for k, fn in GENS.items():
+            if a.only in (None, k):
+                fn()
