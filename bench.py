@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- merges/sec of the HypTokenizer merge loop on B200 (BASELINE.json configs[1]).
+
+Workload ("c2"): FastHyperbolicTokenizer, embedding_dim=100, V0=10 000 synthetic tokens grown to
+target_vocab_size=50 000 (40 000 merges), SURVEY.md 8d.  One "step" = one whole job: initial
+all-pairs argmin over V0 rows + 40 000 device-resident merges.
+
+  value   merges/s with the table already in HBM, C-ABI calls only, CUDA events on the launch stream
+  e2e     the same job through the public class (host embeddings in pinned memory -> H2D,
+          optimize_merges, D2H of the merge log and of embeddings[:n], host string rebuild)
+  roofline  the merge-loop kernel against measured HBM bandwidth: algorithmic bytes
+          sum_n 4*n*(d+1) over the merges of one launch / its CUDA-event duration
+  cpu_baseline  the oracle port (reference algorithm, torch CPU eager) on a bounded sample
+
+`--impl reference` times the reference's own algorithm (oracle port: the reference is pure Python
+and cannot travel to the GPU box) on the host cores.
+
+N > 1 (torchrun): the merge loop is inherently sequential and its table fits one GPU's L2, so the
+path does not shard ("replicas only"): every rank runs an independent job on its own
+seed; value = total merges of all ranks / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+V0, D_EMB, TARGET = 10000, 100, 50000
+SCALE = 0.01            # the reference's init scale (scripts/train_hyperbolic_tokenizer.py:92)
+THRESHOLD = 0.1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--semantics", default="lorentz", choices=["reference", "lorentz"])
+    ap.add_argument("--v0", type=int, default=V0)
+    ap.add_argument("--target", type=int, default=TARGET)
+    ap.add_argument("--dim", type=int, default=D_EMB)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(v0: int, merges: int, d: int) -> float:
+    """each merge reads the n current rows once: 4*n*(d+1) bytes (+ one row written)."""
+    n_sum = merges * v0 + merges * (merges - 1) // 2
+    return 4.0 * (d + 1) * (n_sum + merges)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch.distributed as dist
+    from hyptokenizer_b200 import _lib
+    from hyptokenizer_b200._lib import SEM, check, ptr
+    from hyptokenizer_b200.synth import synthetic_embeddings, synthetic_vocab
+    from hyptokenizer_b200.tokenizer.fast_hyperbolic_merge import FastHyperbolicTokenizer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    _lib.check_device(dev)
+
+    v0, d, target = a.v0, a.dim, a.target
+    merges = target - v0
+    D = d + 1
+    sem = SEM[a.semantics]
+    host_emb = synthetic_embeddings(v0, d, scale=SCALE, seed=42 + rank).pin_memory()
+    init = host_emb.to(dev)
+    E = torch.zeros((target, D), dtype=torch.float32, device=dev)
+    lens0 = torch.tensor([len(t) for t in synthetic_vocab(v0)], dtype=torch.int32)
+    lens_init = torch.zeros(target, dtype=torch.int32)
+    lens_init[:v0] = lens0
+    lens_init = lens_init.to(dev)
+    lens = torch.empty_like(lens_init)
+    ws_ap = torch.empty(L.hyp_allpairs_workspace_bytes(v0), dtype=torch.uint8, device=dev)
+    ws_lp = torch.empty(L.hyp_merge_workspace_bytes(), dtype=torch.uint8, device=dev)
+    best = torch.empty(32, dtype=torch.uint8, device=dev)
+    state = torch.empty(40, dtype=torch.uint8, device=dev)
+    log = torch.empty((merges, 4), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    thr32 = float(np.float32(THRESHOLD))
+
+    def one_step(timed):
+        # reset the table to the initial vocabulary (not part of the path; outside the events)
+        E[:v0].copy_(init)
+        E[v0:].zero_()
+        lens.copy_(lens_init)
+        flush.fill_(1)                                   # L2 flush between timed iterations
+        ev[0].record(stream)
+        check(L.hyp_allpairs_min(ptr(E), D, v0, D, 1.0, sem, thr32, ptr(best), ptr(ws_ap), ws_ap.numel(), sp))
+        check(L.hyp_merge_state_init(ptr(state), ptr(best), v0, target, THRESHOLD, sp))
+        ev[1].record(stream)
+        check(L.hyp_merge_steps(ptr(E), D, ptr(lens), D, 1.0, sem, ptr(state), ptr(log), merges, 0, 1000, 1.1,
+                                ptr(ws_lp), ws_lp.numel(), sp))
+        ev[2].record(stream)
+        if not timed:
+            return None
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[2]), ev[1].elapsed_time(ev[2])
+
+    for _ in range(a.warmup):
+        one_step(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_total, t_loop = [], []
+    for _ in range(a.steps):
+        tt, tl = one_step(True)
+        t_total.append(tt)
+        t_loop.append(tl)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    from hyptokenizer_b200._lib import HypMergeState
+    st = HypMergeState.from_buffer_copy(state.cpu().numpy().tobytes())
+    done = st.steps_done
+    ms_total = float(sum(t_total))
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    done_all = torch.tensor([done * a.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(done_all, op=dist.ReduceOp.SUM)
+    value = float(done_all.item()) / (float(tmax.item()) * 1e-3)
+
+    # ---- end to end through the public class, host buffers, copies inside the timed region ----------
+    e2e = None
+    if not a.no_e2e:
+        vocab = synthetic_vocab(v0)
+        e2e_t = []
+        for it in range(2):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            tok = FastHyperbolicTokenizer(vocab, torch.nn.Parameter(host_emb), merge_threshold=THRESHOLD,
+                                          max_vocab_size=target, device=dev, semantics=a.semantics)
+            tok.optimize_merges(steps=merges, log_every=10 ** 9, adaptive_threshold=True)
+            out = tok.embeddings[: tok.current_vocab_size].detach().cpu()
+            torch.cuda.synchronize()
+            e2e_t.append(time.perf_counter() - t0)
+            n_e2e = len(tok.last_trace)
+        te = torch.tensor([min(e2e_t)], dtype=torch.float64, device=dev)
+        ne = torch.tensor([float(n_e2e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ne, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(ne.item()) / float(te.item()), "unit": "merges/s",
+               "h2d_bytes_per_step": int(host_emb.numel() * 4 + target * 4 + 40),
+               "d2h_bytes_per_step": int(n_e2e * 16 + out.numel() * 4 + 40)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk, pk_kind = peaks()
+    loop_ms = float(np.mean(t_loop))
+    abytes = algorithmic_bytes(v0, done, d)
+    achieved = abytes / (loop_ms * 1e-3) / 1e9
+    line = {
+        "metric": "merges/sec at V=50k,d=100", "value": value, "unit": "merges/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"c2: FastHyperbolicTokenizer d={d}, V0={v0} -> target_vocab_size={target} "
+                               f"({merges} merges/step, exact device search in place of HNSW M=32/ef=100)",
+                   "semantics": a.semantics, "init_scale": SCALE, "merge_threshold": THRESHOLD,
+                   "merges_done_per_step": done, "stop_code": st.stop,
+                   "l2": "flushed between timed steps (256 MiB write); within a step the table is L2-resident by design",
+                   "parallelism": "replicas only" if world > 1 else "1 GPU"},
+        "gpu_launches": 3 * a.steps,
+        "launches_note": "per step: allpairs_tile_kernel<min>, merge_state_init_kernel, merge_loop_kernel (cooperative)",
+        "roofline": {"bound": "hbm", "kernel": "merge_loop_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                     "algorithmic_bytes_per_launch": abytes, "kernel_ms": loop_ms,
+                     "note": "table (<= 20.2 MB) is re-read from L2 every merge; frac is against HBM copy bandwidth"},
+        "clocks": clocks,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not a.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(a)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_sample(a, rows: int):
+    """One bounded sample of one reference merge step at n = V0: the reference recomputes all n x n
+    distances and extracts candidates every step (hyperbolic_merge.py:247-269); rows are independent,
+    so `rows` query rows x all n columns are timed and scaled by n/rows."""
+    from oracle import lorentz as OL
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    v0, d = a.v0, a.dim
+    emb = synthetic_embeddings(v0, d, scale=SCALE, seed=42)
+    rows = min(rows, v0)
+    t0 = time.perf_counter()
+    dist = OL.batch_distance(emb[:rows], emb, 1.0, a.semantics)
+    keep = (dist < THRESHOLD) & (torch.arange(v0)[None, :] > torch.arange(rows)[:, None])
+    ii, jj = keep.nonzero(as_tuple=True)
+    dd = dist[ii, jj]
+    if len(dd):
+        int(np.argmin(dd.numpy()))
+    dt = time.perf_counter() - t0
+    return dt * (v0 / rows), int(len(dd))
+
+
+def cpu_baseline(a, rows: int = 1024):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _cpu_sample(a, 64)
+    t, ncand = _cpu_sample(a, rows)
+    return {"value": 1.0 / t, "unit": "merges/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one brute-force merge step of the reference at n={a.v0} (all-pairs recompute + candidate "
+                      f"extraction, vectorised), {rows} of {a.v0} query rows timed and scaled by n/rows; the "
+                      f"reference itself cannot run this size (n^2*d*4 B = {a.v0 ** 2 * a.dim * 4 / 1e9:.0f} GB temporary)"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rows = 1024
+    for _ in range(a.warmup):
+        _cpu_sample(a, rows)
+    ts = []
+    for _ in range(a.steps):
+        t, _ = _cpu_sample(a, rows)
+        ts.append(t)
+    value = len(ts) / sum(ts)
+    sample = (f"each step = one brute-force merge step of the reference algorithm at n={a.v0}, d={a.dim} "
+              f"({rows} of {a.v0} query rows timed, scaled by n/rows); oracle port, torch CPU eager fp32")
+    line = {"impl": "reference", "metric": "merges/sec at V=50k,d=100", "value": value, "unit": "merges/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"c2: d={a.dim}, V0={a.v0} -> {a.target}", "semantics": a.semantics,
+                       "note": "per-step cost grows as n^2; n=V0 is the CHEAPEST step of the job, so this flatters the reference"},
+            "cpu_baseline": {"value": value, "unit": "merges/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -1,0 +1,361 @@
+// allpairs.cu -- K2, exact fp32 path: all-pairs Lorentz distance on CUDA cores (sm_100a).
+//
+// Replaces embedding/lorentz_model.py:141-178 (`batch_distance`, which materialises an
+// (n, n, d) temporary) and the candidate scan of tokenizer/hyperbolic_merge.py:247-269.
+// The Minkowski product of every pair is accumulated in ATen's CPU order (SURVEY.md
+// Appendix D) with separately rounded products, so it is bit-identical to the reference;
+// that is why this path runs on the FP32 pipe and not on tensor cores (the tcgen05 Gram
+// kernel in gram_tc.cu trades that for speed and re-scores its finalists here).
+//
+// Tiling: 64x64 pairs per CTA, 256 threads, 4x4 pairs per thread; both operand tiles are
+// staged TRANSPOSED in shared memory ([k][row], 16-byte aligned rows) so each k costs two
+// LDS.128 per 16 products.  Persistent CTAs walk the (upper-triangular) tile list.
+// Compiled with -fmad=false.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace hyp {
+
+constexpr int TM = 64, TN = 64, TPAD = 68, NTHREADS = 256;
+constexpr int kMaxBlocks = 148 * 8;
+
+enum Mode { kDense = 0, kMin = 1, kEmit = 2 };
+
+struct MinWorkspace {
+  unsigned int ticket;
+  unsigned int pad0;
+  unsigned long long count;
+  Key block_best[kMaxBlocks];
+};
+
+struct Params {
+  const float *x;
+  int64_t ldx;
+  int64_t n1;
+  const float *y;
+  int64_t ldy;
+  int64_t n2;
+  int D;
+  float sqrt_c, sgn, thr;
+  // dense
+  float *out;
+  int64_t ldo;
+  // min
+  MinWorkspace *ws;
+  hyp_best *best;
+  // emit
+  int32_t *out_i, *out_j;
+  float *out_d;
+  int64_t capacity;
+  unsigned long long *emit_count;
+  // tiles
+  int64_t tiles_m, tiles_n, n_tiles;
+  int triangular;
+};
+
+__device__ __forceinline__ void tile_coords(const Params &p, int64_t t, int64_t &tm, int64_t &tn) {
+  if (!p.triangular) {
+    tm = t / p.tiles_n;
+    tn = t - tm * p.tiles_n;
+    return;
+  }
+  // t enumerates (tm, tn) with tn >= tm, row-major
+  const double T = (double)p.tiles_m;
+  double b = 2.0 * T + 1.0;
+  int64_t r = (int64_t)floor((b - sqrt(b * b - 8.0 * (double)t)) * 0.5);
+  if (r < 0) r = 0;
+  if (r >= p.tiles_m) r = p.tiles_m - 1;
+  auto start = [&](int64_t q) { return q * p.tiles_m - q * (q - 1) / 2; };
+  while (r > 0 && start(r) > t) --r;
+  while (r + 1 < p.tiles_m && start(r + 1) <= t) ++r;
+  tm = r;
+  tn = r + (t - start(r));
+}
+
+// Load rows [r0, r0+64) of a row-major table into a transposed tile: T[k][r], k = spatial index.
+__device__ __forceinline__ void load_tile_T(const float *__restrict__ src, int64_t ld, int64_t n, int64_t r0,
+                                            int d, float *__restrict__ T, float *__restrict__ t0) {
+  // a warp reads one row's contiguous floats (coalesced); 8 warps -> 8 rows per pass
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int r = w; r < TM; r += NTHREADS / 32) {
+    const int64_t gr = r0 + r;
+    const bool ok = gr < n;
+    const float *row = src + (ok ? gr : 0) * ld;
+    for (int k = lane; k < d; k += 32) T[k * TPAD + r] = ok ? row[1 + k] : 0.f;
+    if (lane == 0) t0[r] = ok ? row[0] : 0.f;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS) allpairs_tile_kernel(const Params p) {
+  extern __shared__ __align__(16) float smem[];
+  const int d = p.D - 1;
+  float *As = smem;                 // [d][TPAD]
+  float *Bs = As + (size_t)d * TPAD;  // [d][TPAD]
+  float *a0 = Bs + (size_t)d * TPAD;  // [64]
+  float *b0 = a0 + TM;              // [64]
+  __shared__ Key s_keys[NTHREADS / 32];
+  __shared__ unsigned long long s_cnt[NTHREADS / 32];
+  __shared__ int s_last;
+
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Key best = key_none();
+  unsigned long long below = 0;
+
+  for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    int64_t tm, tn;
+    tile_coords(p, t, tm, tn);
+    const int64_t i0 = tm * TM, j0 = tn * TN;
+    __syncthreads();  // previous tile fully consumed
+    load_tile_T(p.x, p.ldx, p.n1, i0, d, As, a0);
+    load_tile_T(p.y, p.ldy, p.n2, j0, d, Bs, b0);
+    __syncthreads();
+
+    float S[4][4];
+    if (d >= 8) {
+      const int vs = d >> 3, full = vs >> 2;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) S[r][c] = 0.f;
+      // scalar tail first (from zero), then lanes 0..7 in order
+      for (int e = 8 * vs; e < d; ++e) {
+        const float4 a = *reinterpret_cast<const float4 *>(As + e * TPAD + 4 * ty);
+        const float4 b = *reinterpret_cast<const float4 *>(Bs + e * TPAD + 4 * tx);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) S[r][c] = __fadd_rn(S[r][c], __fmul_rn(av[r], bv[c]));
+      }
+      for (int l = 0; l < 8; ++l) {
+        float L[4][4];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          float P[4][4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) P[r][c] = 0.f;
+          auto step = [&](int e) {
+            const float4 a = *reinterpret_cast<const float4 *>(As + e * TPAD + 4 * ty);
+            const float4 b = *reinterpret_cast<const float4 *>(Bs + e * TPAD + 4 * tx);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) P[r][c] = __fadd_rn(P[r][c], __fmul_rn(av[r], bv[c]));
+          };
+          for (int r = 0; r < full; ++r) step(32 * r + 8 * c4 + l);
+          if (c4 == 0)
+            for (int k = 4 * full; k < vs; ++k) step(8 * k + l);
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) L[r][c] = (c4 == 0) ? P[r][c] : __fadd_rn(L[r][c], P[r][c]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) S[r][c] = __fadd_rn(S[r][c], L[r][c]);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          S[r][c] = thread_sum_aten(
+              [&](int e) { return __fmul_rn(As[e * TPAD + 4 * ty + r], Bs[e * TPAD + 4 * tx + c]); }, d);
+    }
+
+    // epilogue: m = fl(fl(x0*y0) - S), distance, then the mode's consumer
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t gi = i0 + 4 * ty + r;
+      float dist[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float m = __fsub_rn(__fmul_rn(a0[4 * ty + r], b0[4 * tx + c]), S[r][c]);
+        dist[c] = dist_from_mdot(m, p.sgn, p.sqrt_c);
+      }
+      if (MODE == kDense) {
+        if (gi < p.n1) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int64_t gj = j0 + 4 * tx + c;
+            if (gj < p.n2) p.out[gi * p.ldo + gj] = dist[c];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int64_t gj = j0 + 4 * tx + c;
+          if (gi < gj && gj < p.n2 && gi < p.n1 && dist[c] == dist[c]) {
+            if (MODE == kMin) {
+              if (dist[c] < p.thr) ++below;
+              Key k{dist[c], (int)gi, (int)gj};
+              if (key_less(k, best)) best = k;
+            } else if (dist[c] < p.thr) {
+              unsigned long long pos = atomicAdd(p.emit_count, 1ULL);
+              if ((int64_t)pos < p.capacity) {
+                p.out_i[pos] = (int)gi;
+                p.out_j[pos] = (int)gj;
+                p.out_d[pos] = dist[c];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  if (MODE == kMin) {
+    best = warp_key_min(best);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(HYP_FULL_MASK, below, o);
+    if (lane == 0) {
+      s_keys[warp] = best;
+      s_cnt[warp] = below;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      Key b = s_keys[0];
+      unsigned long long cnt = s_cnt[0];
+      for (int w = 1; w < NTHREADS / 32; ++w) {
+        if (key_less(s_keys[w], b)) b = s_keys[w];
+        cnt += s_cnt[w];
+      }
+      p.ws->block_best[blockIdx.x] = b;
+      if (cnt) atomicAdd(&p.ws->count, cnt);
+      __threadfence();
+      unsigned int tk = atomicAdd(&p.ws->ticket, 1u);
+      s_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      Key b = key_none();
+      for (int q = threadIdx.x; q < (int)gridDim.x; q += NTHREADS) {
+        Key k = p.ws->block_best[q];
+        if (key_less(k, b)) b = k;
+      }
+      b = warp_key_min(b);
+      if (lane == 0) s_keys[warp] = b;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        Key r = s_keys[0];
+        for (int w = 1; w < NTHREADS / 32; ++w)
+          if (key_less(s_keys[w], r)) r = s_keys[w];
+        unsigned long long cnt = *((volatile unsigned long long *)&p.ws->count);
+        hyp_best o;
+        o.d = r.i < 0 ? __int_as_float(0x7f800000) : r.d;
+        o.i = r.i;
+        o.j = r.j;
+        o.count_lo = (uint32_t)(cnt & 0xffffffffu);
+        o.count_hi = (uint32_t)(cnt >> 32);
+        o.pad[0] = o.pad[1] = o.pad[2] = 0;
+        *p.best = o;
+      }
+    }
+  }
+}
+
+static size_t tile_smem_bytes(int D) { return ((size_t)2 * (D - 1) * TPAD + TM + TN) * sizeof(float); }
+
+template <int MODE>
+static int launch_tiles(Params &p, cudaStream_t st, const char *what) {
+  const size_t smem = tile_smem_bytes(p.D);
+  if (smem > 200 * 1024) {
+    set_error("%s: D=%d needs %zu bytes of shared memory per CTA (max 200 KiB => D <= 368)", what, p.D, smem);
+    return HYP_ERR_ARG;
+  }
+  cudaError_t e = cudaFuncSetAttribute(allpairs_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    return HYP_ERR_CUDA;
+  }
+  int per_sm = 0, dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, allpairs_tile_kernel<MODE>, NTHREADS, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)sms * per_sm;
+  if (grid > kMaxBlocks) grid = kMaxBlocks;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  if (grid < 1) grid = 1;
+  allpairs_tile_kernel<MODE><<<(int)grid, NTHREADS, smem, st>>>(p);
+  return check_launch(what);
+}
+
+static int fill_params(Params &p, const float *x, int64_t ldx, int64_t n1, const float *y, int64_t ldy, int64_t n2,
+                       int D, float c, int semantics, int triangular) {
+  if (!x || !y || n1 < 0 || n2 < 0 || D < 2 || D > HYP_MAX_D || !(c > 0.f)) {
+    set_error("all-pairs: bad arguments (n1=%lld n2=%lld D=%d c=%g)", (long long)n1, (long long)n2, D, c);
+    return HYP_ERR_ARG;
+  }
+  p = Params{};
+  p.x = x; p.ldx = ldx; p.n1 = n1; p.y = y; p.ldy = ldy; p.n2 = n2; p.D = D;
+  p.sqrt_c = sqrtf(c);
+  p.sgn = semantics == HYP_SEM_REFERENCE ? -1.f : 1.f;
+  p.tiles_m = (n1 + TM - 1) / TM;
+  p.tiles_n = (n2 + TN - 1) / TN;
+  p.triangular = triangular;
+  p.n_tiles = triangular ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
+  return HYP_OK;
+}
+
+}  // namespace hyp
+
+using namespace hyp;
+
+extern "C" int hyp_batch_distance(const float *x, int64_t ldx, int64_t n1, const float *y, int64_t ldy, int64_t n2,
+                                  float *out, int64_t ldo, int D, float c, int semantics, void *stream) {
+  Params p;
+  int rc = fill_params(p, x, ldx, n1, y, ldy, n2, D, c, semantics, 0);
+  if (rc) return rc;
+  if (!out) return HYP_ERR_ARG;
+  if (n1 == 0 || n2 == 0) return HYP_OK;
+  p.out = out;
+  p.ldo = ldo;
+  return launch_tiles<kDense>(p, (cudaStream_t)stream, "hyp_batch_distance");
+}
+
+extern "C" int64_t hyp_allpairs_workspace_bytes(int64_t) { return (int64_t)sizeof(MinWorkspace); }
+
+extern "C" int hyp_allpairs_min(const float *E, int64_t ldE, int64_t n, int D, float c, int semantics, float threshold,
+                                hyp_best *best, void *workspace, int64_t workspace_bytes, void *stream) {
+  Params p;
+  int rc = fill_params(p, E, ldE, n, E, ldE, n, D, c, semantics, 1);
+  if (rc) return rc;
+  if (!best || !workspace) return HYP_ERR_ARG;
+  if (workspace_bytes < (int64_t)sizeof(MinWorkspace)) {
+    set_error("hyp_allpairs_min: workspace %lld < %zu bytes", (long long)workspace_bytes, sizeof(MinWorkspace));
+    return HYP_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(workspace, 0, 16, st);
+  p.ws = (MinWorkspace *)workspace;
+  p.best = best;
+  p.thr = threshold;
+  return launch_tiles<kMin>(p, st, "hyp_allpairs_min");
+}
+
+extern "C" int hyp_allpairs_emit(const float *E, int64_t ldE, int64_t n, int D, float c, int semantics, float threshold,
+                                 int32_t *out_i, int32_t *out_j, float *out_d, int64_t capacity,
+                                 unsigned long long *count, void *stream) {
+  Params p;
+  int rc = fill_params(p, E, ldE, n, E, ldE, n, D, c, semantics, 1);
+  if (rc) return rc;
+  if (!count || capacity < 0 || (capacity > 0 && (!out_i || !out_j || !out_d))) return HYP_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(count, 0, sizeof(unsigned long long), st);
+  if (n < 2) return HYP_OK;
+  p.thr = threshold;
+  p.out_i = out_i; p.out_j = out_j; p.out_d = out_d;
+  p.capacity = capacity;
+  p.emit_count = count;
+  return launch_tiles<kEmit>(p, st, "hyp_allpairs_emit");
+}

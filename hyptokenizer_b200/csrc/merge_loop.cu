@@ -1,0 +1,416 @@
+// merge_loop.cu -- K4 (one row against the table) and K5 (device-resident merge loop), sm_100a.
+//
+// Replaces the per-step "recompute all pairs, build a Python list, sort, take [0], merge" of
+// tokenizer/hyperbolic_merge.py:357-412, scripts/train_hyperbolic_tokenizer.py:236-283 and
+// tokenizer/fast_hyperbolic_merge.py:467-576 (whose HNSW index and AdaptiveMergeCache exist only
+// to make that affordable).  The reference never removes a merged pair and never changes an
+// existing row, so after appending row n:
+//     argmin_{i<j<=n} (d,i,j) = min( argmin_{i<j<n} (d,i,j) , argmin_{i<n} (d(i,n), i, n) )
+// i.e. one new row scored against the table (HBM/L2-bound GEMV + min) per merge.
+//
+// K5 is ONE cooperative launch for up to max_steps merges: every CTA recomputes the (tiny)
+// midpoint row redundantly and bit-identically, CTA 0 appends it, all CTAs scan their share of
+// rows, one grid barrier, every CTA reduces the per-CTA minima to the same new state.
+// Compiled with -fmad=false.
+#include "common.cuh"
+
+namespace hyp {
+
+constexpr int kLoopThreads = 512;
+constexpr int kLoopWarps = kLoopThreads / 32;
+constexpr int kMaxLoopBlocks = 148 * 4;
+constexpr int kRowsPerIter = 4;  // rows a warp keeps in flight (independent reduction chains)
+
+struct LoopWorkspace {
+  unsigned int barrier;  // monotonically increasing arrival counter
+  unsigned int ticket;   // hyp_row_min: last-block-done
+  unsigned int pad[30];
+  Key slot[2][kMaxLoopBlocks];  // per-CTA minima, double-buffered by step parity
+  unsigned long long below[kMaxLoopBlocks];
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned int *p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// All CTAs of a cooperative launch (co-resident by construction).
+__device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    red_release_add_u32(ctr, 1u);
+    while (ld_acquire_u32(ctr) < target) {
+    }
+  }
+  __syncthreads();
+}
+
+// Score table rows against `q` (D floats in shared memory): R rows per warp iteration.
+// Table reads bypass L1 (ld.global.cg): rows appended by another CTA share cache lines with
+// rows this SM has already read.
+template <int R>
+__device__ __forceinline__ void warp_mdot_rows(const float *__restrict__ E, int64_t ldE, const int64_t *rows,
+                                               int nrows, const float *__restrict__ q, int D, int lane,
+                                               float *m_out) {
+  const int N = D - 1;
+  const float *qs = q + 1;
+  if (N < 8) {
+    for (int a = 0; a < R; ++a) {
+      if (a >= nrows) break;
+      const float *xs = E + rows[a] * ldE + 1;
+      float s = thread_sum_aten([&](int e) { return __fmul_rn(__ldcg(xs + e), qs[e]); }, N);
+      m_out[a] = __fsub_rn(__fmul_rn(__ldcg(xs - 1), q[0]), s);
+    }
+    return;
+  }
+  const int vs = N >> 3, full = vs >> 2;
+  const int c = lane >> 3, l = lane & 7;
+  float P[R], acc[R], x0[R];
+  const float *xs[R];
+#pragma unroll
+  for (int a = 0; a < R; ++a) {
+    xs[a] = E + rows[a < nrows ? a : 0] * ldE + 1;
+    P[a] = 0.f;
+    acc[a] = 0.f;
+  }
+  for (int r = 0; r < full; ++r) {
+    const int e = 32 * r + lane;
+    const float qe = qs[e];
+#pragma unroll
+    for (int a = 0; a < R; ++a) P[a] = __fadd_rn(P[a], __fmul_rn(__ldcg(xs[a] + e), qe));
+  }
+  if (c == 0)
+    for (int k = 4 * full; k < vs; ++k) {
+      const int e = 8 * k + l;
+      const float qe = qs[e];
+#pragma unroll
+      for (int a = 0; a < R; ++a) P[a] = __fadd_rn(P[a], __fmul_rn(__ldcg(xs[a] + e), qe));
+    }
+  for (int k = 8 * vs; k < N; ++k) {
+    const float qe = qs[k];
+#pragma unroll
+    for (int a = 0; a < R; ++a) acc[a] = __fadd_rn(acc[a], __fmul_rn(__ldcg(xs[a] + k), qe));
+  }
+#pragma unroll
+  for (int a = 0; a < R; ++a) x0[a] = __ldcg(xs[a] - 1);
+#pragma unroll
+  for (int a = 0; a < R; ++a) {
+    float p1 = __shfl_down_sync(HYP_FULL_MASK, P[a], 8);
+    float p2 = __shfl_down_sync(HYP_FULL_MASK, P[a], 16);
+    float p3 = __shfl_down_sync(HYP_FULL_MASK, P[a], 24);
+    P[a] = __fadd_rn(__fadd_rn(__fadd_rn(P[a], p1), p2), p3);
+  }
+#pragma unroll
+  for (int qn = 0; qn < 8; ++qn)
+#pragma unroll
+    for (int a = 0; a < R; ++a) acc[a] = __fadd_rn(acc[a], __shfl_sync(HYP_FULL_MASK, P[a], qn));
+#pragma unroll
+  for (int a = 0; a < R; ++a) m_out[a] = __fsub_rn(__fmul_rn(x0[a], q[0]), acc[a]);
+}
+
+// Scan rows [0, n) strided over all warps of the grid; returns this CTA's min key (thread 0).
+__device__ __forceinline__ Key block_scan_rows(const float *__restrict__ E, int64_t ldE, int n, int row_new,
+                                               const float *q, int D, float sqrt_c, float sgn, float thr_f,
+                                               double thr_d, bool cmp_double, unsigned long long *below_out,
+                                               Key *s_keys, unsigned long long *s_cnt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t total_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  Key best = key_none();
+  unsigned long long below = 0;
+  for (int64_t base = gw * kRowsPerIter; base < n; base += total_warps * kRowsPerIter) {
+    int64_t rows[kRowsPerIter];
+    int nrows = 0;
+#pragma unroll
+    for (int a = 0; a < kRowsPerIter; ++a) {
+      rows[a] = base + a;
+      if (base + a < n) nrows = a + 1;
+    }
+    float m[kRowsPerIter];
+    warp_mdot_rows<kRowsPerIter>(E, ldE, rows, nrows, q, D, lane, m);
+#pragma unroll
+    for (int a = 0; a < kRowsPerIter; ++a) {
+      if (a < nrows && rows[a] != row_new) {
+        float d = dist_from_mdot(m[a], sgn, sqrt_c);
+        if (d == d) {
+          bool lt = cmp_double ? ((double)d < thr_d) : (d < thr_f);
+          if (lt) ++below;
+          int lo = rows[a] < row_new ? (int)rows[a] : row_new;
+          int hi = rows[a] < row_new ? row_new : (int)rows[a];
+          Key k{d, lo, hi};
+          if (key_less(k, best)) best = k;
+        }
+      }
+    }
+  }
+  // every lane of a warp holds the same `best`; combine across warps
+  if (lane == 0) {
+    s_keys[warp] = best;
+    s_cnt[warp] = below;
+  }
+  __syncthreads();
+  Key b = key_none();
+  if (threadIdx.x == 0) {
+    unsigned long long cnt = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      if (key_less(s_keys[w], b)) b = s_keys[w];
+      cnt += s_cnt[w];
+    }
+    *below_out = cnt;
+  }
+  __syncthreads();
+  return b;
+}
+
+__global__ void __launch_bounds__(kLoopThreads)
+row_min_kernel(const float *__restrict__ E, int64_t ldE, int n, int row, int D, float sqrt_c, float sgn,
+               float thr, LoopWorkspace *ws, hyp_best *out) {
+  extern __shared__ float smem[];
+  __shared__ Key s_keys[kLoopWarps];
+  __shared__ unsigned long long s_cnt[kLoopWarps];
+  __shared__ int s_last;
+  float *q = smem;
+  for (int k = threadIdx.x; k < D; k += blockDim.x) q[k] = __ldcg(E + (int64_t)row * ldE + k);
+  __syncthreads();
+  unsigned long long below = 0;
+  Key b = block_scan_rows(E, ldE, n, row, q, D, sqrt_c, sgn, thr, (double)thr, false, &below, s_keys, s_cnt);
+  if (threadIdx.x == 0) {
+    ws->slot[0][blockIdx.x] = b;
+    ws->below[blockIdx.x] = below;
+    __threadfence();
+    s_last = (atomicAdd(&ws->ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    Key r = key_none();
+    unsigned long long cnt = 0;
+    for (int q2 = 0; q2 < (int)gridDim.x; ++q2) {
+      Key k;
+      k.d = __ldcg(&ws->slot[0][q2].d);
+      k.i = __ldcg(&ws->slot[0][q2].i);
+      k.j = __ldcg(&ws->slot[0][q2].j);
+      if (key_less(k, r)) r = k;
+      cnt += __ldcg(&ws->below[q2]);
+    }
+    hyp_best o;
+    o.d = r.i < 0 ? __int_as_float(0x7f800000) : r.d;
+    o.i = r.i;
+    o.j = r.j;
+    o.count_lo = (uint32_t)(cnt & 0xffffffffu);
+    o.count_hi = (uint32_t)(cnt >> 32);
+    o.pad[0] = o.pad[1] = o.pad[2] = 0;
+    *out = o;
+    ws->ticket = 0;
+  }
+}
+
+struct LoopParams {
+  float *E;
+  int64_t ldE;
+  int32_t *len;
+  int D;
+  float c, sqrt_c, sgn;
+  int semantics;
+  hyp_merge_state *state;
+  hyp_merge_record *log;
+  int max_steps, step0, thr_every;
+  double thr_mul;
+  LoopWorkspace *ws;
+};
+
+__global__ void __launch_bounds__(kLoopThreads) merge_loop_kernel(const LoopParams p) {
+  extern __shared__ float smem[];
+  const int D = p.D;
+  float *q = smem;           // [D] new row
+  float *xi = q + D;         // [D]
+  float *xj = xi + D;        // [D]
+  float *scratch = xj + D;   // [2D]
+  __shared__ Key s_keys[kLoopWarps];
+  __shared__ unsigned long long s_cnt[kLoopWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // replicated loop state (identical in every CTA)
+  int n = p.state->n;
+  const int cap = p.state->capacity;
+  Key best{p.state->best_d, p.state->best_i, p.state->best_j};
+  double thr = p.state->threshold;
+  int done = 0, stop = 0;
+  unsigned int arrivals = 0;
+
+  for (int k = 0; k < p.max_steps; ++k) {
+    const bool cmp_double = n <= 100;  // hyperbolic_merge.py:247 vs :270 (tensor `<` vs Python float `<`)
+    const bool have = best.i >= 0 && (cmp_double ? ((double)best.d < thr) : (best.d < (float)thr));
+    if (!have) { stop = 1; break; }
+    if (n >= cap) { stop = 2; break; }
+
+    // ---- midpoint row (hyperbolic_merge.py:317-340), redundantly in every CTA -------------
+    for (int e = threadIdx.x; e < D; e += blockDim.x) {
+      xi[e] = __ldcg(p.E + (int64_t)best.i * p.ldE + e);
+      xj[e] = __ldcg(p.E + (int64_t)best.j * p.ldE + e);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int li = __ldcg(p.len + best.i), lj = __ldcg(p.len + best.j);
+      warp_midpoint(xi, xj, li, lj, D, p.c, p.semantics, true, scratch, lane,
+                    [&](int e, float v) { q[e] = v; });
+      if (blockIdx.x == 0) {
+        __syncwarp();
+        for (int e = lane; e < D; e += 32) p.E[(int64_t)n * p.ldE + e] = q[e];
+        if (lane == 0) {
+          p.len[n] = li + lj;
+          p.log[k] = hyp_merge_record{best.i, best.j, best.d, n};
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- score row n against rows 0..n-1 ------------------------------------------------------
+    unsigned long long below = 0;
+    const float thr_f = (float)thr;
+    Key b = block_scan_rows(p.E, p.ldE, n, n, q, D, p.sqrt_c, p.sgn, thr_f, thr, cmp_double, &below, s_keys, s_cnt);
+    const int par = k & 1;
+    if (threadIdx.x == 0) p.ws->slot[par][blockIdx.x] = b;
+    arrivals += gridDim.x;
+    grid_barrier(&p.ws->barrier, arrivals);
+
+    // ---- every CTA folds the per-CTA minima into the same new state ------------------------------
+    Key r = key_none();
+    for (int t = threadIdx.x; t < (int)gridDim.x; t += blockDim.x) {
+      Key kk;
+      const Key *src = &p.ws->slot[par][t];
+      kk.d = __ldcg(&src->d);
+      kk.i = __ldcg(&src->i);
+      kk.j = __ldcg(&src->j);
+      if (key_less(kk, r)) r = kk;
+    }
+    r = warp_key_min(r);
+    if (lane == 0) s_keys[warp] = r;
+    __syncthreads();
+    r = s_keys[0];
+    for (int w = 1; w < kLoopWarps; ++w)
+      if (key_less(s_keys[w], r)) r = s_keys[w];
+    __syncthreads();
+    if (key_less(r, best)) best = r;
+    ++n;
+    ++done;
+    const int step = p.step0 + k;
+    if (p.thr_every > 0 && step > 0 && step % p.thr_every == 0) thr *= p.thr_mul;
+  }
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.state->n = n;
+    p.state->best_d = best.d;
+    p.state->best_i = best.i;
+    p.state->best_j = best.j;
+    p.state->threshold = thr;
+    p.state->steps_done = done;
+    p.state->stop = stop;
+  }
+}
+
+__global__ void merge_state_init_kernel(hyp_merge_state *st, const hyp_best *best, int n, int capacity, double thr) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->threshold = thr;
+    st->n = n;
+    st->capacity = capacity;
+    st->best_d = best->d;
+    st->best_i = best->i;
+    st->best_j = best->j;
+    st->steps_done = 0;
+    st->stop = 0;
+    st->pad = 0;
+  }
+}
+
+static int loop_grid(size_t smem, int *blocks_out) {
+  int dev = 0, sms = 148, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_loop_kernel, kLoopThreads, smem);
+  if (per_sm < 1) {
+    set_error("merge loop: kernel does not fit on an SM (smem=%zu)", smem);
+    return HYP_ERR_CUDA;
+  }
+  if (per_sm > 2) per_sm = 2;
+  int g = sms * per_sm;
+  if (g > kMaxLoopBlocks) g = kMaxLoopBlocks;
+  *blocks_out = g;
+  return HYP_OK;
+}
+
+}  // namespace hyp
+
+using namespace hyp;
+
+extern "C" int64_t hyp_merge_workspace_bytes(void) { return (int64_t)sizeof(LoopWorkspace); }
+
+extern "C" int hyp_merge_state_init(hyp_merge_state *state, const hyp_best *best, int32_t n, int32_t capacity,
+                                    double threshold, void *stream) {
+  if (!state || !best || n < 0 || capacity < n) {
+    set_error("hyp_merge_state_init: bad arguments");
+    return HYP_ERR_ARG;
+  }
+  merge_state_init_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, best, n, capacity, threshold);
+  return check_launch("hyp_merge_state_init");
+}
+
+extern "C" int hyp_row_min(const float *E, int64_t ldE, int64_t n, int64_t row, int D, float c, int semantics,
+                           float threshold, hyp_best *best, void *workspace, int64_t workspace_bytes,
+                           void *stream) {
+  if (!E || !best || !workspace || n < 0 || row < 0 || D < 2 || D > HYP_MAX_D || !(c > 0.f)) {
+    set_error("hyp_row_min: bad arguments");
+    return HYP_ERR_ARG;
+  }
+  if (workspace_bytes < (int64_t)sizeof(LoopWorkspace)) {
+    set_error("hyp_row_min: workspace %lld < %zu bytes", (long long)workspace_bytes, sizeof(LoopWorkspace));
+    return HYP_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(workspace, 0, 128, st);
+  int64_t want = (n + (int64_t)kLoopWarps * kRowsPerIter - 1) / ((int64_t)kLoopWarps * kRowsPerIter);
+  int grid = (int)(want < 1 ? 1 : (want > kMaxLoopBlocks ? kMaxLoopBlocks : want));
+  row_min_kernel<<<grid, kLoopThreads, (size_t)D * sizeof(float), st>>>(
+      E, ldE, (int)n, (int)row, D, sqrtf(c), semantics == HYP_SEM_REFERENCE ? -1.f : 1.f, threshold,
+      (LoopWorkspace *)workspace, best);
+  return check_launch("hyp_row_min");
+}
+
+extern "C" int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float c, int semantics,
+                               hyp_merge_state *state, hyp_merge_record *log, int32_t max_steps, int32_t step0,
+                               int32_t threshold_every, double threshold_mul, void *workspace,
+                               int64_t workspace_bytes, void *stream) {
+  if (!E || !len || !state || !log || !workspace || D < 2 || D > HYP_MAX_D || max_steps < 0 || !(c > 0.f)) {
+    set_error("hyp_merge_steps: bad arguments");
+    return HYP_ERR_ARG;
+  }
+  if (workspace_bytes < (int64_t)sizeof(LoopWorkspace)) {
+    set_error("hyp_merge_steps: workspace %lld < %zu bytes", (long long)workspace_bytes, sizeof(LoopWorkspace));
+    return HYP_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  LoopParams p;
+  p.E = E; p.ldE = ldE; p.len = len; p.D = D; p.c = c; p.sqrt_c = sqrtf(c);
+  p.sgn = semantics == HYP_SEM_REFERENCE ? -1.f : 1.f;
+  p.semantics = semantics;
+  p.state = state; p.log = log; p.max_steps = max_steps; p.step0 = step0;
+  p.thr_every = threshold_every; p.thr_mul = threshold_mul;
+  p.ws = (LoopWorkspace *)workspace;
+  const size_t smem = (size_t)5 * D * sizeof(float);
+  int grid = 0;
+  int rc = loop_grid(smem, &grid);
+  if (rc) return rc;
+  cudaMemsetAsync(workspace, 0, 128, st);
+  void *args[] = {(void *)&p};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void *)merge_loop_kernel, dim3(grid), dim3(kLoopThreads), args,
+                                              smem, st);
+  if (e != cudaSuccess) {
+    set_error("hyp_merge_steps: cooperative launch failed: %s", cudaGetErrorString(e));
+    return HYP_ERR_CUDA;
+  }
+  return check_launch("hyp_merge_steps");
+}

@@ -1,0 +1,175 @@
+/*
+ * hyptok_b200.h -- C ABI of the B200 (sm_100a) merge-loop hot path of HypTokenizer.
+ *
+ * The reference (sangaprabhav/HypTokenizer) is pure Python on torch tensors and has no
+ * FFI of its own; the boundary it offers is the Python API of embedding/lorentz_model.py
+ * and tokenizer/{hyperbolic_merge,fast_hyperbolic_merge,frequency_aware_hyperbolic_merge}.py.
+ * This library is what sits UNDER that API: every entry point names the reference
+ * function(s) it replaces.  INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller unless marked `host`
+ *   - no hidden allocation: workspaces are passed in, sizes come from *_workspace_bytes()
+ *   - `stream` is a cudaStream_t passed as void*; every call is stream-ordered, none syncs
+ *   - return value: HYP_OK or a negative HYP_ERR_*; hyp_last_error() gives the text
+ *   - fp32 everywhere; rows are D = d+1 floats (time component first), `ld*` are in floats
+ *   - `semantics`: HYP_SEM_REFERENCE = the shipped arithmetic (negated product, 0*NaN mask),
+ *                  HYP_SEM_LORENTZ   = corrected geometry
+ *   - arithmetic on the pre-clamp Minkowski product follows ATen's CPU summation order
+ *     (SURVEY.md Appendix D), so it is bit-identical to the reference's torch CPU value
+ */
+#ifndef HYPTOK_B200_H
+#define HYPTOK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYP_ABI_VERSION 1
+
+#define HYP_OK 0
+#define HYP_ERR_ARG (-1)         /* bad argument (NULL, negative size, unsupported D)          */
+#define HYP_ERR_CUDA (-2)        /* CUDA runtime / driver error, see hyp_last_error()           */
+#define HYP_ERR_FULL (-3)        /* vocabulary table full: reference raises ValueError          */
+#define HYP_ERR_UNSUPPORTED (-4) /* device is not sm_100 or a feature is unavailable            */
+#define HYP_ERR_WORKSPACE (-5)   /* workspace too small                                         */
+
+#define HYP_SEM_REFERENCE 0
+#define HYP_SEM_LORENTZ 1
+
+#define HYP_MAX_D 1025 /* largest supported row length D = d+1 */
+
+int hyp_abi_version(void);
+const char *hyp_last_error(void);
+/* 0 if the current device is compute capability 10.x, HYP_ERR_UNSUPPORTED otherwise. */
+int hyp_check_device(void);
+
+/* ---- K1: fused pointwise Lorentz ops (embedding/lorentz_model.py) ----------------------
+ * n independent row pairs.  Operand r of x is at x + r*ldx (ldx == 0 broadcasts one row). */
+
+/* minkowski_dot, lorentz_model.py:14-25.  out[n] */
+int hyp_minkowski_dot(const float *x, int64_t ldx, const float *y, int64_t ldy, float *out,
+                      int64_t n, int D, void *stream);
+/* distance, lorentz_model.py:122-138: acosh(clamp(sgn*<x,y>, 1.0f)) / sqrt(c).  out[n] */
+int hyp_distance(const float *x, int64_t ldx, const float *y, int64_t ldy, float *out,
+                 int64_t n, int D, float c, int semantics, void *stream);
+/* log_map, lorentz_model.py:96-119.  out[n][D] (ldo) */
+int hyp_log_map(const float *x, int64_t ldx, const float *y, int64_t ldy, float *out,
+                int64_t ldo, int64_t n, int D, int semantics, void *stream);
+/* exp_map, lorentz_model.py:73-93.  out[n][D] */
+int hyp_exp_map(const float *x, int64_t ldx, const float *v, int64_t ldv, float *out,
+                int64_t ldo, int64_t n, int D, void *stream);
+/* project_to_hyperboloid, lorentz_model.py:41-56.  out[n][D]; out may alias x */
+int hyp_project(const float *x, int64_t ldx, float *out, int64_t ldo, int64_t n, int D, float c,
+                void *stream);
+/* weighted midpoint of tokenizer/hyperbolic_merge.py:323-340 for n index pairs of table E:
+ * project(exp_xi(w_j * log_xi(xj))), w_j = len_j/(len_i+len_j) (double, rounded to fp32).
+ * `project`==0 gives the un-projected point of frequency_aware_hyperbolic_merge.py:139-141. */
+int hyp_midpoint(const float *E, int64_t ldE, const int32_t *idx_i, const int32_t *idx_j,
+                 const int32_t *len_i, const int32_t *len_j, float *out, int64_t ldo, int64_t n,
+                 int D, float c, int semantics, int project, void *stream);
+
+/* ---- K3: exact re-scoring of index pairs (hyperbolic_merge.py:230-241,
+ * fast_hyperbolic_merge.py:320-324, :450-454).  u_out (pre-clamp, pre-sign product) may be NULL. */
+int hyp_rescore_pairs(const float *E, int64_t ldE, const int32_t *idx_i, const int32_t *idx_j,
+                      float *d_out, float *u_out, int64_t n, int D, float c, int semantics,
+                      void *stream);
+
+/* ---- K2 (exact fp32 path): all-pairs Lorentz distance, lorentz_model.py:141-178 ----------- */
+
+/* batch_distance: full (n1, n2) matrix, out[n1][ldo]. */
+int hyp_batch_distance(const float *x, int64_t ldx, int64_t n1, const float *y, int64_t ldy,
+                       int64_t n2, float *out, int64_t ldo, int D, float c, int semantics,
+                       void *stream);
+
+/* Result record of the reductions below: the argmin over the key (d, i, j) -- what the
+ * reference's stable sort on distance selects (hyperbolic_merge.py:378). i == -1: none. */
+typedef struct hyp_best {
+  float d;
+  int32_t i;
+  int32_t j;
+  uint32_t count_lo; /* number of pairs with d < threshold, i < j (low / high word) */
+  uint32_t count_hi;
+  uint32_t pad[3];
+} hyp_best; /* 32 bytes */
+
+int64_t hyp_allpairs_workspace_bytes(int64_t n);
+/* _find_merge_candidates + sort + [0] (hyperbolic_merge.py:247-269,:378) without materialising
+ * the list: argmin over i<j<n of (d,i,j), plus the count of pairs with d < threshold.
+ * NaN distances never qualify (`NaN < thr` is False). `best` is device memory. */
+int hyp_allpairs_min(const float *E, int64_t ldE, int64_t n, int D, float c, int semantics,
+                     float threshold, hyp_best *best, void *workspace, int64_t workspace_bytes,
+                     void *stream);
+/* The candidate list itself (hyperbolic_merge.py:259-269): writes up to `capacity` records
+ * (i, j, d) with i<j, d<threshold in UNSPECIFIED order (the host sorts by (i,j) to get the
+ * reference's row-major order) and the total count into *count (device, uint64). */
+int hyp_allpairs_emit(const float *E, int64_t ldE, int64_t n, int D, float c, int semantics,
+                      float threshold, int32_t *out_i, int32_t *out_j, float *out_d,
+                      int64_t capacity, unsigned long long *count, void *stream);
+
+/* ---- K4/K5: incremental merge loop (hyperbolic_merge.py:309-412, the loop of
+ * scripts/train_hyperbolic_tokenizer.py:236-283, fast_hyperbolic_merge.py:467-576) ------------
+ * Device-resident state; the loop never leaves the GPU.  Because the reference never removes
+ * a merged pair and never changes an existing row, argmin over all pairs after appending row n
+ * equals min(previous argmin, argmin over pairs (i, n)) -- SURVEY.md section 0.3. */
+typedef struct hyp_merge_state {
+  double threshold;   /* merge_threshold: a Python float in the reference. Compared as the
+                         reference does: `d < (float)thr` when n > 100 (tensor `<`,
+                         hyperbolic_merge.py:262), `(double)d < thr` when n <= 100 (:288)   */
+  int32_t n;          /* current vocabulary size                                   */
+  int32_t capacity;   /* max_vocab_size (rows allocated in E)                      */
+  float best_d;       /* running argmin over all i<j<n of (d, i, j); i == -1: none */
+  int32_t best_i;
+  int32_t best_j;
+  int32_t steps_done; /* merges appended by the last hyp_merge_steps call          */
+  int32_t stop;       /* 0 ran max_steps, 1 no candidate below threshold, 2 table full */
+  int32_t pad;
+} hyp_merge_state;    /* 40 bytes */
+
+typedef struct hyp_merge_record {
+  int32_t i;
+  int32_t j;
+  float d;
+  int32_t n_new; /* row index the merged token received */
+} hyp_merge_record;
+
+int64_t hyp_merge_workspace_bytes(void);
+/* Fill *state on the device from an argmin record produced by hyp_allpairs_min (no host round
+ * trip between the initial all-pairs search and the loop). */
+int hyp_merge_state_init(hyp_merge_state *state, const hyp_best *best, int32_t n, int32_t capacity,
+                         double threshold, void *stream);
+/* Runs up to `max_steps` merges on the device: pick state.best if best_d < threshold,
+ * append midpoint row n (lengths in `len`, len[n] = len[i]+len[j]), score row n against rows
+ * 0..n-1, fold into the running argmin.  Appends one record per merge to `log`
+ * (capacity >= max_steps).  `threshold_every`/`threshold_mul`: every `threshold_every` steps
+ * (step > 0, counted from `step0`) threshold *= threshold_mul, as the reference loops do
+ * (x1.05 / x1.1 per 1000); pass 0 to disable.  Stops early when nothing is below threshold
+ * (state->stop = 1) or the table is full (stop = 2, the reference's ValueError). */
+int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float c, int semantics,
+                    hyp_merge_state *state, hyp_merge_record *log, int32_t max_steps,
+                    int32_t step0, int32_t threshold_every, double threshold_mul, void *workspace,
+                    int64_t workspace_bytes, void *stream);
+/* One row against the table: argmin over i<n of (d(E[i], E[row]), i) and count below
+ * threshold; the single-step building block (K4). */
+int hyp_row_min(const float *E, int64_t ldE, int64_t n, int64_t row, int D, float c, int semantics,
+                float threshold, hyp_best *best, void *workspace, int64_t workspace_bytes,
+                void *stream);
+
+/* ---- K6: pair counting (frequency_aware_hyperbolic_merge.py:92-112) ----------------------- */
+/* Adjacent code-point pairs inside each `line.strip()` of a UTF-8 byte stream (16-byte aligned),
+ * lines split at '\n' / '\r' (text-mode universal newlines), never across lines; strip() removes
+ * every str.isspace() code point.  ASCII pairs land in ascii_counts[a*128+b] (uint64[16384]); all
+ * other pairs in an open-addressing table: hash_keys[h] = (cp_a << 32 | cp_b), 0xFFFF.. = empty,
+ * hash_vals[h] = count; hash_capacity must be a power of two.  The callee zeroes/initialises all
+ * outputs.  *overflow (device int) != 0 if the table filled up.  Input must be valid UTF-8 (the
+ * reference would raise UnicodeDecodeError otherwise). */
+int hyp_pair_count(const uint8_t *text, int64_t n_bytes, unsigned long long *ascii_counts,
+                   unsigned long long *hash_keys, unsigned long long *hash_vals,
+                   int64_t hash_capacity, int *overflow, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPTOK_B200_H */

@@ -1,0 +1,226 @@
+"""GPU parity: merge loops (K2 argmin, K4/K5 device loop, candidate lists) through the drop-in
+tokenizer classes, against golden traces of the unmodified reference and against the oracle.
+
+Bar: identical merge sequence (i, j) and identical vocab / merge strings; distances and the
+appended rows within 1e-5 relative (north_star); NaN rows of the shipped semantics reproduced."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from helpers import from_bits, same_bits
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+def g(b):
+    return np.asarray(b, dtype=np.uint32).view(np.float32)
+
+
+def rows_close(got, want_bits, n, D):
+    want = g(want_bits).reshape(n, D)
+    got = got.detach().cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.all(np.abs(got[ok] - want[ok]) <= REL * np.abs(want[ok]) + 1e-9)
+
+
+def check_trace(rec, trace):
+    assert len(rec) == len(trace)
+    assert [(int(a), int(b)) for a, b in zip(rec["i"], rec["j"])] == [(t[0], t[1]) for t in trace]
+    want_d = g([t[2] for t in trace])
+    assert np.all(np.abs(rec["d"] - want_d) <= REL * np.abs(want_d))
+
+
+def HT():
+    from hyptokenizer_b200.tokenizer.hyperbolic_merge import HyperbolicTokenizer
+    return HyperbolicTokenizer
+
+
+def test_trace_test9(golden):
+    gd = golden("trace_test9.json")
+    for sem in ("reference", "lorentz"):
+        r = gd[sem]
+        emb = from_bits(r["init"], 9, r["d"] + 1)
+        tok = HT()(r["vocab0"], torch.nn.Parameter(emb), curvature=1.0, merge_threshold=10.0, max_vocab_size=64,
+                   semantics=sem)
+        cands = tok._find_merge_candidates()          # reference test_find_merge_candidates
+        want = r["candidates_thr10"]
+        assert [(i, j) for i, j, _ in cands] == [(i, j) for i, j, _ in want]
+        for (_, _, d), (_, _, wb) in zip(cands, want):
+            w = float(g([wb])[0])
+            assert isinstance(d, float) and abs(d - w) <= REL * abs(w)
+        tok.merge_threshold = 0.5
+        tok.optimize_merges(steps=12)
+        check_trace(tok.last_trace, r["trace"])
+        assert tok.vocab == r["final"]["vocab"]
+        assert [list(m) for m in tok.merge_history] == r["final"]["merges"]
+        rows_close(tok.embeddings[: tok.current_vocab_size], r["final"]["embeddings"], r["final"]["n"], r["d"] + 1)
+
+
+def test_trace_c1(golden):
+    gd = golden("trace_c1.json")
+    for run in gd["runs"]:
+        emb = from_bits(run["init"], len(gd["vocab0"]), gd["d"] + 1)
+        tok = HT()(gd["vocab0"], torch.nn.Parameter(emb), merge_threshold=run["threshold"], max_vocab_size=1000,
+                   semantics=run["semantics"])
+        rec = tok.train(merge_steps=100000, target_vocab_size=run["target"])
+        check_trace(rec, run["trace"])
+        assert tok.vocab == run["final"]["vocab"]
+        rows_close(tok.embeddings[: tok.current_vocab_size], run["final"]["embeddings"], run["final"]["n"], gd["d"] + 1)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLDEN, "trace_c1_full.json")), reason="full C1 fixture absent")
+def test_trace_c1_full(golden):
+    """BASELINE config 1 at full size: 30 -> 1000 tokens, d=50, both semantics."""
+    gd = golden("trace_c1_full.json")
+    for run in gd["runs"]:
+        emb = from_bits(run["init"], len(gd["vocab0"]), gd["d"] + 1)
+        tok = HT()(gd["vocab0"], torch.nn.Parameter(emb), merge_threshold=run["threshold"], max_vocab_size=1000,
+                   semantics=run["semantics"])
+        rec = tok.train(merge_steps=100000, target_vocab_size=run["target"])
+        check_trace(rec, run["trace"])
+        assert tok.vocab == run["final"]["vocab"]
+        assert len(tok.vocab) == 1000
+
+
+def test_host_loop_equals_device_loop(golden):
+    """The step-by-step API (_find_merge_candidates -> sort -> _merge_tokens) and the device-resident
+    loop produce the same tokenizer."""
+    gd = golden("trace_c1.json")
+    run = [r for r in gd["runs"] if r["semantics"] == "lorentz" and r["scale"] == 0.3][0]
+    emb = from_bits(run["init"], len(gd["vocab0"]), gd["d"] + 1)
+    a = HT()(gd["vocab0"], torch.nn.Parameter(emb.clone()), merge_threshold=run["threshold"], max_vocab_size=200,
+             semantics="lorentz")
+    b = HT()(gd["vocab0"], torch.nn.Parameter(emb.clone()), merge_threshold=run["threshold"], max_vocab_size=200,
+             semantics="lorentz")
+    a.optimize_merges(steps=40)
+    b._host_loop(40, 1000)
+    assert a.vocab == b.vocab and a.merge_history == b.merge_history
+    assert same_bits(a.embeddings[: a.current_vocab_size], b.embeddings[: b.current_vocab_size])
+
+
+def test_fast_snapshot_trace(golden):
+    from hyptokenizer_b200.tokenizer.fast_hyperbolic_merge import FastHyperbolicTokenizer
+    gd = golden("trace_fast300.json")
+    for run in gd["runs"]:
+        emb = from_bits(run["init"], 300, run["d"] + 1)
+        random.seed(42)
+        tok = FastHyperbolicTokenizer([f"w{k}" for k in range(300)], torch.nn.Parameter(emb),
+                                      merge_threshold=run["threshold0"], max_vocab_size=1024,
+                                      use_approximate_search=False, semantics=run["semantics"],
+                                      cache_semantics="snapshot")
+        tok.optimize_merges(steps=250, log_every=1000)
+        assert [[a, b] for a, b, _ in tok.last_trace] == run["merges_ij"]
+        assert tok.vocab == run["final"]["vocab"]
+        assert abs(tok.merge_threshold - run["final"]["merge_threshold"]) <= 1e-6 * run["final"]["merge_threshold"]
+        cs, got = run["cache_stats"], tok.cache.get_stats()
+        assert (got["size"], got["hit_count"], got["miss_count"]) == (cs["size"], cs["hit_count"], cs["miss_count"])
+
+
+@pytest.mark.parametrize("sem,scale,thr", [("reference", 0.01, 0.1), ("lorentz", 0.1, 0.9), ("lorentz", 0.01, 0.12)])
+def test_fast_fresh_equals_bruteforce_oracle(sem, scale, thr):
+    """north_star gate: the Fast class (exact device search) reproduces the merge sequence of the
+    reference's brute-force HyperbolicTokenizer on the same synthetic vocabulary and seed."""
+    from hyptokenizer_b200.tokenizer.fast_hyperbolic_merge import FastHyperbolicTokenizer
+    from oracle import lorentz as OL
+    from oracle import merge as OM
+    torch.manual_seed(42)
+    n0, d, steps = 400, 100, 120
+    emb = OL.initialize_embeddings(n0, d, scale=scale)
+    vocab = [f"w{k}" for k in range(n0)]
+    ora = OM.OracleTokenizer(vocab, emb, 1.0, thr, 1024, sem)
+    ora.optimize_merges(steps)
+    tok = FastHyperbolicTokenizer(vocab, torch.nn.Parameter(emb.clone()), merge_threshold=thr, max_vocab_size=1024,
+                                  semantics=sem)
+    tok.optimize_merges(steps=steps, adaptive_threshold=False)
+    got = [(int(a), int(b)) for a, b in zip(tok.last_trace["i"], tok.last_trace["j"])]
+    assert got == [(a, b) for a, b, _ in ora.trace]
+    assert tok.vocab == ora.vocab
+    want = np.array([t[2] for t in ora.trace], dtype=np.float32)
+    assert np.all(np.abs(tok.last_trace["d"] - want) <= REL * np.abs(want))
+
+
+def test_running_argmin_equals_recompute_full_size():
+    """Size-independent property at BASELINE config-2 scale (d=100, V0=10k): after k device-loop merges
+    the running argmin equals a from-scratch all-pairs argmin, and every logged distance equals an
+    exact re-score of its pair."""
+    from hyptokenizer_b200 import _lib
+    from hyptokenizer_b200._lib import SEM, check, ptr, stream_ptr
+    from hyptokenizer_b200.embedding import lorentz_model as LM
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    from hyptokenizer_b200.tokenizer.hyperbolic_merge import HyperbolicTokenizer, _threshold_f32
+    n0, d, steps = 10000, 100, 1500
+    emb = synthetic_embeddings(n0, d, scale=0.05, seed=7, device="cuda")
+    tok = HyperbolicTokenizer([f"w{k}" for k in range(n0)], torch.nn.Parameter(emb), merge_threshold=0.9,
+                              max_vocab_size=n0 + steps, semantics="lorentz")
+    tok.optimize_merges(steps=steps)
+    rec = tok.last_trace
+    assert len(rec) == steps and tok.current_vocab_size == n0 + steps
+    st = tok._last_state
+    fresh = tok._global_best(_threshold_f32(tok.merge_threshold, tok.current_vocab_size))
+    assert (fresh.i, fresh.j) == (st.best_i, st.best_j) and fresh.d == st.best_d
+    E = tok.embeddings.data
+    ii = torch.from_numpy(rec["i"].copy()).cuda()
+    jj = torch.from_numpy(rec["j"].copy()).cuda()
+    dd = torch.empty(steps, device="cuda")
+    check(_lib.lib().hyp_rescore_pairs(ptr(E), E.stride(0), ptr(ii), ptr(jj), ptr(dd), None, steps, d + 1, 1.0,
+                                       SEM["lorentz"], stream_ptr()))
+    assert same_bits(dd, rec["d"])
+    assert np.all(rec["d"] < tok.merge_threshold)
+    nn = LM.minkowski_dot(E[: tok.current_vocab_size], E[: tok.current_vocab_size])
+    assert torch.allclose(nn, torch.ones_like(nn), atol=1e-4)
+
+
+def test_vocab_full_raises_value_error(golden):
+    gd = golden("trace_test9.json")["reference"]
+    emb = from_bits(gd["init"], 9, gd["d"] + 1)
+    tok = HT()(gd["vocab0"], torch.nn.Parameter(emb), merge_threshold=0.5, max_vocab_size=12)
+    with pytest.raises(ValueError, match="Maximum vocabulary size"):
+        tok.optimize_merges(steps=10)
+    assert tok.current_vocab_size == 12          # three merges fit, the fourth raises (reference :343-344)
+    with pytest.raises(ValueError):
+        tok._merge_tokens(0, 1)
+
+
+def test_no_candidates_stops(golden):
+    gd = golden("trace_test9.json")["lorentz"]
+    emb = from_bits(gd["init"], 9, gd["d"] + 1)
+    tok = HT()(gd["vocab0"], torch.nn.Parameter(emb), merge_threshold=1e-9, max_vocab_size=64, semantics="lorentz")
+    tok.optimize_merges(steps=10)
+    assert tok.current_vocab_size == 9 and tok._find_merge_candidates() == []
+
+
+def test_tokenize_encode_decode_save_load(golden, tmp_path):
+    """reference tests test_tokenize_encode_decode / test_save_load, re-used as drop-in API tests."""
+    gd = golden("trace_test9.json")["reference"]
+    emb = from_bits(gd["init"], 9, gd["d"] + 1)
+    tok = HT()(gd["vocab0"], torch.nn.Parameter(emb), merge_threshold=0.5, lr=1e-3)
+    for a, b in (("a", "b"), ("c", "d")):
+        tok.vocab.append(a + b)
+        tok.token2idx[a + b] = len(tok.vocab) - 1
+        tok.merge_history.append((a, b, a + b))
+    new = torch.zeros((len(tok.vocab), 6), device="cuda")
+    new[:9] = emb.cuda()
+    new[9:] = emb[4:6].cuda()
+    tok.embeddings = torch.nn.Parameter(new)
+    assert tok.tokenize("abcde") == ["ab", "cd", "e"]
+    ids = tok.encode("abcde")
+    assert ids == [tok.token2idx["ab"], tok.token2idx["cd"], tok.token2idx["e"]]
+    assert tok.decode(ids) == "abcde"
+    tok.current_vocab_size = len(tok.vocab)
+    path = str(tmp_path / "tok")
+    tok.save(path)
+    for fn in ("vocab.json", "embeddings.pt", "merges.json", "config.json"):
+        assert os.path.exists(os.path.join(path, fn))
+    saved = torch.load(os.path.join(path, "embeddings.pt"))
+    assert saved.device.type == "cpu" and saved.shape == (11, 6) and saved.dtype == torch.float32
+    back = HT().load(path)
+    assert back.vocab == tok.vocab and back.merge_history == [list(m) for m in tok.merge_history]
+    assert torch.equal(back.embeddings[:11].cpu(), tok.embeddings[:11].cpu())
+    assert back.embeddings.shape[0] == back.max_vocab_size
+    assert (back.curvature, back.merge_threshold) == (tok.curvature, tok.merge_threshold)
