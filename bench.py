@@ -172,7 +172,7 @@ def run_ours(a):
         check(L.hyp_merge_state_init(ptr(state), ptr(best), v0, target, THRESHOLD, sp))
         ev[1].record(stream)
         check(L.hyp_merge_steps(ptr(E), D, ptr(lens), D, 1.0, sem, ptr(state), ptr(log), merges, 0, 1000, 1.1,
-                                ptr(ws_lp), ws_lp.numel(), sp))
+                                target, ptr(ws_lp), ws_lp.numel(), sp))
         ev[2].record(stream)
         if not timed:
             return None
@@ -196,6 +196,12 @@ def run_ours(a):
         dist.barrier()
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
+    prof = ws_lp[32:96].cpu().numpy().view(np.int64)
+    if rank == 0 and prof[3] > 0:
+        for name, base in (("cta0", 0), ("ctaN", 4)):
+            n_ = max(int(prof[base + 3]), 1)
+            print(f"[phases {name}] cycles/merge: midpoint={prof[base] / n_:.0f} scan={prof[base + 1] / n_:.0f} "
+                  f"barrier={prof[base + 2] / n_:.0f}", file=sys.stderr)
     from hyptokenizer_b200._lib import HypMergeState
     st = HypMergeState.from_buffer_copy(state.cpu().numpy().tobytes())
     done = st.steps_done

@@ -292,7 +292,7 @@ static int launch_tiles(Params &p, cudaStream_t st, const char *what) {
 
 static int fill_params(Params &p, const float *x, int64_t ldx, int64_t n1, const float *y, int64_t ldy, int64_t n2,
                        int D, float c, int semantics, int triangular) {
-  if (!x || !y || n1 < 0 || n2 < 0 || D < 2 || D > HYP_MAX_D || !(c > 0.f)) {
+  if (((!x || !y) && n1 > 0 && n2 > 0) || n1 < 0 || n2 < 0 || D < 2 || D > HYP_MAX_D || !(c > 0.f)) {
     set_error("all-pairs: bad arguments (n1=%lld n2=%lld D=%d c=%g)", (long long)n1, (long long)n2, D, c);
     return HYP_ERR_ARG;
   }
@@ -316,8 +316,8 @@ extern "C" int hyp_batch_distance(const float *x, int64_t ldx, int64_t n1, const
   Params p;
   int rc = fill_params(p, x, ldx, n1, y, ldy, n2, D, c, semantics, 0);
   if (rc) return rc;
-  if (!out) return HYP_ERR_ARG;
   if (n1 == 0 || n2 == 0) return HYP_OK;
+  if (!out) return HYP_ERR_ARG;
   p.out = out;
   p.ldo = ldo;
   return launch_tiles<kDense>(p, (cudaStream_t)stream, "hyp_batch_distance");

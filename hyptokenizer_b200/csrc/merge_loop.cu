@@ -12,6 +12,8 @@
 // midpoint row redundantly and bit-identically, CTA 0 appends it, all CTAs scan their share of
 // rows, one grid barrier, every CTA reduces the per-CTA minima to the same new state.
 // Compiled with -fmad=false.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hyp {
@@ -24,8 +26,10 @@ constexpr int kRowsPerIter = 4;  // rows a warp keeps in flight (independent red
 struct LoopWorkspace {
   unsigned int barrier;  // monotonically increasing arrival counter
   unsigned int ticket;   // hyp_row_min: last-block-done
-  unsigned int pad[30];
-  Key slot[2][kMaxLoopBlocks];  // per-CTA minima, double-buffered by step parity
+  unsigned int pad[6];
+  long long prof[8];               // resident loop: phase cycle counters of CTA 0 and CTA G-1
+  unsigned long long key_ring[4];  // resident loop: per-step atomicMin target (d_bits << 32 | row)
+  Key slot[2][kMaxLoopBlocks];     // L2 loop: per-CTA minima, double-buffered by step parity
   unsigned long long below[kMaxLoopBlocks];
 };
 
@@ -223,7 +227,7 @@ struct LoopParams {
   LoopWorkspace *ws;
 };
 
-__global__ void __launch_bounds__(kLoopThreads) merge_loop_kernel(const LoopParams p) {
+__global__ void __launch_bounds__(kLoopThreads) merge_loop_l2_kernel(const LoopParams p) {
   extern __shared__ float smem[];
   const int D = p.D;
   float *q = smem;           // [D] new row
@@ -313,6 +317,215 @@ __global__ void __launch_bounds__(kLoopThreads) merge_loop_kernel(const LoopPara
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K5, table-resident variant.  The whole table lives in the shared memory of the persistent grid:
+// CTA b owns rows r = b (mod G) in slot r / G.  Spatial parts are stored as float4 groups,
+// T4[g][slot] = elements 4g..4g+3 of the row in `slot` (time parts in T0[slot]), so that
+//  (a) one THREAD scores one row with conflict-free LDS.128 (a warp reads 512 contiguous bytes) and
+//      ~3 instructions per element -- the warp-per-row L2 loop is issue-bound at ~10x that;
+//  (b) the ATen summation order falls out of streaming the row in natural order into 32 register
+//      accumulators P[e mod 32] (partial c = (e/8) mod 4, lane l = e mod 8  <=>  8c + l = e mod 32);
+//  (c) appending a row is 25 strided float4 stores (odd slot stride).
+// 148 SMs x ~220 KB hold ~80 k rows of D=101: the table of BASELINE configs[1] (50 k x 101 fp32 =
+// 20.2 MB) never leaves the SMs between merges.  Per merge: one 64-bit atomicMin per CTA on
+// (d_bits << 32 | row) and one grid barrier.
+// ---------------------------------------------------------------------------------------------
+constexpr int kResThreads = 384;
+constexpr int kResWarps = kResThreads / 32;
+constexpr unsigned long long kNoKey = 0xffffffffffffffffULL;
+
+struct ResidentParams {
+  LoopParams lp;
+  int slots;   // slot capacity per CTA (odd)
+};
+
+// exact-order Minkowski product of the row in `slot` with q; N known at compile time.
+template <int N>
+__device__ __forceinline__ float resident_mdot_static(const float4 *__restrict__ T4, const float *__restrict__ T0, int S,
+                                                      int slot, const float4 *__restrict__ q4, float q0) {
+  constexpr int vs = N / 8, full = vs / 4, G4 = (N + 3) / 4;
+  float P[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) P[k] = 0.f;
+  float tail = 0.f;
+#pragma unroll
+  for (int g = 0; g < G4; ++g) {
+    const float4 a = T4[(size_t)g * S + slot];
+    const float4 b = q4[g];
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int e = 4 * g + c;
+      if (e < N) {
+        const float pr = __fmul_rn(av[c], bv[c]);
+        if (e < 32 * full) P[e & 31] = __fadd_rn(P[e & 31], pr);
+        else if (e < 8 * vs) P[e & 7] = __fadd_rn(P[e & 7], pr);   // left-over lane vectors join partial 0
+        else tail = __fadd_rn(tail, pr);
+      }
+    }
+  }
+  float acc = tail;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) {
+    const float L = __fadd_rn(__fadd_rn(__fadd_rn(P[l], P[8 + l]), P[16 + l]), P[24 + l]);
+    acc = __fadd_rn(acc, L);
+  }
+  return __fsub_rn(__fmul_rn(T0[slot], q0), acc);
+}
+
+// any N (including N < 8): scalar reads of the same layout
+__device__ __forceinline__ float resident_mdot_dynamic(const float4 *__restrict__ T4, const float *__restrict__ T0, int S,
+                                                       int slot, const float4 *__restrict__ q4, float q0, int N) {
+  const float *Tf = reinterpret_cast<const float *>(T4);
+  const float *qf = reinterpret_cast<const float *>(q4);
+  float s = thread_sum_aten(
+      [&](int e) { return __fmul_rn(Tf[((size_t)(e >> 2) * S + slot) * 4 + (e & 3)], qf[e]); }, N);
+  return __fsub_rn(__fmul_rn(T0[slot], q0), s);
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(const ResidentParams rp) {
+  extern __shared__ __align__(16) float smem[];
+  const LoopParams &p = rp.lp;
+  const int D = p.D, S = rp.slots, N = D - 1;
+  const int G4 = (N + 3) / 4;
+  const int G = gridDim.x, b = blockIdx.x;
+  // layout (floats): q4[4*G4] | T4[4*G4*S] | T0[S] | q[D] xi[D] xj[D] scratch[2D]
+  float4 *q4 = reinterpret_cast<float4 *>(smem);
+  float4 *T4 = q4 + G4;
+  float *T0 = reinterpret_cast<float *>(T4 + (size_t)G4 * S);
+  float *q = T0 + S;
+  float *xi = q + D;
+  float *xj = xi + D;
+  float *scratch = xj + D;
+  float *Tf = reinterpret_cast<float *>(T4);
+  float *qf = reinterpret_cast<float *>(q4);
+  __shared__ unsigned long long s_key[kResWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  int n = p.state->n;
+  const int cap = p.state->capacity;
+  Key best{p.state->best_d, p.state->best_i, p.state->best_j};
+  double thr = p.state->threshold;
+  int done = 0, stop = 0;
+  unsigned int arrivals = 0;
+  long long t_mid = 0, t_scan = 0, t_bar = 0, t_mark = 0;
+
+  // ---- load the rows this CTA owns: a warp reads one row (coalesced), scatters it conflict-free --
+  {
+    const int owned = (n > b) ? (n - b + G - 1) / G : 0;
+    for (int sl = warp; sl < owned; sl += kResWarps) {
+      const float *row = p.E + ((int64_t)sl * G + b) * p.ldE;
+      for (int k = lane; k < D; k += 32) {
+        const float v = __ldcg(row + k);
+        if (k == 0) T0[sl] = v;
+        else Tf[((size_t)((k - 1) >> 2) * S + sl) * 4 + ((k - 1) & 3)] = v;
+      }
+    }
+    for (int k = threadIdx.x; k < 4 * G4; k += blockDim.x) qf[k] = 0.f;   // padding lanes of q4 stay zero
+  }
+  if (b == 0 && threadIdx.x < 4) p.ws->key_ring[threadIdx.x] = kNoKey;
+  arrivals += G;
+  grid_barrier(&p.ws->barrier, arrivals);
+  if (threadIdx.x == 0) t_mark = clock64();
+
+  for (int k = 0; k < p.max_steps; ++k) {
+    const bool cmp_double = n <= 100;
+    const bool have = best.i >= 0 && (cmp_double ? ((double)best.d < thr) : (best.d < (float)thr));
+    if (!have) { stop = 1; break; }
+    if (n >= cap) { stop = 2; break; }
+
+    // ---- midpoint row, redundantly and bit-identically in every CTA --------------------------
+    for (int e = threadIdx.x; e < D; e += blockDim.x) {
+      xi[e] = __ldcg(p.E + (int64_t)best.i * p.ldE + e);
+      xj[e] = __ldcg(p.E + (int64_t)best.j * p.ldE + e);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int li = __ldcg(p.len + best.i), lj = __ldcg(p.len + best.j);
+      warp_midpoint(xi, xj, li, lj, D, p.c, p.semantics, true, scratch, lane, [&](int e, float v) {
+        q[e] = v;
+        if (e) qf[e - 1] = v;
+      });
+      if (b == 0) {
+        __syncwarp();
+        for (int e = lane; e < D; e += 32) p.E[(int64_t)n * p.ldE + e] = q[e];
+        if (lane == 0) {
+          p.len[n] = li + lj;
+          p.log[k] = hyp_merge_record{best.i, best.j, best.d, n};
+          p.ws->key_ring[(k + 2) & 3] = kNoKey;  // recycled two barriers from now
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { long long t = clock64(); t_mid += t - t_mark; t_mark = t; }
+
+    // ---- score row n against the resident rows (< n) of this CTA: one thread per row ------------
+    const int owned = (n > b) ? (n - b + G - 1) / G : 0;
+    const float q0 = q[0];
+    unsigned long long mine = kNoKey;
+    for (int t = threadIdx.x; t < owned; t += blockDim.x) {
+      const float m = (NS > 0) ? resident_mdot_static<(NS > 0 ? NS : 8)>(T4, T0, S, t, q4, q0)
+                               : resident_mdot_dynamic(T4, T0, S, t, q4, q0, N);
+      const float d = dist_from_mdot(m, p.sgn, p.sqrt_c);
+      if (d == d) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)(t * G + b);
+        mine = key < mine ? key : mine;
+      }
+    }
+    // the owner of row n appends it (its slot is beyond `owned`, so nobody reads it this step)
+    if (n % G == b) {
+      const int sl = n / G;
+      for (int e = threadIdx.x; e < D; e += blockDim.x) {
+        if (e == 0) T0[sl] = q[0];
+        else Tf[((size_t)((e - 1) >> 2) * S + sl) * 4 + ((e - 1) & 3)] = q[e];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long other = __shfl_xor_sync(HYP_FULL_MASK, mine, o);
+      mine = other < mine ? other : mine;
+    }
+    if (lane == 0) s_key[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long m2 = s_key[0];
+      for (int w = 1; w < kResWarps; ++w) m2 = s_key[w] < m2 ? s_key[w] : m2;
+      if (m2 != kNoKey) atomicMin(&p.ws->key_ring[k & 3], m2);
+      long long t = clock64(); t_scan += t - t_mark; t_mark = t;
+    }
+    arrivals += G;
+    grid_barrier(&p.ws->barrier, arrivals);
+    if (threadIdx.x == 0) { long long t = clock64(); t_bar += t - t_mark; t_mark = t; }
+
+    const unsigned long long win = __ldcg(&p.ws->key_ring[k & 3]);
+    if (win != kNoKey) {
+      Key r{__uint_as_float((unsigned int)(win >> 32)), (int)(win & 0xffffffffu), n};
+      if (key_less(r, best)) best = r;
+    }
+    ++n;
+    ++done;
+    const int step = p.step0 + k;
+    if (p.thr_every > 0 && step > 0 && step % p.thr_every == 0) thr *= p.thr_mul;
+  }
+
+  if (threadIdx.x == 0 && (b == 0 || b == G - 1)) {
+    // phase cycle counters of the first and last CTA (diagnostics; read by bench.py --phases)
+    long long *prof = p.ws->prof + (b == 0 ? 0 : 4);
+    prof[0] = t_mid; prof[1] = t_scan; prof[2] = t_bar; prof[3] = done;
+  }
+  if (b == 0 && threadIdx.x == 0) {
+    p.state->n = n;
+    p.state->best_d = best.d;
+    p.state->best_i = best.i;
+    p.state->best_j = best.j;
+    p.state->threshold = thr;
+    p.state->steps_done = done;
+    p.state->stop = stop;
+  }
+}
+
 __global__ void merge_state_init_kernel(hyp_merge_state *st, const hyp_best *best, int n, int capacity, double thr) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->threshold = thr;
@@ -331,7 +544,7 @@ static int loop_grid(size_t smem, int *blocks_out) {
   int dev = 0, sms = 148, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_loop_kernel, kLoopThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, merge_loop_l2_kernel, kLoopThreads, smem);
   if (per_sm < 1) {
     set_error("merge loop: kernel does not fit on an SM (smem=%zu)", smem);
     return HYP_ERR_CUDA;
@@ -382,8 +595,8 @@ extern "C" int hyp_row_min(const float *E, int64_t ldE, int64_t n, int64_t row, 
 
 extern "C" int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float c, int semantics,
                                hyp_merge_state *state, hyp_merge_record *log, int32_t max_steps, int32_t step0,
-                               int32_t threshold_every, double threshold_mul, void *workspace,
-                               int64_t workspace_bytes, void *stream) {
+                               int32_t threshold_every, double threshold_mul, int32_t capacity_hint,
+                               void *workspace, int64_t workspace_bytes, void *stream) {
   if (!E || !len || !state || !log || !workspace || D < 2 || D > HYP_MAX_D || max_steps < 0 || !(c > 0.f)) {
     set_error("hyp_merge_steps: bad arguments");
     return HYP_ERR_ARG;
@@ -400,13 +613,48 @@ extern "C" int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float
   p.state = state; p.log = log; p.max_steps = max_steps; p.step0 = step0;
   p.thr_every = threshold_every; p.thr_mul = threshold_mul;
   p.ws = (LoopWorkspace *)workspace;
+  int dev = 0, sms = 148, max_smem = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaMemsetAsync(workspace, 0, 128, st);
+
+  // table-resident variant when every row up to `capacity_hint` fits in the grid's shared memory
+  const int Nsp = D - 1, G4 = (Nsp + 3) / 4;
+  const int64_t fixed = ((int64_t)4 * G4 + (int64_t)5 * D) * (int64_t)sizeof(float) + 1024;
+  int slots = (int)(((int64_t)max_smem - fixed) / (((int64_t)4 * G4 + 1) * (int64_t)sizeof(float)));
+  if ((slots & 1) == 0) --slots;  // odd stride: conflict-free scattered stores
+  const char *force = getenv("HYP_MERGE_LOOP");
+  const bool want_l2 = force && force[0] == 'l';
+  const int64_t rows_max = capacity_hint > 0 ? capacity_hint : 0;
+  if (!want_l2 && slots >= 1 && rows_max > 0 && (rows_max + sms - 1) / sms <= slots) {
+    ResidentParams rp;
+    rp.lp = p;
+    rp.slots = slots;
+    const size_t smem = ((size_t)4 * G4 + (size_t)4 * G4 * slots + slots + (size_t)5 * D) * sizeof(float);
+    const void *fn = Nsp == 100 ? (const void *)merge_loop_resident_kernel<100>
+                     : Nsp == 50 ? (const void *)merge_loop_resident_kernel<50>
+                                 : (const void *)merge_loop_resident_kernel<0>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("hyp_merge_steps: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+      return HYP_ERR_CUDA;
+    }
+    void *args[] = {(void *)&rp};
+    e = cudaLaunchCooperativeKernel(fn, dim3(sms), dim3(kResThreads), args, smem, st);
+    if (e != cudaSuccess) {
+      set_error("hyp_merge_steps: cooperative launch (resident) failed: %s", cudaGetErrorString(e));
+      return HYP_ERR_CUDA;
+    }
+    return check_launch("hyp_merge_steps");
+  }
+
   const size_t smem = (size_t)5 * D * sizeof(float);
   int grid = 0;
   int rc = loop_grid(smem, &grid);
   if (rc) return rc;
-  cudaMemsetAsync(workspace, 0, 128, st);
   void *args[] = {(void *)&p};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void *)merge_loop_kernel, dim3(grid), dim3(kLoopThreads), args,
+  cudaError_t e = cudaLaunchCooperativeKernel((const void *)merge_loop_l2_kernel, dim3(grid), dim3(kLoopThreads), args,
                                               smem, st);
   if (e != cudaSuccess) {
     set_error("hyp_merge_steps: cooperative launch failed: %s", cudaGetErrorString(e));

@@ -108,6 +108,7 @@ static inline int grid_for(int64_t n) {
 }
 
 static int bad_dims(int64_t n, int D) {
+  if (n == 0 && D >= 2 && D <= HYP_MAX_D) return 0;
   if (n < 0 || D < 2 || D > HYP_MAX_D) {
     set_error("bad shape: n=%lld D=%d (need n>=0, 2<=D<=%d)", (long long)n, D, HYP_MAX_D);
     return 1;
@@ -121,16 +122,18 @@ using namespace hyp;
 
 extern "C" int hyp_minkowski_dot(const float *x, int64_t ldx, const float *y, int64_t ldy, float *out,
                                  int64_t n, int D, void *stream) {
-  if (bad_dims(n, D) || !x || !y || !out) return HYP_ERR_ARG;
+  if (bad_dims(n, D)) return HYP_ERR_ARG;
   if (n == 0) return HYP_OK;
+  if (!x || !y || !out) return HYP_ERR_ARG;
   mdot_kernel<<<grid_for(n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, out, n, D);
   return check_launch("hyp_minkowski_dot");
 }
 
 extern "C" int hyp_distance(const float *x, int64_t ldx, const float *y, int64_t ldy, float *out,
                             int64_t n, int D, float c, int semantics, void *stream) {
-  if (bad_dims(n, D) || !x || !y || !out) return HYP_ERR_ARG;
+  if (bad_dims(n, D)) return HYP_ERR_ARG;
   if (n == 0) return HYP_OK;
+  if (!x || !y || !out) return HYP_ERR_ARG;
   distance_kernel<<<grid_for(n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       x, ldx, y, ldy, out, n, D, sqrtf(c), semantics == HYP_SEM_REFERENCE ? -1.f : 1.f);
   return check_launch("hyp_distance");
@@ -139,8 +142,9 @@ extern "C" int hyp_distance(const float *x, int64_t ldx, const float *y, int64_t
 extern "C" int hyp_rescore_pairs(const float *E, int64_t ldE, const int32_t *idx_i, const int32_t *idx_j,
                                  float *d_out, float *u_out, int64_t n, int D, float c, int semantics,
                                  void *stream) {
-  if (bad_dims(n, D) || !E || !idx_i || !idx_j || !d_out) return HYP_ERR_ARG;
+  if (bad_dims(n, D)) return HYP_ERR_ARG;
   if (n == 0) return HYP_OK;
+  if (!E || !idx_i || !idx_j || !d_out) return HYP_ERR_ARG;
   rescore_kernel<<<grid_for(n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       E, ldE, idx_i, idx_j, d_out, u_out, n, D, sqrtf(c), semantics == HYP_SEM_REFERENCE ? -1.f : 1.f);
   return check_launch("hyp_rescore_pairs");
@@ -148,8 +152,9 @@ extern "C" int hyp_rescore_pairs(const float *E, int64_t ldE, const int32_t *idx
 
 extern "C" int hyp_log_map(const float *x, int64_t ldx, const float *y, int64_t ldy, float *out,
                            int64_t ldo, int64_t n, int D, int semantics, void *stream) {
-  if (bad_dims(n, D) || !x || !y || !out) return HYP_ERR_ARG;
+  if (bad_dims(n, D)) return HYP_ERR_ARG;
   if (n == 0) return HYP_OK;
+  if (!x || !y || !out) return HYP_ERR_ARG;
   logmap_kernel<<<grid_for(n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, out, ldo, n,
                                                                               D, semantics);
   return check_launch("hyp_log_map");
@@ -157,16 +162,18 @@ extern "C" int hyp_log_map(const float *x, int64_t ldx, const float *y, int64_t 
 
 extern "C" int hyp_exp_map(const float *x, int64_t ldx, const float *v, int64_t ldv, float *out,
                            int64_t ldo, int64_t n, int D, void *stream) {
-  if (bad_dims(n, D) || !x || !v || !out) return HYP_ERR_ARG;
+  if (bad_dims(n, D)) return HYP_ERR_ARG;
   if (n == 0) return HYP_OK;
+  if (!x || !v || !out) return HYP_ERR_ARG;
   expmap_kernel<<<grid_for(n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(x, ldx, v, ldv, out, ldo, n, D);
   return check_launch("hyp_exp_map");
 }
 
 extern "C" int hyp_project(const float *x, int64_t ldx, float *out, int64_t ldo, int64_t n, int D, float c,
                            void *stream) {
-  if (bad_dims(n, D) || !x || !out) return HYP_ERR_ARG;
+  if (bad_dims(n, D)) return HYP_ERR_ARG;
   if (n == 0) return HYP_OK;
+  if (!x || !out) return HYP_ERR_ARG;
   project_kernel<<<grid_for(n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, n, D, c);
   return check_launch("hyp_project");
 }
@@ -174,8 +181,9 @@ extern "C" int hyp_project(const float *x, int64_t ldx, float *out, int64_t ldo,
 extern "C" int hyp_midpoint(const float *E, int64_t ldE, const int32_t *idx_i, const int32_t *idx_j,
                             const int32_t *len_i, const int32_t *len_j, float *out, int64_t ldo, int64_t n,
                             int D, float c, int semantics, int project, void *stream) {
-  if (bad_dims(n, D) || !E || !idx_i || !idx_j || !len_i || !len_j || !out) return HYP_ERR_ARG;
+  if (bad_dims(n, D)) return HYP_ERR_ARG;
   if (n == 0) return HYP_OK;
+  if (!E || !idx_i || !idx_j || !len_i || !len_j || !out) return HYP_ERR_ARG;
   size_t smem = (size_t)kWarpsPerBlock * 2 * D * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {

@@ -20,6 +20,20 @@ def g(b):
     return np.asarray(b, dtype=np.uint32).view(np.float32)
 
 
+def rows_close(got, want, D, rel=REL_TOL):
+    """Vector outputs (tangent vectors, points): error measured against the largest component of the
+    row -- component-wise relative error is meaningless where y - <x,y>x cancels to ~0."""
+    got = got.detach().cpu().numpy().reshape(-1, D)
+    want = np.asarray(want, dtype=np.float32).reshape(-1, D)
+    assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN pattern differs"
+    inf = np.isinf(want)
+    assert np.array_equal(got[inf], want[inf]), "infinities differ"
+    fin = np.isfinite(want)
+    scale = np.where(fin, np.abs(want), 0).max(axis=1, keepdims=True) * np.ones_like(want)
+    err = np.abs(np.where(fin, got, 0).astype(np.float64) - np.where(fin, want, 0))
+    assert np.all(err <= rel * scale + 1e-30)
+
+
 def close(got, want, rel=REL_TOL, ulps=None):
     got = got.detach().cpu().numpy().reshape(-1) if isinstance(got, torch.Tensor) else np.asarray(got).reshape(-1)
     want = np.asarray(want, dtype=np.float32).reshape(-1)
@@ -49,12 +63,18 @@ def test_golden_lorentz_ops(golden, LM):
         ia, ib = torch.tensor(case["ia"], device=dev), torch.tensor(case["ib"], device=dev)
         # bit-exact family
         assert same_bits(LM.minkowski_dot(X.unsqueeze(1), X.unsqueeze(0)), g(case["mdot"]))
-        assert same_bits(LM.minkowski_norm(X), g(case["mnorm"]))
-        assert same_bits(LM.project_to_hyperboloid(P, c), g(case["project"]))
-        assert same_bits(LM.project_to_hyperboloid(P[2], c), g(case["project_row"]))
+        # torch's CPU sqrt is a Sleef routine that is NOT correctly rounded (0.7 % of inputs are 1 ulp off
+        # IEEE sqrt, probed); the device uses IEEE sqrt, so sqrt outputs are pinned to 1 ulp, the rest exactly
+        assert ulp_diff(LM.minkowski_norm(X), g(case["mnorm"])).max() <= 1
+        pr = LM.project_to_hyperboloid(P, c)
+        want = torch.from_numpy(g(case["project"]).reshape(n, d + 1).copy())
+        assert same_bits(pr[:, 1:], want[:, 1:]) and ulp_diff(pr[:, 0], want[:, 0]).max() <= 1
+        pr = LM.project_to_hyperboloid(P[2], c)
+        want = torch.from_numpy(g(case["project_row"]).copy())
+        assert same_bits(pr[1:], want[1:]) and ulp_diff(pr[:1], want[:1]).max() <= 1
         # transcendental family
         V = from_bits(case["V"], len(ia), d + 1).to(dev)
-        close(LM.exp_map(X[ia], V, c), g(case["exp_map"]), ulps=ULP_TOL)
+        rows_close(LM.exp_map(X[ia], V, c), g(case["exp_map"]), d + 1)
         for sem in ("reference", "lorentz"):
             r = case[sem]
             got_d = LM.distance(X[ia], X[ib], c, semantics=sem)
@@ -68,7 +88,7 @@ def test_golden_lorentz_ops(golden, LM):
             else:
                 close(got_d, g(r["distance"]), ulps=ULP_TOL)
                 close(got_b, g(r["batch_distance"]), ulps=ULP_TOL)
-                close(got_l, g(r["log_map"]))
+                rows_close(got_l, g(r["log_map"]), d + 1)
 
 
 def test_golden_midpoint(golden):
@@ -87,7 +107,7 @@ def test_golden_midpoint(golden):
             out = torch.empty((m, d + 1), device=dev)
             check(_lib.lib().hyp_midpoint(ptr(X), d + 1, ptr(ia), ptr(ib), ptr(li), ptr(lj), ptr(out), d + 1, m, d + 1,
                                           c, SEM[sem], 1, stream_ptr()))
-            close(out, g(case[sem]["midpoint_1_3"]))
+            rows_close(out, g(case[sem]["midpoint_1_3"]), d + 1)
 
 
 @pytest.mark.parametrize("d,scale", [(50, 0.01), (100, 0.01), (100, 0.3), (37, 0.1), (8, 0.2), (5, 0.5), (130, 0.05)])
