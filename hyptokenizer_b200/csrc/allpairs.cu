@@ -87,6 +87,66 @@ __device__ __forceinline__ void load_tile_T(const float *__restrict__ src, int64
   }
 }
 
+// Exact-order spatial dot products of a 4x4 block of pairs from two transposed tiles.
+__device__ __forceinline__ void tile_dots(const float *__restrict__ As, const float *__restrict__ Bs, int d, int ty,
+                                          int tx, float (&S)[4][4]) {
+  if (d >= 8) {
+    const int vs = d >> 3, full = vs >> 2;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) S[r][c] = 0.f;
+    // scalar tail first (from zero), then lanes 0..7 in order
+    for (int e = 8 * vs; e < d; ++e) {
+      const float4 a = *reinterpret_cast<const float4 *>(As + e * TPAD + 4 * ty);
+      const float4 b = *reinterpret_cast<const float4 *>(Bs + e * TPAD + 4 * tx);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) S[r][c] = __fadd_rn(S[r][c], __fmul_rn(av[r], bv[c]));
+    }
+    for (int l = 0; l < 8; ++l) {
+      float L[4][4];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        float P[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) P[r][c] = 0.f;
+        auto step = [&](int e) {
+          const float4 a = *reinterpret_cast<const float4 *>(As + e * TPAD + 4 * ty);
+          const float4 b = *reinterpret_cast<const float4 *>(Bs + e * TPAD + 4 * tx);
+          const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) P[r][c] = __fadd_rn(P[r][c], __fmul_rn(av[r], bv[c]));
+        };
+        for (int r = 0; r < full; ++r) step(32 * r + 8 * c4 + l);
+        if (c4 == 0)
+          for (int k = 4 * full; k < vs; ++k) step(8 * k + l);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) L[r][c] = (c4 == 0) ? P[r][c] : __fadd_rn(L[r][c], P[r][c]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) S[r][c] = __fadd_rn(S[r][c], L[r][c]);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        S[r][c] = thread_sum_aten(
+            [&](int e) { return __fmul_rn(As[e * TPAD + 4 * ty + r], Bs[e * TPAD + 4 * tx + c]); }, d);
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(NTHREADS) allpairs_tile_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
@@ -114,61 +174,7 @@ __global__ void __launch_bounds__(NTHREADS) allpairs_tile_kernel(const Params p)
     __syncthreads();
 
     float S[4][4];
-    if (d >= 8) {
-      const int vs = d >> 3, full = vs >> 2;
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) S[r][c] = 0.f;
-      // scalar tail first (from zero), then lanes 0..7 in order
-      for (int e = 8 * vs; e < d; ++e) {
-        const float4 a = *reinterpret_cast<const float4 *>(As + e * TPAD + 4 * ty);
-        const float4 b = *reinterpret_cast<const float4 *>(Bs + e * TPAD + 4 * tx);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) S[r][c] = __fadd_rn(S[r][c], __fmul_rn(av[r], bv[c]));
-      }
-      for (int l = 0; l < 8; ++l) {
-        float L[4][4];
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          float P[4][4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) P[r][c] = 0.f;
-          auto step = [&](int e) {
-            const float4 a = *reinterpret_cast<const float4 *>(As + e * TPAD + 4 * ty);
-            const float4 b = *reinterpret_cast<const float4 *>(Bs + e * TPAD + 4 * tx);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-              for (int c = 0; c < 4; ++c) P[r][c] = __fadd_rn(P[r][c], __fmul_rn(av[r], bv[c]));
-          };
-          for (int r = 0; r < full; ++r) step(32 * r + 8 * c4 + l);
-          if (c4 == 0)
-            for (int k = 4 * full; k < vs; ++k) step(8 * k + l);
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) L[r][c] = (c4 == 0) ? P[r][c] : __fadd_rn(L[r][c], P[r][c]);
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) S[r][c] = __fadd_rn(S[r][c], L[r][c]);
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          S[r][c] = thread_sum_aten(
-              [&](int e) { return __fmul_rn(As[e * TPAD + 4 * ty + r], Bs[e * TPAD + 4 * tx + c]); }, d);
-    }
+    tile_dots(As, Bs, d, ty, tx, S);
 
     // epilogue: m = fl(fl(x0*y0) - S), distance, then the mode's consumer
 #pragma unroll
@@ -257,6 +263,122 @@ __global__ void __launch_bounds__(NTHREADS) allpairs_tile_kernel(const Params p)
         o.count_hi = (uint32_t)(cnt >> 32);
         o.pad[0] = o.pad[1] = o.pad[2] = 0;
         *p.best = o;
+      }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Exact per-row k nearest neighbours: out[i][0..k) = the k smallest (d(i,j), j), j != i, ascending.
+// One CTA owns a 64-row tile and streams every column tile past it, so the per-row candidate lists
+// live in shared memory for the CTA's lifetime (no cross-CTA merging).  After each 64x64 tile the
+// distances go through shared memory to 64 "row owner" threads that run a threshold test against
+// the row's current k-th best and replace-max on the rare hit (expected k ln(V/k) inserts per row).
+// Key = d_bits << 32 | j  (d >= 0, so the bit pattern orders like the value; ties break on j).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxTopK = 64;
+
+__global__ void __launch_bounds__(NTHREADS)
+allpairs_topk_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D,
+                     float sqrt_c, float sgn, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d) {
+  extern __shared__ __align__(16) float smem[];
+  const int d = D - 1;
+  float *As = smem;
+  float *Bs = As + (size_t)d * TPAD;
+  float *a0 = Bs + (size_t)d * TPAD;
+  float *b0 = a0 + TM;
+  float *dist = b0 + TN;                                        // [64][65]
+  unsigned long long *lists = reinterpret_cast<unsigned long long *>(dist + TM * (TN + 1) + 1);  // [64][k]
+  lists = reinterpret_cast<unsigned long long *>(((uintptr_t)lists + 7) & ~(uintptr_t)7);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t col_tiles = (n + TN - 1) / TN;
+  const int64_t row_tiles = (nrows + TM - 1) / TM;
+  const unsigned long long kEmpty = 0xffffffffffffffffULL;
+
+  for (int64_t rt = blockIdx.x; rt < row_tiles; rt += gridDim.x) {
+    const int64_t i0 = row0 + rt * TM;
+    const int64_t i_end = (row0 + nrows < n) ? row0 + nrows : n;
+    __syncthreads();
+    // rows of this tile: [i0, i0+64) clipped to the shard
+    {
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+      for (int r = w; r < TM; r += NTHREADS / 32) {
+        const int64_t gr = i0 + r;
+        const bool ok = gr < i_end;
+        const float *row = E + (ok ? gr : 0) * ldE;
+        for (int kk = lane; kk < d; kk += 32) As[kk * TPAD + r] = ok ? row[1 + kk] : 0.f;
+        if (lane == 0) a0[r] = ok ? row[0] : 0.f;
+      }
+    }
+    for (int q = threadIdx.x; q < TM * k; q += NTHREADS) lists[q] = kEmpty;
+    // per-row running threshold (largest kept key) and its position: owner threads 0..63
+    unsigned long long worst = kEmpty;
+    int worst_pos = 0, filled = 0;
+
+    for (int64_t ct = 0; ct < col_tiles; ++ct) {
+      const int64_t j0 = ct * TN;
+      __syncthreads();
+      load_tile_T(E, ldE, n, j0, d, Bs, b0);
+      __syncthreads();
+      float S[4][4];
+      tile_dots(As, Bs, d, ty, tx, S);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float m = __fsub_rn(__fmul_rn(a0[4 * ty + r], b0[4 * tx + c]), S[r][c]);
+          dist[(4 * ty + r) * (TN + 1) + 4 * tx + c] = dist_from_mdot(m, sgn, sqrt_c);
+        }
+      __syncthreads();
+      if (threadIdx.x < TM) {
+        const int r = threadIdx.x;
+        const int64_t gi = i0 + r;
+        if (gi < i_end) {
+          unsigned long long *mine = lists + (size_t)r * k;
+          const int64_t jn = (j0 + TN < n) ? TN : n - j0;
+          for (int c = 0; c < (int)jn; ++c) {
+            const float dv = dist[r * (TN + 1) + c];
+            const int64_t gj = j0 + c;
+            if (!(dv == dv) || gj == gi) continue;
+            const unsigned long long key = ((unsigned long long)__float_as_uint(dv) << 32) | (unsigned int)gj;
+            if (filled < k) {
+              mine[filled++] = key;
+              if (filled == k) {
+                worst = 0;
+                for (int q = 0; q < k; ++q)
+                  if (mine[q] >= worst) { worst = mine[q]; worst_pos = q; }
+              }
+            } else if (key < worst) {
+              mine[worst_pos] = key;
+              worst = 0;
+              for (int q = 0; q < k; ++q)
+                if (mine[q] >= worst) { worst = mine[q]; worst_pos = q; }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // sort each row's list (insertion sort by its owner; k <= 64) and write out
+    if (threadIdx.x < TM) {
+      const int r = threadIdx.x;
+      const int64_t gi = i0 + r;
+      if (gi < i_end) {
+        unsigned long long *mine = lists + (size_t)r * k;
+        for (int a = 1; a < k; ++a) {
+          unsigned long long v = mine[a];
+          int bpos = a - 1;
+          while (bpos >= 0 && mine[bpos] > v) { mine[bpos + 1] = mine[bpos]; --bpos; }
+          mine[bpos + 1] = v;
+        }
+        const int64_t orow = gi - row0;
+        for (int q = 0; q < k; ++q) {
+          const unsigned long long v = mine[q];
+          const bool empty = v == kEmpty;
+          out_idx[orow * k + q] = empty ? -1 : (int32_t)(v & 0xffffffffu);
+          out_d[orow * k + q] = empty ? __int_as_float(0x7f800000) : __uint_as_float((unsigned int)(v >> 32));
+        }
       }
     }
   }
@@ -358,4 +480,37 @@ extern "C" int hyp_allpairs_emit(const float *E, int64_t ldE, int64_t n, int D, 
   p.capacity = capacity;
   p.emit_count = count;
   return launch_tiles<kEmit>(p, st, "hyp_allpairs_emit");
+}
+
+extern "C" int hyp_allpairs_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c,
+                                 int semantics, int k, int32_t *out_idx, float *out_d, void *stream) {
+  if (n < 0 || row0 < 0 || nrows < 0 || row0 + nrows > n || D < 2 || D > HYP_MAX_D || !(c > 0.f) || k < 1 ||
+      k > kMaxTopK) {
+    set_error("hyp_allpairs_topk: bad arguments (n=%lld row0=%lld nrows=%lld D=%d k=%d, k <= %d)", (long long)n,
+              (long long)row0, (long long)nrows, D, k, kMaxTopK);
+    return HYP_ERR_ARG;
+  }
+  if (nrows == 0) return HYP_OK;
+  if (!E || !out_idx || !out_d) return HYP_ERR_ARG;
+  const size_t smem = tile_smem_bytes(D) + ((size_t)TM * (TN + 1) + 4) * sizeof(float) + (size_t)TM * k * 8 + 16;
+  if (smem > 200 * 1024) {
+    set_error("hyp_allpairs_topk: D=%d k=%d needs %zu bytes of shared memory per CTA", D, k, smem);
+    return HYP_ERR_ARG;
+  }
+  cudaError_t e = cudaFuncSetAttribute(allpairs_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("hyp_allpairs_topk: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return HYP_ERR_CUDA;
+  }
+  int per_sm = 0, dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, allpairs_topk_kernel, NTHREADS, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t row_tiles = (nrows + TM - 1) / TM;
+  int64_t grid = (int64_t)sms * per_sm;
+  if (grid > row_tiles) grid = row_tiles;
+  allpairs_topk_kernel<<<(int)grid, NTHREADS, smem, (cudaStream_t)stream>>>(
+      E, ldE, n, row0, nrows, D, sqrtf(c), semantics == HYP_SEM_REFERENCE ? -1.f : 1.f, k, out_idx, out_d);
+  return check_launch("hyp_allpairs_topk");
 }

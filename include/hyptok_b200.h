@@ -109,6 +109,14 @@ int hyp_allpairs_emit(const float *E, int64_t ldE, int64_t n, int D, float c, in
                       float threshold, int32_t *out_i, int32_t *out_j, float *out_d,
                       int64_t capacity, unsigned long long *count, void *stream);
 
+/* Exact per-row nearest neighbours (what the reference asks FAISS for, fast_hyperbolic_merge.py:
+ * 301-304, hyperbolic_merge.py:217, but in the true Lorentz distance instead of Klein-L2 and
+ * without sampling): for every row i of the shard [row0, row0+nrows) the k smallest (d(i,j), j)
+ * over all j in [0,n), j != i, ascending; ties break on j.  out_idx/out_d are [nrows][k]
+ * (-1 / +inf padded when n-1 < k).  k <= 64.  Rows are independent: one shard per GPU. */
+int hyp_allpairs_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D,
+                      float c, int semantics, int k, int32_t *out_idx, float *out_d, void *stream);
+
 /* ---- K4/K5: incremental merge loop (hyperbolic_merge.py:309-412, the loop of
  * scripts/train_hyperbolic_tokenizer.py:236-283, fast_hyperbolic_merge.py:467-576) ------------
  * Device-resident state; the loop never leaves the GPU.  Because the reference never removes
@@ -159,6 +167,14 @@ int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float c, int sem
 int hyp_row_min(const float *E, int64_t ldE, int64_t n, int64_t row, int D, float c, int semantics,
                 float threshold, hyp_best *best, void *workspace, int64_t workspace_bytes,
                 void *stream);
+
+/* ---- K7: frequency-aware scoring, inner loop (frequency_aware_hyperbolic_merge.py:114-166) ---
+ * For each of C candidates: the UN-projected weighted midpoint of rows (idx_i, idx_j) (:139-141)
+ * and its distance to the S rows sample[c*S .. c*S+S) (:149-153); out[C][S].  The sample indices
+ * are drawn on the host with the reference's own torch.randperm calls. */
+int hyp_coherence_distances(const float *E, int64_t ldE, const int32_t *idx_i, const int32_t *idx_j,
+                            const int32_t *len_i, const int32_t *len_j, const int32_t *sample, int S,
+                            float *out, int64_t C, int D, float c, int semantics, void *stream);
 
 /* ---- K6: pair counting (frequency_aware_hyperbolic_merge.py:92-112) ----------------------- */
 /* Adjacent code-point pairs inside each `line.strip()` of a UTF-8 byte stream (16-byte aligned),
