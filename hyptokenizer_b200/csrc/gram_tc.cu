@@ -1,0 +1,557 @@
+// gram_tc.cu -- K2, tensor-core path: all-pairs Lorentz distance as a Gram GEMM on tcgen05 (sm_100a).
+//
+// Replaces the O(n^2 d) broadcast of embedding/lorentz_model.py:141-178 + the neighbour search the
+// reference delegates to FAISS (fast_hyperbolic_merge.py:301-304) for per-row top-k at large V.
+//
+//   S[i][j] = sum_k xs_i[k] xs_j[k]              tcgen05.mma kind::tf32, A/B tiles fed by TMA
+//                                                 (SWIZZLE_128B, K-major), fp32 accumulators in TMEM
+//   u~      = x0_i x0_j - S                       epilogue, fp32 (time-like term kept OUT of the MMA,
+//                                                 it would cost ~1e-4 in d)
+//   key     = max(sgn * u~, 1)                    clamped pre-acosh value; acosh is monotone, so the
+//                                                 order of keys is the order of distances
+//
+// TF32 keeps 10 mantissa bits of each operand, so |u~ - u| <= eps_i = 2^-9 |xs_i| max_j|xs_j| (+ fp32
+// accumulation slack).  The kernel therefore never DECIDES anything; it bounds and filters:
+//   pass 1  per row, the minimum key of every 128-column tile          -> tilemin[tile][row]
+//           (k distinct tiles' minima are k distinct elements, so the k-th smallest tile minimum is an
+//            upper bound tau_i of the row's true k-th smallest key; with V/128 tiles it is tight)
+//   select  tau_i = k-th smallest of the row's tile minima              (kth_select_kernel)
+//   pass 2  collect every column with key <= tau_i + 2 eps_i            -> cand[row][<= CAP]
+//           a certified superset of the exact top-k, typically k+3 entries
+//   finish  exact fp32 re-score of the candidates in ATen order (allpairs.cu arithmetic), sort by
+//           (d, j), emit k; rows whose candidate buffer overflowed are flagged and re-done by the exact
+//           CUDA-core kernel, so the result is ALWAYS the exact one.
+//
+// Warp roles per CTA (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
+// warps 2..5 epilogue (one thread per accumulator row = TMEM lane).  A CTA owns a 128-row block (its A
+// tile stays in shared memory) and streams all column tiles through a 2-stage B ring; accumulators are
+// double-buffered in TMEM (2 x 128 columns) so the epilogue of tile t overlaps the MMA of tile t+1.
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace hyp {
+
+constexpr int TC_M = 128;          // rows per CTA block (UMMA M)
+constexpr int TC_N = 128;          // columns per tile (UMMA N)
+constexpr int TC_KSLAB = 32;       // fp32 elements per 128-byte swizzle row
+constexpr int TC_SLAB_BYTES = TC_M * 128;   // 16 KiB: 128 rows x 128 B
+constexpr int TC_MAX_SLABS = 4;    // K padded up to 128
+constexpr int TC_STAGES = 2;
+constexpr int TC_THREADS = 192;
+constexpr int TC_CAP = 64;         // candidate capacity per row
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate, M=128, N=128, K=8 per instruction
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 in
+// [0,14), LBO >> 4 in [16,30) (unused for swizzled K-major, 1), SBO >> 4 in [32,46) = 1024 B between
+// 8-row groups, version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both,
+// N>>3 in [17,23), M>>4 in [24,29).
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
+                                ((uint32_t)(TC_M >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------
+// operand preparation: XP[r][0..Kp) = spatial part zero-padded, x0[r], nrm[r], max norm
+// ---------------------------------------------------------------------------------------------
+__global__ void tc_pack_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int D, int Kp,
+                               float *__restrict__ XP, float *__restrict__ x0, float *__restrict__ nrm,
+                               unsigned int *__restrict__ max_nrm_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const float *row = E + r * ldE;
+    float ss = 0.f;
+    for (int k = lane; k < Kp; k += 32) {
+      float v = (k < D - 1) ? row[1 + k] : 0.f;
+      XP[r * Kp + k] = v;
+      ss = fmaf(v, v, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(HYP_FULL_MASK, ss, o);
+    if (lane == 0) {
+      x0[r] = row[0];
+      float nr = sqrtf(ss);
+      nrm[r] = nr;
+      if (nr == nr) atomicMax(max_nrm_bits, __float_as_uint(nr));
+    }
+  }
+}
+
+struct TcParams {
+  int64_t n;          // table rows (columns of the Gram matrix)
+  int64_t row0;       // shard start
+  int64_t nrows;      // shard rows
+  int n_slabs;        // Kp / 32
+  int n_ksteps;       // ceil(d / 8) MMAs per tile
+  float sgn;
+  const float *x0;
+  // pass 1
+  float *tilemin;     // [col_tiles][ld_tm]
+  int64_t ld_tm;
+  // pass 2
+  const float *thr;   // [nrows] tau + 2 eps
+  int32_t *cand;      // [nrows][TC_CAP]
+  int32_t *cand_cnt;  // [nrows] (> TC_CAP == overflow)
+};
+
+template <int PASS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // layout: A slabs | B stage 0 slabs | B stage 1 slabs | colx0[2][128] | barriers | tmem ptr
+  uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *sA = base;
+  uint8_t *sB = sA + p.n_slabs * TC_SLAB_BYTES;
+  float *colx0 = reinterpret_cast<float *>(sB + TC_STAGES * p.n_slabs * TC_SLAB_BYTES);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(colx0 + 2 * TC_N);
+  uint64_t *a_full = bars + 0, *a_empty = bars + 1;
+  uint64_t *b_full = bars + 2, *b_empty = bars + 4;      // [2] each
+  uint64_t *acc_full = bars + 6, *acc_empty = bars + 8;  // [2] each
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row_blocks = (p.nrows + TC_M - 1) / TC_M;
+  const int64_t col_tiles = (p.n + TC_N - 1) / TC_N;
+  const uint32_t slab_tx = TC_SLAB_BYTES;
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_empty + s, 1);
+      mbar_init(acc_full + s, 1);
+      mbar_init(acc_empty + s, 4);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 2 * TC_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t bstage = 0, bphase = 0, aphase = 0;
+      for (int64_t rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
+        mbar_wait(a_empty, aphase ^ 1);
+        mbar_expect_tx(a_full, slab_tx * p.n_slabs);
+        for (int s = 0; s < p.n_slabs; ++s)
+          tma_load_2d(&tmap, a_full, sA + s * TC_SLAB_BYTES, s * TC_KSLAB, (int)(p.row0 + rb * TC_M));
+        aphase ^= 1;
+        for (int64_t ct = 0; ct < col_tiles; ++ct) {
+          mbar_wait(b_empty + bstage, bphase ^ 1);
+          mbar_expect_tx(b_full + bstage, slab_tx * p.n_slabs);
+          uint8_t *dst = sB + (size_t)bstage * p.n_slabs * TC_SLAB_BYTES;
+          for (int s = 0; s < p.n_slabs; ++s)
+            tma_load_2d(&tmap, b_full + bstage, dst + s * TC_SLAB_BYTES, s * TC_KSLAB, (int)(ct * TC_N));
+          if (++bstage == TC_STAGES) { bstage = 0; bphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      uint32_t bstage = 0, bphase = 0, aphase = 0, abuf = 0, accphase = 0;
+      for (int64_t rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
+        mbar_wait(a_full, aphase);
+        aphase ^= 1;
+        for (int64_t ct = 0; ct < col_tiles; ++ct) {
+          mbar_wait(b_full + bstage, bphase);
+          mbar_wait(acc_empty + abuf, accphase ^ 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA);
+          const uint32_t b_addr = smem_u32(sB + (size_t)bstage * p.n_slabs * TC_SLAB_BYTES);
+          const uint32_t d_addr = tmem_base + abuf * TC_N;
+          for (int ks = 0; ks < p.n_ksteps; ++ks) {
+            const int slab = ks >> 2, within = ks & 3;   // 4 k-steps of 8 fp32 (32 B) per 128-byte swizzle row
+            const uint64_t ad = smem_desc_sw128(a_addr + slab * TC_SLAB_BYTES + within * 32);
+            const uint64_t bd = smem_desc_sw128(b_addr + slab * TC_SLAB_BYTES + within * 32);
+            umma_tf32(d_addr, ad, bd, kIdescTf32, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(b_empty + bstage);     // B stage reusable once these MMAs have read it
+          umma_commit(acc_full + abuf);      // accumulator ready for the epilogue
+          if (++bstage == TC_STAGES) { bstage = 0; bphase ^= 1; }
+          if (++abuf == 2) { abuf = 0; accphase ^= 1; }
+        }
+        umma_commit(a_empty);                // A tile reusable
+      }
+    }
+  } else {
+    // ================= epilogue: warps 2..5, thread <-> accumulator row =================
+    const int lane_base = 32 * (warp & 3);          // TMEM lanes this warp may read
+    const int r_in_block = lane_base + lane;
+    const int ep_tid = r_in_block;                   // 0..127, a permutation over the 4 warps
+    uint32_t abuf = 0, accphase = 0;
+    for (int64_t rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
+      const int64_t gi = p.row0 + rb * TC_M + r_in_block;
+      const bool row_ok = gi < p.row0 + p.nrows;
+      const float x0i = row_ok ? __ldg(p.x0 + gi) : 0.f;
+      float thr = 0.f;
+      int cnt = 0;
+      if (PASS == 2) thr = row_ok ? __ldg(p.thr + (gi - p.row0)) : -1.f;
+      for (int64_t ct = 0; ct < col_tiles; ++ct) {
+        const int64_t j0 = ct * TC_N;
+        // stage the tile's time components (double-buffered with the accumulator)
+        {
+          const int64_t gj = j0 + ep_tid;
+          colx0[abuf * TC_N + ep_tid] = gj < p.n ? __ldg(p.x0 + gj) : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(acc_full + abuf, accphase);
+        tc_fence_after();
+        float tmin = __int_as_float(0x7f800000);
+        const float *cx = colx0 + abuf * TC_N;
+#pragma unroll 1
+        for (int chunk = 0; chunk < TC_N / 32; ++chunk) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + abuf * TC_N + chunk * 32, v);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int64_t gj = j0 + chunk * 32 + c;
+            float u = fmaf(x0i, cx[chunk * 32 + c], -v[c]);
+            u = p.sgn < 0.f ? -u : u;
+            float key = (u < 1.0f) ? 1.0f : u;                 // NaN stays NaN
+            const bool ok = (key == key) && gj < p.n && gj != gi;
+            if (PASS == 1) {
+              if (ok) tmin = fminf(tmin, key);
+            } else {
+              if (ok && key <= thr) {
+                if (cnt < TC_CAP) p.cand[(gi - p.row0) * TC_CAP + cnt] = (int32_t)gj;
+                ++cnt;
+              }
+            }
+          }
+        }
+        // release the accumulator buffer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + abuf);
+        if (PASS == 1 && row_ok) p.tilemin[ct * p.ld_tm + (gi - p.row0)] = tmin;
+        if (++abuf == 2) { abuf = 0; accphase ^= 1; }
+      }
+      if (PASS == 2 && row_ok) p.cand_cnt[gi - p.row0] = cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 2 * TC_N);
+  }
+}
+
+// tau_i = k-th smallest tile minimum of row i (thread per row, coalesced over rows), then
+// thr_i = tau_i + 2 eps_i with eps_i = 2^-9 * 1.05 * |xs_i| * max|xs| + 2e-6 * max(1, tau_i)
+__global__ void kth_select_kernel(const float *__restrict__ tilemin, int64_t ld_tm, int64_t col_tiles, int64_t nrows,
+                                  int64_t row0, int k, const float *__restrict__ nrm,
+                                  const unsigned int *__restrict__ max_nrm_bits, float *__restrict__ thr) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  float best[64];
+  const float inf = __int_as_float(0x7f800000);
+  for (int q = 0; q < k; ++q) best[q] = inf;
+  float worst = inf;
+  int wpos = 0;
+  for (int64_t t = 0; t < col_tiles; ++t) {
+    const float v = tilemin[t * ld_tm + r];
+    if (v < worst) {
+      best[wpos] = v;
+      worst = -1.f;
+      for (int q = 0; q < k; ++q)
+        if (best[q] >= worst) { worst = best[q]; wpos = q; }
+    }
+  }
+  const float tau = worst;     // +inf when fewer than k tiles hold a finite minimum
+  const float eps = 0.001953125f * 1.05f * nrm[row0 + r] * __uint_as_float(*max_nrm_bits) + 2e-6f * fmaxf(1.f, tau);
+  thr[r] = tau + 2.f * eps;
+}
+
+// exact fp32 re-score of each row's candidates (ATen order), sort by (d, j), write the first k.
+// One warp per row.  flags[r] = 1 when the candidate buffer overflowed (row must be redone exactly).
+__global__ void __launch_bounds__(128)
+tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, int64_t nrows, float sqrt_c, float sgn,
+                 int k, const int32_t *__restrict__ cand, const int32_t *__restrict__ cand_cnt,
+                 int32_t *__restrict__ out_idx, float *__restrict__ out_d, int32_t *__restrict__ flags) {
+  __shared__ unsigned long long keys[4][TC_CAP];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned long long kEmpty = 0xffffffffffffffffULL;
+  for (int64_t r = (int64_t)blockIdx.x * 4 + w; r < nrows; r += (int64_t)gridDim.x * 4) {
+    const int cnt = cand_cnt[r];
+    const bool overflow = cnt > TC_CAP || cnt < 0;
+    const int m = overflow ? 0 : cnt;
+    for (int q = lane; q < TC_CAP; q += 32) keys[w][q] = kEmpty;
+    __syncwarp();
+    const float *xi = E + (row0 + r) * ldE;
+    for (int q = 0; q < m; ++q) {
+      const int j = cand[r * TC_CAP + q];
+      const float mm = warp_mdot(xi, E + (int64_t)j * ldE, D, lane);
+      if (lane == 0) {
+        const float dv = dist_from_mdot(mm, sgn, sqrt_c);
+        if (dv == dv) keys[w][q] = ((unsigned long long)__float_as_uint(dv) << 32) | (unsigned int)j;
+      }
+    }
+    __syncwarp();
+    // rank sort: TC_CAP = 64 keys, two per lane, all keys distinct (distinct j)
+    for (int q = lane; q < TC_CAP; q += 32) {
+      const unsigned long long mine = keys[w][q];
+      if (mine == kEmpty) continue;
+      int rank = 0;
+      for (int t = 0; t < TC_CAP; ++t) rank += keys[w][t] < mine;
+      if (rank < k) {
+        out_idx[r * k + rank] = (int32_t)(mine & 0xffffffffu);
+        out_d[r * k + rank] = __uint_as_float((unsigned int)(mine >> 32));
+      }
+    }
+    // pad (fewer than k valid candidates can only happen with < k finite distances in the row)
+    int valid = 0;
+    for (int t = lane; t < TC_CAP; t += 32) valid += keys[w][t] != kEmpty;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(HYP_FULL_MASK, valid, o);
+    for (int q = valid + lane; q < k; q += 32) {
+      out_idx[r * k + q] = -1;
+      out_d[r * k + q] = __int_as_float(0x7f800000);
+    }
+    if (lane == 0) flags[r] = overflow ? 1 : 0;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+struct TcLayout {
+  int Kp, n_slabs, n_ksteps;
+  int64_t ld_tm, col_tiles;
+  size_t off_xp, off_x0, off_nrm, off_max, off_tilemin, off_thr, off_cand, off_cnt, off_flags, total;
+};
+
+static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
+  TcLayout L;
+  const int d = D - 1;
+  L.Kp = ((d + TC_KSLAB - 1) / TC_KSLAB) * TC_KSLAB;
+  L.n_slabs = L.Kp / TC_KSLAB;
+  L.n_ksteps = (d + 7) / 8;
+  L.col_tiles = (n + TC_N - 1) / TC_N;
+  L.ld_tm = ((nrows + 31) / 32) * 32;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
+  L.off_xp = take((size_t)n * L.Kp * 4);
+  L.off_x0 = take((size_t)n * 4);
+  L.off_nrm = take((size_t)n * 4);
+  L.off_max = take(256);
+  L.off_tilemin = take((size_t)L.col_tiles * L.ld_tm * 4);
+  L.off_thr = take((size_t)nrows * 4);
+  L.off_cand = take((size_t)nrows * TC_CAP * 4);
+  L.off_cnt = take((size_t)nrows * 4);
+  L.off_flags = take((size_t)nrows * 4);
+  L.total = o;
+  return L;
+}
+
+}  // namespace hyp
+
+using namespace hyp;
+
+extern "C" int64_t hyp_gram_topk_workspace_bytes(int64_t n, int64_t nrows, int D) {
+  if (n < 0 || nrows < 0 || D < 2 || D - 1 > TC_MAX_SLABS * TC_KSLAB) return -1;
+  return (int64_t)tc_layout(n, nrows, D).total;
+}
+
+extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c,
+                             int semantics, int k, int32_t *out_idx, float *out_d, int32_t *row_flags, void *workspace,
+                             int64_t workspace_bytes, void *stream) {
+  if (n < 0 || row0 < 0 || nrows < 0 || row0 + nrows > n || D < 2 || !(c > 0.f) || k < 1 || k > TC_CAP / 2) {
+    set_error("hyp_gram_topk: bad arguments (n=%lld row0=%lld nrows=%lld D=%d k=%d, k <= %d)", (long long)n,
+              (long long)row0, (long long)nrows, D, k, TC_CAP / 2);
+    return HYP_ERR_ARG;
+  }
+  if (D - 1 > TC_MAX_SLABS * TC_KSLAB) {
+    set_error("hyp_gram_topk: d=%d exceeds the %d columns one shared-memory A tile holds", D - 1,
+              TC_MAX_SLABS * TC_KSLAB);
+    return HYP_ERR_UNSUPPORTED;
+  }
+  if (nrows == 0) return HYP_OK;
+  if (!E || !out_idx || !out_d || !row_flags || !workspace) return HYP_ERR_ARG;
+  const TcLayout L = tc_layout(n, nrows, D);
+  if (workspace_bytes < (int64_t)L.total) {
+    set_error("hyp_gram_topk: workspace %lld < %zu bytes", (long long)workspace_bytes, L.total);
+    return HYP_ERR_WORKSPACE;
+  }
+  if (((uintptr_t)workspace & 255) != 0) {
+    set_error("hyp_gram_topk: workspace must be 256-byte aligned");
+    return HYP_ERR_ARG;
+  }
+  EncodeTiledFn encode = get_encode();
+  if (!encode) {
+    set_error("hyp_gram_topk: cuTensorMapEncodeTiled is unavailable in this driver");
+    return HYP_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t *ws = (uint8_t *)workspace;
+  float *XP = (float *)(ws + L.off_xp), *x0 = (float *)(ws + L.off_x0), *nrm = (float *)(ws + L.off_nrm);
+  unsigned int *maxn = (unsigned int *)(ws + L.off_max);
+  float *tilemin = (float *)(ws + L.off_tilemin), *thr = (float *)(ws + L.off_thr);
+  int32_t *cand = (int32_t *)(ws + L.off_cand), *cnt = (int32_t *)(ws + L.off_cnt);
+
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+  cudaMemsetAsync(maxn, 0, 4, st);
+  tc_pack_kernel<<<sms * 4, 256, 0, st>>>(E, ldE, n, D, L.Kp, XP, x0, nrm, maxn);
+  int rc = check_launch("hyp_gram_topk(pack)");
+  if (rc) return rc;
+
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)L.Kp, (cuuint64_t)n};
+  const cuuint64_t gstride[1] = {(cuuint64_t)L.Kp * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_KSLAB, (cuuint32_t)TC_M};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)XP, gdim, gstride, box, estride,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("hyp_gram_topk: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return HYP_ERR_CUDA;
+  }
+
+  TcParams p{};
+  p.n = n; p.row0 = row0; p.nrows = nrows; p.n_slabs = L.n_slabs; p.n_ksteps = L.n_ksteps;
+  p.sgn = semantics == HYP_SEM_REFERENCE ? -1.f : 1.f;
+  p.x0 = x0; p.tilemin = tilemin; p.ld_tm = L.ld_tm; p.thr = thr; p.cand = cand; p.cand_cnt = cnt;
+  const size_t smem = 1024 + (size_t)(1 + TC_STAGES) * L.n_slabs * TC_SLAB_BYTES + 2 * TC_N * 4 + 16 * 8;
+  cudaFuncSetAttribute(gram_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(gram_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int64_t row_blocks = (nrows + TC_M - 1) / TC_M;
+  const int grid = (int)(row_blocks < sms ? row_blocks : sms);
+
+  gram_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(tmap, p);
+  rc = check_launch("hyp_gram_topk(pass 1)");
+  if (rc) return rc;
+  kth_select_kernel<<<(int)((nrows + 127) / 128), 128, 0, st>>>(tilemin, L.ld_tm, L.col_tiles, nrows, row0, k, nrm, maxn,
+                                                                thr);
+  rc = check_launch("hyp_gram_topk(select)");
+  if (rc) return rc;
+  gram_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(tmap, p);
+  rc = check_launch("hyp_gram_topk(pass 2)");
+  if (rc) return rc;
+  int64_t fb = (nrows + 3) / 4;
+  if (fb > sms * 16) fb = sms * 16;
+  tc_finish_kernel<<<(int)fb, 128, 0, st>>>(E, ldE, D, row0, nrows, sqrtf(c), p.sgn, k, cand, cnt, out_idx, out_d,
+                                           row_flags);
+  return check_launch("hyp_gram_topk(finish)");
+}

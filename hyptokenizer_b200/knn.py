@@ -43,11 +43,35 @@ def lorentz_topk(E: torch.Tensor, k: int = 32, c: float = 1.0, semantics: Option
     sem = SEM[LM.get_semantics() if semantics is None else semantics]
     idx = torch.empty((nrows, k), dtype=torch.int32, device=E.device)
     d = torch.empty((nrows, k), dtype=torch.float32, device=E.device)
-    if engine != "exact":
-        raise ValueError("engine must be 'exact'")
+    L = _lib.lib()
+    if engine == "auto":
+        engine = "tc" if (n >= 8192 and k <= 32 and E.shape[1] - 1 <= 128 and sem == SEM["lorentz"]) else "exact"
+    if engine == "exact":
+        with torch.cuda.device(E.device):
+            check(L.hyp_allpairs_topk(ptr(E), E.stride(0), n, row0, nrows, E.shape[1], float(c), sem, k,
+                                      ptr(idx), ptr(d), stream_ptr()))
+        return idx, d
+    if engine != "tc":
+        raise ValueError("engine must be 'exact', 'tc' or 'auto'")
+    nbytes = L.hyp_gram_topk_workspace_bytes(n, nrows, E.shape[1])
+    if nbytes < 0:
+        raise ValueError("tensor-core path supports d <= 128")
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=E.device)
+    off = (-ws.data_ptr()) % 256
+    flags = torch.empty(nrows, dtype=torch.int32, device=E.device)
     with torch.cuda.device(E.device):
-        check(_lib.lib().hyp_allpairs_topk(ptr(E), E.stride(0), n, row0, nrows, E.shape[1], float(c), sem, k,
-                                           ptr(idx), ptr(d), stream_ptr()))
+        check(L.hyp_gram_topk(ptr(E), E.stride(0), n, row0, nrows, E.shape[1], float(c), sem, k, ptr(idx), ptr(d),
+                              ptr(flags), ws.data_ptr() + off, nbytes, stream_ptr()))
+        bad = flags.nonzero(as_tuple=True)[0]
+        lorentz_topk.last_flagged = int(bad.numel())
+        if bad.numel() > max(64, nrows // 8):
+            # ties everywhere (e.g. the shipped semantics, where every distance is 0): exact path for the shard
+            check(L.hyp_allpairs_topk(ptr(E), E.stride(0), n, row0, nrows, E.shape[1], float(c), sem, k,
+                                      ptr(idx), ptr(d), stream_ptr()))
+        else:
+            for r in bad.tolist():
+                check(L.hyp_allpairs_topk(ptr(E), E.stride(0), n, row0 + r, 1, E.shape[1], float(c), sem, k,
+                                          idx[r].data_ptr(), d[r].data_ptr(), stream_ptr()))
     return idx, d
 
 
@@ -89,11 +113,11 @@ def best_pair_from_topk(idx: torch.Tensor, d: torch.Tensor) -> Tuple[int, int, f
 
 
 def lorentz_topk_sharded(E: torch.Tensor, k: int = 32, c: float = 1.0, semantics: Optional[str] = None,
-                         n: Optional[int] = None, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                         n: Optional[int] = None, group=None, engine: str = "exact") -> Tuple[torch.Tensor, torch.Tensor]:
     """Row-sharded all-pairs top-k: local shard on this GPU, one all-gather, full lists everywhere."""
     n = E.shape[0] if n is None else n
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return lorentz_topk(E, k, c, semantics, n)
+        return lorentz_topk(E, k, c, semantics, n, engine=engine)
     row0, nrows, _ = shard_rows(n, dist.get_world_size(group), dist.get_rank(group))
-    li, ld = lorentz_topk(E, k, c, semantics, n, row0, nrows)
+    li, ld = lorentz_topk(E, k, c, semantics, n, row0, nrows, engine=engine)
     return gather_topk(li, ld, n, group)

@@ -117,6 +117,18 @@ int hyp_allpairs_emit(const float *E, int64_t ldE, int64_t n, int D, float c, in
 int hyp_allpairs_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D,
                       float c, int semantics, int k, int32_t *out_idx, float *out_d, void *stream);
 
+/* ---- K2 (tensor-core path): the same per-row top-k through a tcgen05 TF32 Gram GEMM ----------
+ * (TMA-fed tiles, TMEM accumulators, fused x0_i*x0_j - S / sign / clamp epilogue), used as a
+ * certified FILTER: two GEMM passes bound each row's k-th best and collect a provable superset of
+ * the exact top-k, which is re-scored in fp32 (ATen order) and sorted.  Results are bit-identical
+ * to hyp_allpairs_topk for every row whose row_flags[r] == 0; rows with row_flags[r] != 0 (candidate
+ * buffer overflow: massive ties, e.g. the shipped semantics where every distance is 0) must be
+ * recomputed with hyp_allpairs_topk by the caller.  k <= 32, d <= 128.  workspace 256-B aligned. */
+int64_t hyp_gram_topk_workspace_bytes(int64_t n, int64_t nrows, int D);
+int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c,
+                  int semantics, int k, int32_t *out_idx, float *out_d, int32_t *row_flags,
+                  void *workspace, int64_t workspace_bytes, void *stream);
+
 /* ---- K4/K5: incremental merge loop (hyperbolic_merge.py:309-412, the loop of
  * scripts/train_hyperbolic_tokenizer.py:236-283, fast_hyperbolic_merge.py:467-576) ------------
  * Device-resident state; the loop never leaves the GPU.  Because the reference never removes
