@@ -51,6 +51,10 @@ def parse():
     ap.add_argument("--v0", type=int, default=V0)
     ap.add_argument("--target", type=int, default=TARGET)
     ap.add_argument("--dim", type=int, default=D_EMB)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2: merge loop (headline, merges/s); c3: all-pairs Lorentz distance + top-k=32 over V=100k, "
+                         "row-sharded over the ranks with an all-gather (TFLOP/s)")
+    ap.add_argument("--engine", default="tc", choices=["tc", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -336,9 +340,108 @@ def run_reference(a):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------
+# config 3: all-pairs Lorentz distance + top-k over V=100k, row-sharded, all-gather of the lists
+# ------------------------------------------------------------------------------------------------
+def run_c3(a):
+    import torch.distributed as dist
+    from hyptokenizer_b200 import _lib, knn
+    from hyptokenizer_b200._lib import SEM, check, ptr
+    from hyptokenizer_b200.synth import synthetic_embeddings
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    _lib.check_device(dev)
+    V, d, k = 100000, a.dim, 32
+    D = d + 1
+    sem = SEM[a.semantics]
+    E = synthetic_embeddings(V, d, scale=SCALE, seed=42).to(dev)       # every rank holds all columns
+    row0, nrows, per = knn.shard_rows(V, world, rank)
+    idx = torch.empty((per, k), dtype=torch.int32, device=dev)
+    dd = torch.empty((per, k), dtype=torch.float32, device=dev)
+    all_i = torch.empty((world * per, k), dtype=torch.int32, device=dev)
+    all_d = torch.empty((world * per, k), dtype=torch.float32, device=dev)
+    flags = torch.zeros(per, dtype=torch.int32, device=dev)
+    nbytes = L.hyp_gram_topk_workspace_bytes(V, nrows, D)
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    wsp = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+
+    def step():
+        flush.fill_(1)
+        e0.record(stream)
+        if a.engine == "tc":
+            check(L.hyp_gram_topk(ptr(E), D, V, row0, nrows, D, 1.0, sem, k, ptr(idx), ptr(dd), ptr(flags), wsp, nbytes, sp))
+        else:
+            check(L.hyp_allpairs_topk(ptr(E), D, V, row0, nrows, D, 1.0, sem, k, ptr(idx), ptr(dd), sp))
+        e1.record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(all_i, idx)
+            dist.all_gather_into_tensor(all_d, dd)
+        e2.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e2), e0.elapsed_time(e1)
+
+    for _ in range(a.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    tot, ker = [], []
+    for _ in range(a.steps):
+        t, t1 = step()
+        tot.append(t)
+        ker.append(t1)
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    flagged = int(flags[:nrows].sum().item())
+    tmax = torch.tensor([sum(tot)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        flops = 2.0 * V * V * D                                      # one full distance matrix
+        secs = float(tmax.item()) * 1e-3 / a.steps
+        pk, kind = peaks()
+        kern_s = float(np.mean(ker)) * 1e-3
+        shard_flops = 2.0 * nrows * V * D
+        tf32_peak = pk.get("bf16_tflops", 1590.0) / 2.0               # TF32 dense = half the bf16 rate
+        line = {"metric": "all-pairs Lorentz dist TFLOP/s (V=100k,d=100,top-k=32)", "value": flops / secs / 1e12,
+                "unit": "TFLOP/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": secs * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "tf32+f32 rescore",
+                "data": "synthetic",
+                "config": {"workload": f"c3: all-pairs Lorentz distance + top-{k}, V={V}, d={d}, rows sharded over "
+                                       f"{world} GPU(s), all-gather of the (V/G, k) lists", "engine": a.engine,
+                           "semantics": a.semantics, "rows_flagged_for_exact_redo": flagged,
+                           "l2": "flushed between timed steps"},
+                "gpu_launches": (5 if a.engine == "tc" else 1) * a.steps,
+                "roofline": {"bound": "tensor", "kernel": "gram_tc_kernel x2 (+pack/select/finish)",
+                             "achieved": 2.0 * shard_flops / kern_s / 1e12 if a.engine == "tc" else shard_flops / kern_s / 1e12,
+                             "peak": tf32_peak, "unit": "TFLOP/s",
+                             "frac": (2.0 * shard_flops / kern_s / 1e12 if a.engine == "tc" else shard_flops / kern_s / 1e12) / tf32_peak,
+                             "traffic": None, "peak_kind": kind + " bf16/2",
+                             "note": "hardware FLOPs: the tc engine runs the Gram GEMM twice (bound pass + collect pass); "
+                                     "`value` counts the algorithmic 2*V^2*(d+1) once"},
+                "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c3":
+        run_c3(args)
     else:
         run_ours(args)

@@ -22,8 +22,8 @@
 //           (d, j), emit k; rows whose candidate buffer overflowed are flagged and re-done by the exact
 //           CUDA-core kernel, so the result is ALWAYS the exact one.
 //
-// Warp roles per CTA (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
-// warps 2..5 epilogue (one thread per accumulator row = TMEM lane).  A CTA owns a 128-row block (its A
+// Warp roles per CTA (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
+// warps 2..9 epilogue (one thread per accumulator row = TMEM lane and 64-column half of the tile).  A CTA owns a 128-row block (its A
 // tile stays in shared memory) and streams all column tiles through a 2-stage B ring; accumulators are
 // double-buffered in TMEM (2 x 128 columns) so the epilogue of tile t overlaps the MMA of tile t+1.
 #include <cuda.h>
@@ -39,8 +39,11 @@ constexpr int TC_KSLAB = 32;       // fp32 elements per 128-byte swizzle row
 constexpr int TC_SLAB_BYTES = TC_M * 128;   // 16 KiB: 128 rows x 128 B
 constexpr int TC_MAX_SLABS = 4;    // K padded up to 128
 constexpr int TC_STAGES = 2;
-constexpr int TC_THREADS = 192;
-constexpr int TC_CAP = 64;         // candidate capacity per row
+constexpr int TC_EPI_WARPS = 8;    // 2 per TMEM lane quadrant: each handles one 64-column half of the tile
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_HALF = TC_N / 2;
+constexpr int TC_CAPH = 48;        // candidate capacity per row and column half
+constexpr int TC_CAP = 2 * TC_CAPH;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -187,7 +190,7 @@ struct TcParams {
   int32_t *cand_cnt;  // [nrows] (> TC_CAP == overflow)
 };
 
-template <int PASS>
+template <int PASS, bool SGN_POS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -214,7 +217,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       mbar_init(b_full + s, 1);
       mbar_init(b_empty + s, 1);
       mbar_init(acc_full + s, 1);
-      mbar_init(acc_empty + s, 4);   // one arrival per epilogue warp
+      mbar_init(acc_empty + s, TC_EPI_WARPS);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -273,46 +276,71 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       }
     }
   } else {
-    // ================= epilogue: warps 2..5, thread <-> accumulator row =================
-    const int lane_base = 32 * (warp & 3);          // TMEM lanes this warp may read
+    // ================= epilogue: warps 2..9; thread <-> (accumulator row, 64-column half) =============
+    // u' = sgn * (x0_i x0_j - S).  Pass 1 keeps min(u') per half tile (fminf drops NaN operands, and
+    // min_j max(u',1) == max(min_j u', 1), so the clamp is applied once per tile).  Pass 2 tests u' <= thr_i
+    // (thr_i >= 1, so the clamped region always passes) into a 32-bit hit mask and only walks set bits.
+    // Tiles that contain out-of-range columns or the row block's own diagonal take the checked path.
+    const int quad = warp & 3;                       // TMEM lanes [32*quad, +32) are readable by this warp
+    const int half = (warp - 2) >> 2;                // column half of the tile
+    const int lane_base = 32 * quad;
     const int r_in_block = lane_base + lane;
-    const int ep_tid = r_in_block;                   // 0..127, a permutation over the 4 warps
+    const int ep_tid = (warp - 2) * 32 + lane;       // 0..255
+    const float inf = __int_as_float(0x7f800000);
     uint32_t abuf = 0, accphase = 0;
     for (int64_t rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
-      const int64_t gi = p.row0 + rb * TC_M + r_in_block;
+      const int64_t blk0 = p.row0 + rb * TC_M;
+      const int64_t gi = blk0 + r_in_block;
       const bool row_ok = gi < p.row0 + p.nrows;
       const float x0i = row_ok ? __ldg(p.x0 + gi) : 0.f;
+      const float xs = SGN_POS ? x0i : -x0i;
       float thr = 0.f;
       int cnt = 0;
       if (PASS == 2) thr = row_ok ? __ldg(p.thr + (gi - p.row0)) : -1.f;
+      int32_t *my_cand = p.cand + ((gi - p.row0) * 2 + half) * TC_CAPH;
       for (int64_t ct = 0; ct < col_tiles; ++ct) {
         const int64_t j0 = ct * TC_N;
-        // stage the tile's time components (double-buffered with the accumulator)
-        {
+        if (ep_tid < TC_N) {
           const int64_t gj = j0 + ep_tid;
           colx0[abuf * TC_N + ep_tid] = gj < p.n ? __ldg(p.x0 + gj) : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait(acc_full + abuf, accphase);
         tc_fence_after();
-        float tmin = __int_as_float(0x7f800000);
-        const float *cx = colx0 + abuf * TC_N;
+        const bool checked = (j0 + TC_N > p.n) || (j0 < blk0 + TC_M && j0 + TC_N > blk0);
+        const float *cx = colx0 + abuf * TC_N + half * TC_HALF;
+        const int64_t jh = j0 + half * TC_HALF;
+        float tmin = inf;
 #pragma unroll 1
-        for (int chunk = 0; chunk < TC_N / 32; ++chunk) {
+        for (int chunk = 0; chunk < TC_HALF / 32; ++chunk) {
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + abuf * TC_N + chunk * 32, v);
+          tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + abuf * TC_N + half * TC_HALF + chunk * 32, v);
+          const float *cxc = cx + chunk * 32;
+          if (PASS == 1) {
+            if (!checked) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int64_t gj = j0 + chunk * 32 + c;
-            float u = fmaf(x0i, cx[chunk * 32 + c], -v[c]);
-            u = p.sgn < 0.f ? -u : u;
-            float key = (u < 1.0f) ? 1.0f : u;                 // NaN stays NaN
-            const bool ok = (key == key) && gj < p.n && gj != gi;
-            if (PASS == 1) {
-              if (ok) tmin = fminf(tmin, key);
+              for (int c = 0; c < 32; ++c) tmin = fminf(tmin, SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]));
             } else {
-              if (ok && key <= thr) {
-                if (cnt < TC_CAP) p.cand[(gi - p.row0) * TC_CAP + cnt] = (int32_t)gj;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const int64_t gj = jh + chunk * 32 + c;
+                const float u = SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]);
+                if (gj < p.n && gj != gi) tmin = fminf(tmin, u);
+              }
+            }
+          } else {
+            uint32_t hits = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float u = SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]);
+              hits |= (u <= thr ? 1u : 0u) << c;
+            }
+            while (hits) {
+              const int c = __ffs(hits) - 1;
+              hits &= hits - 1;
+              const int64_t gj = jh + chunk * 32 + c;
+              if (!checked || (gj < p.n && gj != gi)) {
+                if (cnt < TC_CAPH) my_cand[cnt] = (int32_t)gj;
                 ++cnt;
               }
             }
@@ -322,10 +350,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + abuf);
-        if (PASS == 1 && row_ok) p.tilemin[ct * p.ld_tm + (gi - p.row0)] = tmin;
+        if (PASS == 1 && row_ok) p.tilemin[(2 * ct + half) * p.ld_tm + (gi - p.row0)] = fmaxf(tmin, 1.0f);
         if (++abuf == 2) { abuf = 0; accphase ^= 1; }
       }
-      if (PASS == 2 && row_ok) p.cand_cnt[gi - p.row0] = cnt;
+      if (PASS == 2 && row_ok) p.cand_cnt[(gi - p.row0) * 2 + half] = cnt;
     }
   }
 
@@ -373,14 +401,14 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned long long kEmpty = 0xffffffffffffffffULL;
   for (int64_t r = (int64_t)blockIdx.x * 4 + w; r < nrows; r += (int64_t)gridDim.x * 4) {
-    const int cnt = cand_cnt[r];
-    const bool overflow = cnt > TC_CAP || cnt < 0;
-    const int m = overflow ? 0 : cnt;
+    const int c0 = cand_cnt[2 * r], c1 = cand_cnt[2 * r + 1];
+    const bool overflow = c0 > TC_CAPH || c1 > TC_CAPH || c0 < 0 || c1 < 0;
+    const int m0 = overflow ? 0 : c0, m1 = overflow ? 0 : c1;
     for (int q = lane; q < TC_CAP; q += 32) keys[w][q] = kEmpty;
     __syncwarp();
     const float *xi = E + (row0 + r) * ldE;
-    for (int q = 0; q < m; ++q) {
-      const int j = cand[r * TC_CAP + q];
+    for (int q = 0; q < m0 + m1; ++q) {
+      const int j = q < m0 ? cand[(2 * r) * TC_CAPH + q] : cand[(2 * r + 1) * TC_CAPH + (q - m0)];
       const float mm = warp_mdot(xi, E + (int64_t)j * ldE, D, lane);
       if (lane == 0) {
         const float dv = dist_from_mdot(mm, sgn, sqrt_c);
@@ -388,7 +416,7 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
       }
     }
     __syncwarp();
-    // rank sort: TC_CAP = 64 keys, two per lane, all keys distinct (distinct j)
+    // rank sort of up to TC_CAP keys, all distinct (distinct j)
     for (int q = lane; q < TC_CAP; q += 32) {
       const unsigned long long mine = keys[w][q];
       if (mine == kEmpty) continue;
@@ -453,10 +481,10 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
   L.off_x0 = take((size_t)n * 4);
   L.off_nrm = take((size_t)n * 4);
   L.off_max = take(256);
-  L.off_tilemin = take((size_t)L.col_tiles * L.ld_tm * 4);
+  L.off_tilemin = take((size_t)2 * L.col_tiles * L.ld_tm * 4);
   L.off_thr = take((size_t)nrows * 4);
   L.off_cand = take((size_t)nrows * TC_CAP * 4);
-  L.off_cnt = take((size_t)nrows * 4);
+  L.off_cnt = take((size_t)nrows * 2 * 4);
   L.off_flags = take((size_t)nrows * 4);
   L.total = o;
   return L;
@@ -474,9 +502,9 @@ extern "C" int64_t hyp_gram_topk_workspace_bytes(int64_t n, int64_t nrows, int D
 extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c,
                              int semantics, int k, int32_t *out_idx, float *out_d, int32_t *row_flags, void *workspace,
                              int64_t workspace_bytes, void *stream) {
-  if (n < 0 || row0 < 0 || nrows < 0 || row0 + nrows > n || D < 2 || !(c > 0.f) || k < 1 || k > TC_CAP / 2) {
+  if (n < 0 || row0 < 0 || nrows < 0 || row0 + nrows > n || D < 2 || !(c > 0.f) || k < 1 || k > 32) {
     set_error("hyp_gram_topk: bad arguments (n=%lld row0=%lld nrows=%lld D=%d k=%d, k <= %d)", (long long)n,
-              (long long)row0, (long long)nrows, D, k, TC_CAP / 2);
+              (long long)row0, (long long)nrows, D, k, 32);
     return HYP_ERR_ARG;
   }
   if (D - 1 > TC_MAX_SLABS * TC_KSLAB) {
@@ -534,19 +562,22 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   p.sgn = semantics == HYP_SEM_REFERENCE ? -1.f : 1.f;
   p.x0 = x0; p.tilemin = tilemin; p.ld_tm = L.ld_tm; p.thr = thr; p.cand = cand; p.cand_cnt = cnt;
   const size_t smem = 1024 + (size_t)(1 + TC_STAGES) * L.n_slabs * TC_SLAB_BYTES + 2 * TC_N * 4 + 16 * 8;
-  cudaFuncSetAttribute(gram_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(gram_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool pos = p.sgn > 0.f;
+  auto k1 = pos ? gram_tc_kernel<1, true> : gram_tc_kernel<1, false>;
+  auto k2 = pos ? gram_tc_kernel<2, true> : gram_tc_kernel<2, false>;
+  cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t row_blocks = (nrows + TC_M - 1) / TC_M;
   const int grid = (int)(row_blocks < sms ? row_blocks : sms);
 
-  gram_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(tmap, p);
+  k1<<<grid, TC_THREADS, smem, st>>>(tmap, p);
   rc = check_launch("hyp_gram_topk(pass 1)");
   if (rc) return rc;
-  kth_select_kernel<<<(int)((nrows + 127) / 128), 128, 0, st>>>(tilemin, L.ld_tm, L.col_tiles, nrows, row0, k, nrm, maxn,
+  kth_select_kernel<<<(int)((nrows + 127) / 128), 128, 0, st>>>(tilemin, L.ld_tm, 2 * L.col_tiles, nrows, row0, k, nrm, maxn,
                                                                 thr);
   rc = check_launch("hyp_gram_topk(select)");
   if (rc) return rc;
-  gram_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(tmap, p);
+  k2<<<grid, TC_THREADS, smem, st>>>(tmap, p);
   rc = check_launch("hyp_gram_topk(pass 2)");
   if (rc) return rc;
   int64_t fb = (nrows + 3) / 4;

@@ -20,8 +20,11 @@ def test_tc_equals_exact(n, d, k, scale, nrows, row0):
     ti, td = lorentz_topk(E, k, 1.0, "lorentz", n, row0, nrows, engine="tc")
     torch.cuda.synchronize()
     assert torch.equal(ti, ei) and same_bits(td, ed)
-    # the filter, not the fallback, did the work (few or no rows flagged on non-degenerate data)
-    assert lorentz_topk.last_flagged <= max(2, nrows // 100)
+    # with at least ~1.5 k column tiles the filter, not the fallback, does the work on non-degenerate data
+    # (fewer than k tiles cannot bound the k-th best: every row is flagged and redone exactly)
+    if n >= 128 * k * 3 // 2:
+        assert lorentz_topk.last_flagged <= max(2, nrows // 100)
+    print("flagged", lorentz_topk.last_flagged, "of", nrows)
 
 
 def test_tc_degenerate_inputs_fall_back():
