@@ -69,17 +69,24 @@ __device__ __forceinline__ float warp_sum_aten(ProdFn prod, int N, int lane) {
   const int full = vs >> 2;
   const int c = lane >> 3, l = lane & 7;
   float P = 0.f;
+#pragma unroll 4
   for (int r = 0; r < full; ++r) P = __fadd_rn(P, prod(32 * r + lane));
-  if (c == 0)
+  if (c == 0) {
+#pragma unroll 3
     for (int k = 4 * full; k < vs; ++k) P = __fadd_rn(P, prod(8 * k + l));
+  }
   float p1 = __shfl_down_sync(HYP_FULL_MASK, P, 8);
   float p2 = __shfl_down_sync(HYP_FULL_MASK, P, 16);
   float p3 = __shfl_down_sync(HYP_FULL_MASK, P, 24);
   float L = __fadd_rn(__fadd_rn(__fadd_rn(P, p1), p2), p3);  // valid on lanes 0..7
   float acc = 0.f;
+#pragma unroll 7
   for (int k = 8 * vs; k < N; ++k) acc = __fadd_rn(acc, prod(k));
+  float Lq[8];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) acc = __fadd_rn(acc, __shfl_sync(HYP_FULL_MASK, L, q));
+  for (int q = 0; q < 8; ++q) Lq[q] = __shfl_sync(HYP_FULL_MASK, L, q);   // independent shuffles first
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc = __fadd_rn(acc, Lq[q]);
   return acc;  // identical on every lane
 }
 
@@ -98,11 +105,13 @@ template <typename ElemFn>
 __device__ __forceinline__ float warp_norm_aten(ElemFn elem, int N, int lane) {
   const int vs = N >> 3;
   float a = 0.f;
-  if (lane < 8)
+  if (lane < 8) {
+#pragma unroll 4
     for (int k = 0; k < vs; ++k) {
       float v = elem(8 * k + lane);
       a = __fadd_rn(a, __fmul_rn(v, v));
     }
+  }
   float b = __shfl_sync(HYP_FULL_MASK, a, 0);
 #pragma unroll
   for (int q = 1; q < 8; ++q) b = __fadd_rn(b, __shfl_sync(HYP_FULL_MASK, a, q));
@@ -236,24 +245,33 @@ __device__ __forceinline__ void warp_expmap(const float *__restrict__ x, const f
 template <typename OutFn>
 __device__ __forceinline__ void warp_midpoint(const float *__restrict__ xi, const float *__restrict__ xj,
                                               int len_i, int len_j, int D, float c, int semantics,
-                                              bool project, float *buf, int lane, OutFn out) {
+                                              bool project, float *buf, int lane, OutFn out,
+                                              long long *tp = nullptr) {
   float *v = buf, *m_row = buf + D;
+  long long tc0 = tp ? clock64() : 0;
   float m = warp_mdot(xi, xj, D, lane);
+  if (tp) { long long t = clock64(); tp[0] += t - tc0; tc0 = t; }
   float ms;
   float coef = logmap_coef(m, semantics, &ms);
-  float w = (float)((double)len_j / (double)(len_i + len_j));  // Python float, cast to fp32 by `*`
+  if (tp) { long long t = clock64(); tp[1] += t - tc0; tc0 = t; }
+  const float w = (float)((double)len_j / (double)(len_i + len_j));  // Python float, cast to fp32 by `*`
+  if (tp) { long long t = clock64(); tp[2] += t - tc0; tc0 = t; }
   for (int k = lane; k < D; k += 32) {
     float lg = __fmul_rn(coef, __fadd_rn(xj[k], __fmul_rn(ms, xi[k])));
     v[k] = __fmul_rn(lg, w);
   }
   __syncwarp();
+  if (tp) { long long t = clock64(); tp[3] += t - tc0; tc0 = t; }
   warp_expmap(xi, v, D, lane, [&](int k, float val) { m_row[k] = val; });
   __syncwarp();
+  if (tp) { long long t = clock64(); tp[4] += t - tc0; tc0 = t; }
   if (project) {
     // lorentz_model.py:52-55: x0 = sqrt(1 + (c*r)*r)
     float r = warp_norm_aten([&](int e) { return m_row[1 + e]; }, D - 1, lane);
     float x0 = __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(__fmul_rn(c, r), r)));
+    if (tp) { long long t = clock64(); tp[5] += t - tc0; tc0 = t; }
     for (int k = lane; k < D; k += 32) out(k, k == 0 ? x0 : m_row[k]);
+    if (tp) { long long t = clock64(); tp[6] += t - tc0; tc0 = t; }
   } else {
     for (int k = lane; k < D; k += 32) out(k, m_row[k]);
   }

@@ -28,15 +28,25 @@ struct LoopWorkspace {
   unsigned int ticket;   // hyp_row_min: last-block-done
   unsigned int pad[6];
   long long prof[8];               // resident loop: phase cycle counters of CTA 0 and CTA G-1
+  long long mprof[8];              // debug: midpoint sub-phase cycles of CTA 0
   unsigned long long key_ring[4];  // resident loop: per-step atomicMin target (d_bits << 32 | row)
   Key slot[2][kMaxLoopBlocks];     // L2 loop: per-CTA minima, double-buffered by step parity
   unsigned long long below[kMaxLoopBlocks];
+  unsigned long long flag[4][kMaxLoopBlocks];  // resident loop: per-step, per-CTA (key | 1<<63), 0 = not yet written
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void red_release_add_u32(unsigned int *p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -337,7 +347,8 @@ constexpr unsigned long long kNoKey = 0xffffffffffffffffULL;
 
 struct ResidentParams {
   LoopParams lp;
-  int slots;   // slot capacity per CTA (odd)
+  int slots;     // slot capacity per CTA (odd)
+  int exchange;  // 0: atomicMin + arrival counter, 1: per-CTA flags polled by one warp
 };
 
 // exact-order Minkowski product of the row in `slot` with q; N known at compile time.
@@ -384,6 +395,11 @@ __device__ __forceinline__ float resident_mdot_dynamic(const float4 *__restrict_
   return __fsub_rn(__fmul_rn(T0[slot], q0), s);
 }
 
+// named barrier over the first `nthreads` threads of the CTA (the speculating warp stays out of it)
+__device__ __forceinline__ void bar_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 template <int NS>
 __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(const ResidentParams rp) {
   extern __shared__ __align__(16) float smem[];
@@ -391,26 +407,39 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   const int D = p.D, S = rp.slots, N = D - 1;
   const int G4 = (N + 3) / 4;
   const int G = gridDim.x, b = blockIdx.x;
-  // layout (floats): q4[4*G4] | T4[4*G4*S] | T0[S] | q[D] xi[D] xj[D] scratch[2D]
-  float4 *q4 = reinterpret_cast<float4 *>(smem);
-  float4 *T4 = q4 + G4;
+  constexpr int kWork = kResThreads - 32;      // threads that scan; the last warp speculates
+  constexpr int kWorkWarps = kWork / 32;
+  // layout (floats): qq4[2][4*G4] | T4[4*G4*S] | T0[S] | qrow[2][D] | xi[D] xj[D] scratch[2][2D]
+  float4 *qq4 = reinterpret_cast<float4 *>(smem);
+  float4 *T4 = qq4 + 2 * G4;
   float *T0 = reinterpret_cast<float *>(T4 + (size_t)G4 * S);
-  float *q = T0 + S;
-  float *xi = q + D;
+  float *qrow = T0 + S;
+  float *xi = qrow + 2 * D;
   float *xj = xi + D;
   float *scratch = xj + D;
   float *Tf = reinterpret_cast<float *>(T4);
-  float *qf = reinterpret_cast<float *>(q4);
   __shared__ unsigned long long s_key[kResWarps];
+  __shared__ unsigned long long s_win[2];
+  __shared__ int s_len[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool spec_warp = warp == kResWarps - 1;
 
   int n = p.state->n;
   const int cap = p.state->capacity;
   Key best{p.state->best_d, p.state->best_i, p.state->best_j};
   double thr = p.state->threshold;
-  int done = 0, stop = 0;
-  unsigned int arrivals = 0;
+  int done = 0, stop = 0, cur = 0;
+  unsigned int arrivals = (unsigned int)G;
   long long t_mid = 0, t_scan = 0, t_bar = 0, t_mark = 0;
+
+  auto midpoint_into = [&](int which, float *scr) {
+    float *qr = qrow + which * D;
+    float *qf = reinterpret_cast<float *>(qq4 + which * G4);
+    warp_midpoint(xi, xj, s_len[0], s_len[1], D, p.c, p.semantics, true, scr, lane, [&](int e, float v) {
+      qr[e] = v;
+      if (e) qf[e - 1] = v;
+    });
+  };
 
   // ---- load the rows this CTA owns: a warp reads one row (coalesced), scatters it conflict-free --
   {
@@ -423,87 +452,117 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
         else Tf[((size_t)((k - 1) >> 2) * S + sl) * 4 + ((k - 1) & 3)] = v;
       }
     }
-    for (int k = threadIdx.x; k < 4 * G4; k += blockDim.x) qf[k] = 0.f;   // padding lanes of q4 stay zero
+    float *qf = reinterpret_cast<float *>(qq4);
+    for (int k = threadIdx.x; k < 8 * G4; k += blockDim.x) qf[k] = 0.f;   // padding lanes of both q4 stay zero
+    // operand rows of the current best pair (kept in shared memory until the best pair changes)
+    if (best.i >= 0) {
+      for (int e = threadIdx.x; e < D; e += blockDim.x) {
+        xi[e] = __ldcg(p.E + (int64_t)best.i * p.ldE + e);
+        xj[e] = __ldcg(p.E + (int64_t)best.j * p.ldE + e);
+      }
+      if (threadIdx.x == 0) s_len[0] = __ldcg(p.len + best.i);
+      if (threadIdx.x == 1) s_len[1] = __ldcg(p.len + best.j);
+    }
   }
   if (b == 0 && threadIdx.x < 4) p.ws->key_ring[threadIdx.x] = kNoKey;
-  arrivals += G;
   grid_barrier(&p.ws->barrier, arrivals);
+  // midpoint row of the initial best pair (hyperbolic_merge.py:317-340)
+  if (warp == 0 && best.i >= 0) midpoint_into(cur, scratch);
+  __syncthreads();
   if (threadIdx.x == 0) t_mark = clock64();
 
   for (int k = 0; k < p.max_steps; ++k) {
+    // invariant: qrow[cur] / qq4[cur] hold the merged row for `best`, computed from xi, xj, s_len
     const bool cmp_double = n <= 100;
     const bool have = best.i >= 0 && (cmp_double ? ((double)best.d < thr) : (best.d < (float)thr));
     if (!have) { stop = 1; break; }
     if (n >= cap) { stop = 2; break; }
+    const float *q = qrow + cur * D;
+    const float4 *q4 = qq4 + cur * G4;
+    unsigned long long win = kNoKey;
 
-    // ---- midpoint row, redundantly and bit-identically in every CTA --------------------------
-    for (int e = threadIdx.x; e < D; e += blockDim.x) {
-      xi[e] = __ldcg(p.E + (int64_t)best.i * p.ldE + e);
-      xj[e] = __ldcg(p.E + (int64_t)best.j * p.ldE + e);
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const int li = __ldcg(p.len + best.i), lj = __ldcg(p.len + best.j);
-      warp_midpoint(xi, xj, li, lj, D, p.c, p.semantics, true, scratch, lane, [&](int e, float v) {
-        q[e] = v;
-        if (e) qf[e - 1] = v;
-      });
-      if (b == 0) {
-        __syncwarp();
+    if (spec_warp) {
+      // ---- speculation: if this step's scan does not produce a better pair, `best` (and so its rows)
+      // stays, and the NEXT merged row is the midpoint of the same operands.  It is recomputed here, in
+      // full, while the other warps scan and exchange; it is used only if the guess holds.
+      midpoint_into(cur ^ 1, scratch + 2 * D);
+    } else {
+      if (b == 0 && warp == 0) {
+        // append row n = q to the table in global memory (the caller's `embeddings`), log the merge
         for (int e = lane; e < D; e += 32) p.E[(int64_t)n * p.ldE + e] = q[e];
         if (lane == 0) {
-          p.len[n] = li + lj;
+          p.len[n] = s_len[0] + s_len[1];
           p.log[k] = hyp_merge_record{best.i, best.j, best.d, n};
-          p.ws->key_ring[(k + 2) & 3] = kNoKey;  // recycled two barriers from now
         }
       }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { long long t = clock64(); t_mid += t - t_mark; t_mark = t; }
-
-    // ---- score row n against the resident rows (< n) of this CTA: one thread per row ------------
-    const int owned = (n > b) ? (n - b + G - 1) / G : 0;
-    const float q0 = q[0];
-    unsigned long long mine = kNoKey;
-    for (int t = threadIdx.x; t < owned; t += blockDim.x) {
-      const float m = (NS > 0) ? resident_mdot_static<(NS > 0 ? NS : 8)>(T4, T0, S, t, q4, q0)
-                               : resident_mdot_dynamic(T4, T0, S, t, q4, q0, N);
-      const float d = dist_from_mdot(m, p.sgn, p.sqrt_c);
-      if (d == d) {
-        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)(t * G + b);
-        mine = key < mine ? key : mine;
+      // ---- score row n against the resident rows (< n) of this CTA: one thread per row ------------
+      const int owned = (n > b) ? (n - b + G - 1) / G : 0;
+      const float q0 = q[0];
+      unsigned long long mine = kNoKey;
+      for (int t = threadIdx.x; t < owned; t += kWork) {
+        const float m = (NS > 0) ? resident_mdot_static<(NS > 0 ? NS : 8)>(T4, T0, S, t, q4, q0)
+                                 : resident_mdot_dynamic(T4, T0, S, t, q4, q0, N);
+        const float d = dist_from_mdot(m, p.sgn, p.sqrt_c);
+        if (d == d) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)(t * G + b);
+          mine = key < mine ? key : mine;
+        }
       }
-    }
-    // the owner of row n appends it (its slot is beyond `owned`, so nobody reads it this step)
-    if (n % G == b) {
-      const int sl = n / G;
-      for (int e = threadIdx.x; e < D; e += blockDim.x) {
-        if (e == 0) T0[sl] = q[0];
-        else Tf[((size_t)((e - 1) >> 2) * S + sl) * 4 + ((e - 1) & 3)] = q[e];
+      // the owner of row n appends it (its slot is beyond `owned`, so nobody reads it this step)
+      if (n % G == b) {
+        const int sl = n / G;
+        for (int e = threadIdx.x; e < D; e += kWork) {
+          if (e == 0) T0[sl] = q[0];
+          else Tf[((size_t)((e - 1) >> 2) * S + sl) * 4 + ((e - 1) & 3)] = q[e];
+        }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      unsigned long long other = __shfl_xor_sync(HYP_FULL_MASK, mine, o);
-      mine = other < mine ? other : mine;
+      for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(HYP_FULL_MASK, mine, o);
+        mine = other < mine ? other : mine;
+      }
+      if (lane == 0) s_key[warp] = mine;
+      bar_named(1, kWork);
+      // ---- exchange: one 64-bit RED.MIN per CTA, then a counting grid barrier ----------------------
+      const int gen = k & 3;
+      arrivals += G;
+      if (threadIdx.x == 0) {
+        unsigned long long m2 = s_key[0];
+        for (int w = 1; w < kWorkWarps; ++w) m2 = s_key[w] < m2 ? s_key[w] : m2;
+        p.ws->key_ring[(k + 2) & 3] = kNoKey;   // recycled two barriers from now (every CTA writes the same value)
+        if (m2 != kNoKey) atomicMin(&p.ws->key_ring[gen], m2);
+        long long t = clock64(); t_scan += t - t_mark; t_mark = t;
+        red_release_add_u32(&p.ws->barrier, 1u);
+        while (ld_acquire_u32(&p.ws->barrier) < arrivals) {
+        }
+        s_win[k & 1] = __ldcg(&p.ws->key_ring[gen]);
+        t = clock64(); t_bar += t - t_mark; t_mark = t;
+      }
     }
-    if (lane == 0) s_key[warp] = mine;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long m2 = s_key[0];
-      for (int w = 1; w < kResWarps; ++w) m2 = s_key[w] < m2 ? s_key[w] : m2;
-      if (m2 != kNoKey) atomicMin(&p.ws->key_ring[k & 3], m2);
-      long long t = clock64(); t_scan += t - t_mark; t_mark = t;
-    }
-    arrivals += G;
-    grid_barrier(&p.ws->barrier, arrivals);
-    if (threadIdx.x == 0) { long long t = clock64(); t_bar += t - t_mark; t_mark = t; }
+    win = s_win[k & 1];
 
-    const unsigned long long win = __ldcg(&p.ws->key_ring[k & 3]);
+    bool changed = false;
     if (win != kNoKey) {
       Key r{__uint_as_float((unsigned int)(win >> 32)), (int)(win & 0xffffffffu), n};
-      if (key_less(r, best)) best = r;
+      if (key_less(r, best)) { best = r; changed = true; }
     }
+    if (changed) {
+      // new best pair = (i_win, n): row n is q (still in shared memory), row i_win comes from L2
+      const int ln = s_len[0] + s_len[1];
+      __syncthreads();
+      for (int e = threadIdx.x; e < D; e += blockDim.x) {
+        xj[e] = q[e];
+        xi[e] = __ldcg(p.E + (int64_t)best.i * p.ldE + e);
+      }
+      if (threadIdx.x == 0) s_len[0] = __ldcg(p.len + best.i);
+      if (threadIdx.x == 1) s_len[1] = ln;
+      __syncthreads();
+      if (warp == 0) midpoint_into(cur ^ 1, scratch);     // the guess failed: compute the real next row
+      __syncthreads();
+    }
+    cur ^= 1;
+    if (threadIdx.x == 0) { long long t = clock64(); t_mid += t - t_mark; t_mark = t; }
     ++n;
     ++done;
     const int step = p.step0 + k;
@@ -511,7 +570,8 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   }
 
   if (threadIdx.x == 0 && (b == 0 || b == G - 1)) {
-    // phase cycle counters of the first and last CTA (diagnostics; read by bench.py --phases)
+    // phase cycle counters of the first and last CTA (diagnostics; read by bench.py):
+    // [0] wait for the speculating warp + recompute on a failed guess, [1] scan, [2] exchange
     long long *prof = p.ws->prof + (b == 0 ? 0 : 4);
     prof[0] = t_mid; prof[1] = t_scan; prof[2] = t_bar; prof[3] = done;
   }
@@ -584,7 +644,7 @@ extern "C" int hyp_row_min(const float *E, int64_t ldE, int64_t n, int64_t row, 
     return HYP_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(workspace, 0, 128, st);
+  cudaMemsetAsync(workspace, 0, 192, st);
   int64_t want = (n + (int64_t)kLoopWarps * kRowsPerIter - 1) / ((int64_t)kLoopWarps * kRowsPerIter);
   int grid = (int)(want < 1 ? 1 : (want > kMaxLoopBlocks ? kMaxLoopBlocks : want));
   row_min_kernel<<<grid, kLoopThreads, (size_t)D * sizeof(float), st>>>(
@@ -617,11 +677,11 @@ extern "C" int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  cudaMemsetAsync(workspace, 0, 128, st);
+  cudaMemsetAsync(workspace, 0, 192, st);
 
   // table-resident variant when every row up to `capacity_hint` fits in the grid's shared memory
   const int Nsp = D - 1, G4 = (Nsp + 3) / 4;
-  const int64_t fixed = ((int64_t)4 * G4 + (int64_t)5 * D) * (int64_t)sizeof(float) + 1024;
+  const int64_t fixed = ((int64_t)8 * G4 + (int64_t)8 * D) * (int64_t)sizeof(float) + 1024;
   int slots = (int)(((int64_t)max_smem - fixed) / (((int64_t)4 * G4 + 1) * (int64_t)sizeof(float)));
   if ((slots & 1) == 0) --slots;  // odd stride: conflict-free scattered stores
   const char *force = getenv("HYP_MERGE_LOOP");
@@ -631,7 +691,9 @@ extern "C" int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float
     ResidentParams rp;
     rp.lp = p;
     rp.slots = slots;
-    const size_t smem = ((size_t)4 * G4 + (size_t)4 * G4 * slots + slots + (size_t)5 * D) * sizeof(float);
+    const char *ex = getenv("HYP_EXCHANGE");
+    rp.exchange = ex ? atoi(ex) : 0;
+    const size_t smem = ((size_t)8 * G4 + (size_t)4 * G4 * slots + slots + (size_t)8 * D) * sizeof(float);
     const void *fn = Nsp == 100 ? (const void *)merge_loop_resident_kernel<100>
                      : Nsp == 50 ? (const void *)merge_loop_resident_kernel<50>
                                  : (const void *)merge_loop_resident_kernel<0>;
