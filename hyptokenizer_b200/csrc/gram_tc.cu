@@ -377,13 +377,20 @@ __global__ void kth_select_kernel(const float *__restrict__ tilemin, int64_t ld_
   for (int q = 0; q < k; ++q) best[q] = inf;
   float worst = inf;
   int wpos = 0;
-  for (int64_t t = 0; t < col_tiles; ++t) {
-    const float v = tilemin[t * ld_tm + r];
-    if (v < worst) {
-      best[wpos] = v;
-      worst = -1.f;
-      for (int q = 0; q < k; ++q)
-        if (best[q] >= worst) { worst = best[q]; wpos = q; }
+  // 8 independent loads in flight per thread (the tile minima stream from HBM once), then the rare inserts
+  for (int64_t t0 = 0; t0 < col_tiles; t0 += 8) {
+    float vals[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) vals[u] = (t0 + u < col_tiles) ? __ldcs(tilemin + (t0 + u) * ld_tm + r) : inf;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float v = vals[u];
+      if (v < worst) {
+        best[wpos] = v;
+        worst = -1.f;
+        for (int q = 0; q < k; ++q)
+          if (best[q] >= worst) { worst = best[q]; wpos = q; }
+      }
     }
   }
   const float tau = worst;     // +inf when fewer than k tiles hold a finite minimum

@@ -58,3 +58,46 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), (dirpath, fn)
+
+
+def test_module_alias_drop_in():
+    """INTEGRATION.md option A: the package can be aliased onto the reference's module names."""
+    import importlib
+    import sys
+    import hyptokenizer_b200.embedding as E
+    import hyptokenizer_b200.tokenizer as T
+    for name in ("lorentz_model",):
+        importlib.import_module(f"hyptokenizer_b200.embedding.{name}")
+    for name in ("hyperbolic_merge", "fast_hyperbolic_merge", "frequency_aware_hyperbolic_merge"):
+        importlib.import_module(f"hyptokenizer_b200.tokenizer.{name}")
+    saved = {k: sys.modules.get(k) for k in ("embedding", "embedding.lorentz_model", "tokenizer",
+                                             "tokenizer.hyperbolic_merge", "tokenizer.fast_hyperbolic_merge",
+                                             "tokenizer.frequency_aware_hyperbolic_merge")}
+    try:
+        sys.modules["embedding"] = E
+        sys.modules["embedding.lorentz_model"] = E.lorentz_model
+        sys.modules["tokenizer"] = T
+        for m in ("hyperbolic_merge", "fast_hyperbolic_merge", "frequency_aware_hyperbolic_merge"):
+            sys.modules[f"tokenizer.{m}"] = getattr(T, m)
+        from embedding.lorentz_model import (batch_distance, distance, exp_map, log_map, minkowski_dot,  # noqa: F401
+                                             minkowski_norm, parallel_transport, project_to_hyperboloid)
+        from tokenizer.fast_hyperbolic_merge import AdaptiveMergeCache, FastHyperbolicTokenizer, MergeCandidate  # noqa: F401
+        from tokenizer.frequency_aware_hyperbolic_merge import FrequencyAwareHyperbolicTokenizer  # noqa: F401
+        from tokenizer.hyperbolic_merge import HyperbolicTokenizer  # noqa: F401
+        import inspect
+        sig = inspect.signature(HyperbolicTokenizer.__init__)
+        assert list(sig.parameters)[1:9] == ["vocab", "embeddings", "curvature", "merge_threshold", "lr", "device",
+                                             "max_vocab_size", "use_approximate_search"]
+        sig = inspect.signature(FastHyperbolicTokenizer.__init__)
+        for name in ("cache_size", "rebuild_frequency", "hnsw_m", "hnsw_ef_construction", "hnsw_ef_search"):
+            assert name in sig.parameters
+        c = AdaptiveMergeCache(max_size=3)
+        c.add_batch([MergeCandidate(0.3, 1, 2), MergeCandidate(0.1, 0, 5), MergeCandidate(0.1, 0, 4), MergeCandidate(0.9, 7, 8)])
+        assert [(m.token_i, m.token_j) for m in c.get_best(2)] == [(0, 5), (0, 4)]     # stable on distance only
+        assert c.get_stats()["size"] == 1 and c.get_stats()["hit_count"] == 2
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
