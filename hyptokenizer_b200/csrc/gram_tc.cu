@@ -28,6 +28,7 @@
 // double-buffered in TMEM (2 x 128 columns) so the epilogue of tile t overlaps the MMA of tile t+1.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -38,7 +39,7 @@ constexpr int TC_N = 128;          // columns per tile (UMMA N)
 constexpr int TC_KSLAB = 32;       // fp32 elements per 128-byte swizzle row
 constexpr int TC_SLAB_BYTES = TC_M * 128;   // 16 KiB: 128 rows x 128 B
 constexpr int TC_MAX_SLABS = 4;    // K padded up to 128
-constexpr int TC_STAGES = 2;
+constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;    // 2 per TMEM lane quadrant: each handles one 64-column half of the tile
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_HALF = TC_N / 2;
@@ -128,6 +129,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
 }
 
+// Tail slab (K not a multiple of 32): rows of 32 B (8 floats, SWIZZLE_32B = 6, 8-row group 256 B) or 64 B
+// (16 floats, SWIZZLE_64B = 4, 8-row group 512 B); same canonical K-major form.
+__device__ __forceinline__ uint64_t smem_desc_tail(uint32_t saddr, int row_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(row_bytes == 32 ? 6 : 4) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 in
 // [0,14), LBO >> 4 in [16,30) (unused for swizzled K-major, 1), SBO >> 4 in [32,46) = 1024 B between
 // 8-row groups, version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
@@ -177,8 +207,12 @@ struct TcParams {
   int64_t n;          // table rows (columns of the Gram matrix)
   int64_t row0;       // shard start
   int64_t nrows;      // shard rows
-  int n_slabs;        // Kp / 32
+  int n_slabs;        // full 128-byte-row slabs (32 floats each)
+  int tail_row_bytes; // 0, 32 or 64: one more slab with narrow rows for K mod 32 in {8, 16}
+  int stage_bytes;    // bytes of one operand tile in shared memory (1024-aligned)
+  int n_stages;       // depth of the B ring
   int n_ksteps;       // ceil(d / 8) MMAs per tile
+  int debug;          // HYP_TC_DEBUG bit 0: epilogue skips TMEM loads + math, bit 1: no MMAs issued, bit 2: no TMA
   float sgn;
   const float *x0;
   // pass 1
@@ -192,32 +226,36 @@ struct TcParams {
 
 template <int PASS, bool SGN_POS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail,
+               const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // layout: A slabs | B stage 0 slabs | B stage 1 slabs | colx0[2][128] | barriers | tmem ptr
+  // layout: A tile | B stages | colx0[2][128] | barriers | tmem ptr
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *sA = base;
-  uint8_t *sB = sA + p.n_slabs * TC_SLAB_BYTES;
-  float *colx0 = reinterpret_cast<float *>(sB + TC_STAGES * p.n_slabs * TC_SLAB_BYTES);
+  uint8_t *sB = sA + p.stage_bytes;
+  float *colx0 = reinterpret_cast<float *>(sB + (size_t)p.n_stages * p.stage_bytes);
   uint64_t *bars = reinterpret_cast<uint64_t *>(colx0 + 2 * TC_N);
   uint64_t *a_full = bars + 0, *a_empty = bars + 1;
-  uint64_t *b_full = bars + 2, *b_empty = bars + 4;      // [2] each
-  uint64_t *acc_full = bars + 6, *acc_empty = bars + 8;  // [2] each
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 10);
+  uint64_t *acc_full = bars + 2, *acc_empty = bars + 4;                  // [2] each
+  uint64_t *b_full = bars + 6, *b_empty = bars + 6 + TC_MAX_STAGES;     // [n_stages] each
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 6 + 2 * TC_MAX_STAGES);
+  const uint32_t tile_tx = p.n_slabs * TC_SLAB_BYTES + TC_M * p.tail_row_bytes;
+  const int tail_elem0 = p.n_slabs * TC_KSLAB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row_blocks = (p.nrows + TC_M - 1) / TC_M;
   const int64_t col_tiles = (p.n + TC_N - 1) / TC_N;
-  const uint32_t slab_tx = TC_SLAB_BYTES;
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(b_full + s, 1);
-      mbar_init(b_empty + s, 1);
       mbar_init(acc_full + s, 1);
       mbar_init(acc_empty + s, TC_EPI_WARPS);   // one arrival per epilogue warp
+    }
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_empty + s, 1);
     }
     fence_barrier_init();
   }
@@ -233,23 +271,45 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       uint32_t bstage = 0, bphase = 0, aphase = 0;
       for (int64_t rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
         mbar_wait(a_empty, aphase ^ 1);
-        mbar_expect_tx(a_full, slab_tx * p.n_slabs);
+        mbar_expect_tx(a_full, tile_tx);
         for (int s = 0; s < p.n_slabs; ++s)
           tma_load_2d(&tmap, a_full, sA + s * TC_SLAB_BYTES, s * TC_KSLAB, (int)(p.row0 + rb * TC_M));
+        if (p.tail_row_bytes)
+          tma_load_2d(&tmap_tail, a_full, sA + p.n_slabs * TC_SLAB_BYTES, tail_elem0, (int)(p.row0 + rb * TC_M));
         aphase ^= 1;
         for (int64_t ct = 0; ct < col_tiles; ++ct) {
           mbar_wait(b_empty + bstage, bphase ^ 1);
-          mbar_expect_tx(b_full + bstage, slab_tx * p.n_slabs);
-          uint8_t *dst = sB + (size_t)bstage * p.n_slabs * TC_SLAB_BYTES;
+          if (p.debug & 4) { mbar_arrive(b_full + bstage); if (++bstage == (uint32_t)p.n_stages) { bstage = 0; bphase ^= 1; } continue; }
+          mbar_expect_tx(b_full + bstage, tile_tx);
+          uint8_t *dst = sB + (size_t)bstage * p.stage_bytes;
           for (int s = 0; s < p.n_slabs; ++s)
             tma_load_2d(&tmap, b_full + bstage, dst + s * TC_SLAB_BYTES, s * TC_KSLAB, (int)(ct * TC_N));
-          if (++bstage == TC_STAGES) { bstage = 0; bphase ^= 1; }
+          if (p.tail_row_bytes)
+            tma_load_2d(&tmap_tail, b_full + bstage, dst + p.n_slabs * TC_SLAB_BYTES, tail_elem0, (int)(ct * TC_N));
+          if (++bstage == (uint32_t)p.n_stages) { bstage = 0; bphase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
+    // One thread issues every tcgen05.mma of the CTA, so its own instruction stream is the limit: the
+    // descriptors of all k-steps are prepared once (low word = (address >> 4) + per-k-step offset, high word
+    // constant per slab kind) and the tile loop only adds a base and issues.
     if (lane == 0) {
+      constexpr int kMaxK = TC_MAX_SLABS * 4;
+      uint32_t koff[kMaxK], khi[kMaxK];
+      const uint32_t hi128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t hitail = (uint32_t)((8 * p.tail_row_bytes) >> 4) | (1u << 14) |
+                              ((p.tail_row_bytes == 32 ? 6u : 4u) << 29);
+#pragma unroll
+      for (int ks = 0; ks < kMaxK; ++ks) {
+        const int slab = ks >> 2, within = ks & 3;
+        const bool tail = slab >= p.n_slabs;
+        koff[ks] = (uint32_t)(((tail ? p.n_slabs : slab) * TC_SLAB_BYTES + within * 32) >> 4);
+        khi[ks] = tail ? hitail : hi128;
+      }
+      const uint32_t a_lo = ((smem_u32(sA) >> 4) & 0x3fff) | (1u << 16);
+      const int nk = (p.debug & 2) ? 0 : p.n_ksteps;
       uint32_t bstage = 0, bphase = 0, aphase = 0, abuf = 0, accphase = 0;
       for (int64_t rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
         mbar_wait(a_full, aphase);
@@ -258,18 +318,19 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           mbar_wait(b_full + bstage, bphase);
           mbar_wait(acc_empty + abuf, accphase ^ 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA);
-          const uint32_t b_addr = smem_u32(sB + (size_t)bstage * p.n_slabs * TC_SLAB_BYTES);
+          const uint32_t b_lo = ((smem_u32(sB + (size_t)bstage * p.stage_bytes) >> 4) & 0x3fff) | (1u << 16);
           const uint32_t d_addr = tmem_base + abuf * TC_N;
-          for (int ks = 0; ks < p.n_ksteps; ++ks) {
-            const int slab = ks >> 2, within = ks & 3;   // 4 k-steps of 8 fp32 (32 B) per 128-byte swizzle row
-            const uint64_t ad = smem_desc_sw128(a_addr + slab * TC_SLAB_BYTES + within * 32);
-            const uint64_t bd = smem_desc_sw128(b_addr + slab * TC_SLAB_BYTES + within * 32);
-            umma_tf32(d_addr, ad, bd, kIdescTf32, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < kMaxK; ++ks) {
+            if (ks < nk) {
+              const uint64_t ad = ((uint64_t)khi[ks] << 32) | (uint64_t)(a_lo + koff[ks]);
+              const uint64_t bd = ((uint64_t)khi[ks] << 32) | (uint64_t)(b_lo + koff[ks]);
+              umma_tf32(d_addr, ad, bd, kIdescTf32, ks > 0 ? 1u : 0u);
+            }
           }
           umma_commit(b_empty + bstage);     // B stage reusable once these MMAs have read it
           umma_commit(acc_full + abuf);      // accumulator ready for the epilogue
-          if (++bstage == TC_STAGES) { bstage = 0; bphase ^= 1; }
+          if (++bstage == (uint32_t)p.n_stages) { bstage = 0; bphase ^= 1; }
           if (++abuf == 2) { abuf = 0; accphase ^= 1; }
         }
         umma_commit(a_empty);                // A tile reusable
@@ -298,11 +359,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       int cnt = 0;
       if (PASS == 2) thr = row_ok ? __ldg(p.thr + (gi - p.row0)) : -1.f;
       int32_t *my_cand = p.cand + ((gi - p.row0) * 2 + half) * TC_CAPH;
+      // time components of the next tile's columns are fetched one tile ahead (an L2 round trip that would
+      // otherwise sit on the critical path of every tile)
+      float x0_next = 0.f;
+      if (ep_tid < TC_N) x0_next = ep_tid < p.n ? __ldg(p.x0 + ep_tid) : 0.f;
       for (int64_t ct = 0; ct < col_tiles; ++ct) {
         const int64_t j0 = ct * TC_N;
         if (ep_tid < TC_N) {
-          const int64_t gj = j0 + ep_tid;
-          colx0[abuf * TC_N + ep_tid] = gj < p.n ? __ldg(p.x0 + gj) : 0.f;
+          colx0[abuf * TC_N + ep_tid] = x0_next;
+          const int64_t gjn = j0 + TC_N + ep_tid;
+          x0_next = gjn < p.n ? __ldg(p.x0 + gjn) : 0.f;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         mbar_wait(acc_full + abuf, accphase);
@@ -311,15 +377,28 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         const float *cx = colx0 + abuf * TC_N + half * TC_HALF;
         const int64_t jh = j0 + half * TC_HALF;
         float tmin = inf;
-#pragma unroll 1
-        for (int chunk = 0; chunk < TC_HALF / 32; ++chunk) {
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + abuf * TC_N + half * TC_HALF + chunk * 32, v);
+        // both 32-column chunks of this thread's half are requested before the first is consumed
+        float v0[32], v1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + abuf * TC_N + half * TC_HALF;
+        if (!(p.debug & 1)) {
+          tmem_ld32_nowait(taddr, v0);
+          tmem_ld32_nowait(taddr + 32, v1);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { v0[c] = 0.f; v1[c] = 0.f; }
+        }
+#pragma unroll
+        for (int chunk = 0; chunk < ((p.debug & 1) ? 0 : 2); ++chunk) {
+          const float (&v)[32] = chunk == 0 ? v0 : v1;
           const float *cxc = cx + chunk * 32;
           if (PASS == 1) {
             if (!checked) {
+              float m4[4] = {inf, inf, inf, inf};      // four independent min chains
 #pragma unroll
-              for (int c = 0; c < 32; ++c) tmin = fminf(tmin, SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]));
+              for (int c = 0; c < 32; ++c)
+                m4[c & 3] = fminf(m4[c & 3], SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]));
+              tmin = fminf(tmin, fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])));
             } else {
 #pragma unroll
               for (int c = 0; c < 32; ++c) {
@@ -329,12 +408,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
               }
             }
           } else {
-            uint32_t hits = 0;
+            uint32_t h4[4] = {0u, 0u, 0u, 0u};            // four independent OR chains
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float u = SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]);
-              hits |= (u <= thr ? 1u : 0u) << c;
+              h4[c & 3] |= (u <= thr ? 1u : 0u) << c;
             }
+            uint32_t hits = (h4[0] | h4[1]) | (h4[2] | h4[3]);
             while (hits) {
               const int c = __ffs(hits) - 1;
               hits &= hits - 1;
@@ -469,7 +549,7 @@ static EncodeTiledFn get_encode() {
 }
 
 struct TcLayout {
-  int Kp, n_slabs, n_ksteps;
+  int Kp, n_slabs, n_ksteps, tail_row_bytes, stage_bytes, n_stages;
   int64_t ld_tm, col_tiles;
   size_t off_xp, off_x0, off_nrm, off_max, off_tilemin, off_thr, off_cand, off_cnt, off_flags, total;
 };
@@ -478,8 +558,21 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
   TcLayout L;
   const int d = D - 1;
   L.Kp = ((d + TC_KSLAB - 1) / TC_KSLAB) * TC_KSLAB;
-  L.n_slabs = L.Kp / TC_KSLAB;
   L.n_ksteps = (d + 7) / 8;
+  const int k8 = L.n_ksteps * 8;
+  L.n_slabs = k8 / TC_KSLAB;
+  int rem = k8 % TC_KSLAB;                 // 0, 8, 16 or 24 floats
+  if (rem == 24) { L.n_slabs += 1; rem = 0; }   // 96-byte rows have no swizzle mode: take a full slab
+  L.tail_row_bytes = rem * 4;
+  L.stage_bytes = ((L.n_slabs * TC_SLAB_BYTES + TC_M * L.tail_row_bytes + 1023) / 1024) * 1024;
+  const int budget = 220 * 1024 - 4096;
+  L.n_stages = (budget - L.stage_bytes) / L.stage_bytes;
+  if (L.n_stages > TC_MAX_STAGES) L.n_stages = TC_MAX_STAGES;
+  if (const char *e = getenv("HYP_TC_STAGES")) {
+    const int want = atoi(e);
+    if (want >= 1 && want < L.n_stages) L.n_stages = want;
+  }
+  if (L.n_stages < 1) L.n_stages = 1;
   L.col_tiles = (n + TC_N - 1) / TC_N;
   L.ld_tm = ((nrows + 31) / 32) * 32;
   size_t o = 0;
@@ -564,11 +657,26 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
     return HYP_ERR_CUDA;
   }
 
+  CUtensorMap tmap_tail = tmap;
+  if (L.tail_row_bytes) {
+    const cuuint32_t tbox[2] = {(cuuint32_t)(L.tail_row_bytes / 4), (cuuint32_t)TC_M};
+    cr = encode(&tmap_tail, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)XP, gdim, gstride, tbox, estride,
+                CU_TENSOR_MAP_INTERLEAVE_NONE,
+                L.tail_row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("hyp_gram_topk: cuTensorMapEncodeTiled (tail) failed (%d)", (int)cr);
+      return HYP_ERR_CUDA;
+    }
+  }
+
   TcParams p{};
   p.n = n; p.row0 = row0; p.nrows = nrows; p.n_slabs = L.n_slabs; p.n_ksteps = L.n_ksteps;
+  p.tail_row_bytes = L.tail_row_bytes; p.stage_bytes = L.stage_bytes; p.n_stages = L.n_stages;
+  p.debug = getenv("HYP_TC_DEBUG") ? atoi(getenv("HYP_TC_DEBUG")) : 0;
   p.sgn = semantics == HYP_SEM_REFERENCE ? -1.f : 1.f;
   p.x0 = x0; p.tilemin = tilemin; p.ld_tm = L.ld_tm; p.thr = thr; p.cand = cand; p.cand_cnt = cnt;
-  const size_t smem = 1024 + (size_t)(1 + TC_STAGES) * L.n_slabs * TC_SLAB_BYTES + 2 * TC_N * 4 + 16 * 8;
+  const size_t smem = 1024 + (size_t)(1 + L.n_stages) * L.stage_bytes + 2 * TC_N * 4 + (8 + 2 * TC_MAX_STAGES) * 8;
   const bool pos = p.sgn > 0.f;
   auto k1 = pos ? gram_tc_kernel<1, true> : gram_tc_kernel<1, false>;
   auto k2 = pos ? gram_tc_kernel<2, true> : gram_tc_kernel<2, false>;
@@ -577,14 +685,14 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   const int64_t row_blocks = (nrows + TC_M - 1) / TC_M;
   const int grid = (int)(row_blocks < sms ? row_blocks : sms);
 
-  k1<<<grid, TC_THREADS, smem, st>>>(tmap, p);
+  k1<<<grid, TC_THREADS, smem, st>>>(tmap, tmap_tail, p);
   rc = check_launch("hyp_gram_topk(pass 1)");
   if (rc) return rc;
   kth_select_kernel<<<(int)((nrows + 127) / 128), 128, 0, st>>>(tilemin, L.ld_tm, 2 * L.col_tiles, nrows, row0, k, nrm, maxn,
                                                                 thr);
   rc = check_launch("hyp_gram_topk(select)");
   if (rc) return rc;
-  k2<<<grid, TC_THREADS, smem, st>>>(tmap, p);
+  k2<<<grid, TC_THREADS, smem, st>>>(tmap, tmap_tail, p);
   rc = check_launch("hyp_gram_topk(pass 2)");
   if (rc) return rc;
   int64_t fb = (nrows + 3) / 4;
