@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--v0", type=int, default=V0)
     ap.add_argument("--target", type=int, default=TARGET)
     ap.add_argument("--dim", type=int, default=D_EMB)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
                     help="c2: merge loop (headline, merges/s); c3: all-pairs Lorentz distance + top-k=32 over V=100k, "
                          "row-sharded over the ranks with an all-gather (TFLOP/s)")
     ap.add_argument("--engine", default="tc", choices=["tc", "exact"])
@@ -263,14 +263,19 @@ def run_ours(a):
                                f"({merges} merges/step, exact device search in place of HNSW M=32/ef=100)",
                    "semantics": a.semantics, "init_scale": SCALE, "merge_threshold": THRESHOLD,
                    "merges_done_per_step": done, "stop_code": st.stop,
-                   "l2": "flushed between timed steps (256 MiB write); within a step the table is L2-resident by design",
+                   "l2": "flushed between timed steps (256 MiB write); within a step the table is on-chip by design",
                    "parallelism": "replicas only" if world > 1 else "1 GPU"},
         "gpu_launches": 3 * a.steps,
-        "launches_note": "per step: allpairs_tile_kernel<min>, merge_state_init_kernel, merge_loop_kernel (cooperative)",
-        "roofline": {"bound": "hbm", "kernel": "merge_loop_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+        "launches_note": "per step: allpairs_tile_kernel<min>, merge_state_init_kernel, "
+                         "merge_loop_resident_kernel<100> (cooperative, persistent)",
+        "roofline": {"bound": "hbm", "kernel": "merge_loop_resident_kernel<100>", "achieved": achieved, "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                     "traffic": 4356608, "traffic_source": "profiles/r01_prof_merge_raw.csv: dram__bytes_read.sum + "
+                                                           "dram__bytes_write.sum of one launch (ncu --set full)",
+                     "peak_kind": pk_kind,
                      "algorithmic_bytes_per_launch": abytes, "kernel_ms": loop_ms,
-                     "note": "table (<= 20.2 MB) is re-read from L2 every merge; frac is against HBM copy bandwidth"},
+                     "note": "the table (<= 20.2 MB) lives in the shared memory of the persistent grid, so DRAM traffic is far "
+                             "below the algorithmic bytes; frac is the algorithmic rate against HBM copy bandwidth"},
         "clocks": clocks,
     }
     if e2e:
@@ -441,10 +446,73 @@ def run_c3(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# config 4 (pair counting part): 1 GB synthetic token stream
+# ------------------------------------------------------------------------------------------------
+def run_c4(a):
+    from hyptokenizer_b200 import _lib
+    from hyptokenizer_b200._lib import check, ptr
+    from hyptokenizer_b200.pair_count import pairs_to_dict
+    from hyptokenizer_b200.synth import synthetic_corpus
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    L = _lib.lib()
+    _lib.check_device(dev)
+    nbytes = 1 << 30
+    host = torch.from_numpy(synthetic_corpus(nbytes, seed=0)).pin_memory()
+    text = host.to(dev)
+    cap = 1 << 20
+    asc = torch.empty(128 * 128, dtype=torch.int64, device=dev)
+    keys = torch.empty(cap, dtype=torch.int64, device=dev)
+    vals = torch.empty(cap, dtype=torch.int64, device=dev)
+    ovf = torch.empty(1, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for it in range(a.warmup + a.steps):
+        e0.record(stream)
+        check(L.hyp_pair_count(ptr(text), nbytes, ptr(asc), ptr(keys), ptr(vals), cap, ptr(ovf), stream.cuda_stream))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if it >= a.warmup:
+            ts.append(e0.elapsed_time(e1))
+    # end to end: pinned host bytes -> H2D -> kernel -> D2H of the tables -> dict
+    t0 = time.perf_counter()
+    t2 = host.to(dev, non_blocking=True)
+    check(L.hyp_pair_count(ptr(t2), nbytes, ptr(asc), ptr(keys), ptr(vals), cap, ptr(ovf), stream.cuda_stream))
+    counts = pairs_to_dict(asc, keys, vals)
+    e2e_s = time.perf_counter() - t0
+    pk, kind = peaks()
+    ms = float(np.mean(ts))
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    line = {"metric": "pair counting GB/s (1 GB token stream)", "value": gbs, "unit": "GB/s", "n_gpus": 1,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "c4 (pair-count part): 1 GiB ASCII stream, lines of 20 random words; input larger than L2",
+                       "distinct_pairs": len(counts), "total_pairs": int(sum(counts.values()))},
+            "gpu_launches": a.steps, "roofline": {"bound": "hbm", "kernel": "pair_count_kernel", "achieved": gbs,
+                                                  "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                                                  "traffic": None, "peak_kind": kind},
+            "e2e": {"value": nbytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes,
+                    "d2h_bytes_per_step": int(asc.numel() * 8 + 2 * cap * 8)}}
+    if not a.no_cpu_baseline:
+        from oracle.pair_count import count_pairs_c
+        sample = host[: 256 << 20].numpy()
+        t0 = time.perf_counter()
+        ref = count_pairs_c(sample)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": sample.size / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                "sample": "first 256 MiB of the same stream, C restatement (oracle/pair_count.c), one thread; "
+                                          "the reference's Python dict loop measured 2.5 MB/s (BASELINE.md)"}
+    print(json.dumps(line))
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4":
+        run_c4(args)
     elif args.workload == "c3":
         run_c3(args)
     else:

@@ -29,7 +29,12 @@ struct LoopWorkspace {
   unsigned int pad[6];
   long long prof[8];               // resident loop: phase cycle counters of CTA 0 and CTA G-1
   long long mprof[8];              // debug: midpoint sub-phase cycles of CTA 0
-  unsigned long long key_ring[4];  // resident loop: per-step atomicMin target (d_bits << 32 | row)
+  unsigned long long key_ring[4];  // (unused by the current kernels; keeps the header layout stable)
+  struct alignas(16) XSlot {       // resident loop: per-step exchange word, polled with ONE 128-bit load
+    unsigned long long key;        //   RED.MIN target: d_bits << 32 | row
+    unsigned int count;            //   arrivals of this step
+    unsigned int pad;
+  } xring[4];
   Key slot[2][kMaxLoopBlocks];     // L2 loop: per-CTA minima, double-buffered by step parity
   unsigned long long below[kMaxLoopBlocks];
   unsigned long long flag[4][kMaxLoopBlocks];  // resident loop: per-step, per-CTA (key | 1<<63), 0 = not yet written
@@ -47,6 +52,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 }
 __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void ld_acquire_v2_u64(const void *p, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.acquire.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void red_release_add_u32(unsigned int *p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -464,7 +472,10 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
       if (threadIdx.x == 1) s_len[1] = __ldcg(p.len + best.j);
     }
   }
-  if (b == 0 && threadIdx.x < 4) p.ws->key_ring[threadIdx.x] = kNoKey;
+  if (b == 0 && threadIdx.x < 4) {
+    p.ws->xring[threadIdx.x].key = kNoKey;
+    p.ws->xring[threadIdx.x].count = 0u;
+  }
   grid_barrier(&p.ws->barrier, arrivals);
   // midpoint row of the initial best pair (hyperbolic_merge.py:317-340)
   if (warp == 0 && best.i >= 0) midpoint_into(cur, scratch);
@@ -523,19 +534,23 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
       }
       if (lane == 0) s_key[warp] = mine;
       bar_named(1, kWork);
-      // ---- exchange: one 64-bit RED.MIN per CTA, then a counting grid barrier ----------------------
+      // ---- exchange: one 64-bit RED.MIN + one release RED.ADD per CTA on the SAME 16-byte slot, which
+      // every CTA then polls with a single 128-bit acquire load: the load that sees count == G also carries
+      // the final minimum (each CTA's RED.MIN is ordered before its arrival), so no second round trip.
       const int gen = k & 3;
-      arrivals += G;
       if (threadIdx.x == 0) {
         unsigned long long m2 = s_key[0];
         for (int w = 1; w < kWorkWarps; ++w) m2 = s_key[w] < m2 ? s_key[w] : m2;
-        p.ws->key_ring[(k + 2) & 3] = kNoKey;   // recycled two barriers from now (every CTA writes the same value)
-        if (m2 != kNoKey) atomicMin(&p.ws->key_ring[gen], m2);
+        LoopWorkspace::XSlot *xr = &p.ws->xring[gen];
+        LoopWorkspace::XSlot *recycle = &p.ws->xring[(k + 2) & 3];   // every CTA writes the same reset values
+        recycle->key = kNoKey;
+        recycle->count = 0u;
+        if (m2 != kNoKey) atomicMin(&xr->key, m2);
         long long t = clock64(); t_scan += t - t_mark; t_mark = t;
-        red_release_add_u32(&p.ws->barrier, 1u);
-        while (ld_acquire_u32(&p.ws->barrier) < arrivals) {
-        }
-        s_win[k & 1] = __ldcg(&p.ws->key_ring[gen]);
+        red_release_add_u32(&xr->count, 1u);
+        unsigned long long kk, cc;
+        do { ld_acquire_v2_u64(xr, kk, cc); } while ((unsigned int)(cc & 0xffffffffu) < (unsigned int)G);
+        s_win[k & 1] = kk;
         t = clock64(); t_bar += t - t_mark; t_mark = t;
       }
     }
