@@ -196,7 +196,8 @@ class HyperbolicTokenizer:
         with torch.cuda.device(E.device):
             check(_lib.lib().hyp_merge_steps(ptr(E), E.stride(0), ptr(lens), D, float(self.curvature),
                                              SEM[self.semantics], ptr(state), ptr(log), max_steps, step0,
-                                             threshold_every, float(threshold_mul), cap, ptr(ws["loop"]),
+                                             threshold_every, float(threshold_mul), min(cap, n0 + max_steps),
+                                             ptr(ws["loop"]),
                                              ws["loop"].numel(), stream_ptr()))
         out = HypMergeState.from_buffer_copy(state.cpu().numpy().tobytes())
         rec = log[: out.steps_done].cpu().numpy().view(_RECORD_DTYPE).reshape(-1)

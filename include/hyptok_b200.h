@@ -167,9 +167,10 @@ int hyp_merge_state_init(hyp_merge_state *state, const hyp_best *best, int32_t n
  * (step > 0, counted from `step0`) threshold *= threshold_mul, as the reference loops do
  * (x1.05 / x1.1 per 1000); pass 0 to disable.  Stops early when nothing is below threshold
  * (state->stop = 1) or the table is full (stop = 2, the reference's ValueError).
- * `capacity_hint` = state->capacity as known to the host (the state itself lives on the device):
- * when that many rows fit in the shared memory of one persistent CTA per SM the table-resident
- * kernel runs, otherwise the L2-streaming one; both produce identical bits. */
+ * `capacity_hint` = an upper bound, known to the host, on the rows the table can reach during this
+ * call (min(state->capacity, n + max_steps); the state itself lives on the device): when that many
+ * rows fit in the shared memory of one persistent CTA per SM the table-resident kernel runs,
+ * otherwise the L2-streaming one; both produce identical bits. */
 int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float c, int semantics,
                     hyp_merge_state *state, hyp_merge_record *log, int32_t max_steps,
                     int32_t step0, int32_t threshold_every, double threshold_mul,

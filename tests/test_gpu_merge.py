@@ -261,3 +261,40 @@ def test_loop_variants_identical(monkeypatch):
             tok.optimize_merges(steps=150)
             logs.append((tok.last_trace.copy(), tok.embeddings[:650].detach().cpu()))
         assert np.array_equal(logs[0][0], logs[1][0]) and same_bits(logs[0][1], logs[1][1])
+
+
+def test_row_min_entry_point():
+    """K4 as a standalone call: argmin over i != row of (d(E[i], E[row]), pair) and the count below threshold."""
+    from hyptokenizer_b200 import _lib
+    from hyptokenizer_b200._lib import HypBest, check, ptr, stream_ptr
+    from hyptokenizer_b200.embedding import lorentz_model as LM
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    n, d, row, thr = 7000, 100, 4321, 0.14
+    E = synthetic_embeddings(n, d, scale=0.01, seed=3, device="cuda")
+    L = _lib.lib()
+    ws = torch.empty(L.hyp_merge_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    best = torch.empty(32, dtype=torch.uint8, device="cuda")
+    check(L.hyp_row_min(ptr(E), d + 1, n, row, d + 1, 1.0, 1, thr, ptr(best), ptr(ws), ws.numel(), stream_ptr()))
+    got = HypBest.from_buffer_copy(best.cpu().numpy().tobytes())
+    dist = LM.distance(E, E[row:row + 1], 1.0, semantics="lorentz")
+    dist[row] = float("inf")
+    j = int(torch.argmin(dist).item())
+    assert (got.i, got.j) == (min(j, row), max(j, row))
+    assert np.float32(got.d) == dist[j].cpu().numpy()
+    assert (got.count_lo | (got.count_hi << 32)) == int((dist < np.float32(thr)).sum().item())
+
+
+def test_default_max_vocab_uses_resident_loop_and_matches(monkeypatch):
+    """max_vocab_size=100000 (the reference default) must not push a small job onto the slow path, and either
+    way the result is the same."""
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    from hyptokenizer_b200.tokenizer.hyperbolic_merge import HyperbolicTokenizer
+    res = []
+    for variant in ("resident", "l2"):
+        monkeypatch.setenv("HYP_MERGE_LOOP", variant)
+        emb = synthetic_embeddings(1200, 50, scale=0.1, seed=5, device="cuda")
+        tok = HyperbolicTokenizer([f"w{k}" for k in range(1200)], torch.nn.Parameter(emb), merge_threshold=1.5,
+                                  semantics="lorentz")           # default max_vocab_size
+        tok.optimize_merges(steps=300)
+        res.append((tok.last_trace.copy(), tok.embeddings[:1500].detach().cpu()))
+    assert np.array_equal(res[0][0], res[1][0]) and same_bits(res[0][1], res[1][1])
