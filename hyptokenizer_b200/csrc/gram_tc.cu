@@ -446,15 +446,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 }
 
 // tau_i = k-th smallest tile minimum of row i (thread per row, coalesced over rows), then
-// thr_i = tau_i + 2 eps_i with eps_i = 2^-9 * 1.05 * |xs_i| * max|xs| + 2e-6 * max(1, tau_i)
+// thr_i = tau_i + 2 eps_i with eps_i = 2^-9 * 1.05 * |xs_i| * max|xs| + 2e-6 * max(1, tau_i).
+// (Measured: the data-dependent insert diverges within a warp and costs ~1 ms at V=100k; splitting a row over
+// several threads made it slower.  A shared-memory transposed bisection select is the next step.)
 __global__ void kth_select_kernel(const float *__restrict__ tilemin, int64_t ld_tm, int64_t col_tiles, int64_t nrows,
                                   int64_t row0, int k, const float *__restrict__ nrm,
                                   const unsigned int *__restrict__ max_nrm_bits, float *__restrict__ thr) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrows) return;
-  float best[64];
+  float best[32];
   const float inf = __int_as_float(0x7f800000);
-  for (int q = 0; q < k; ++q) best[q] = inf;
+  for (int q = 0; q < 32; ++q) best[q] = inf;
   float worst = inf;
   int wpos = 0;
   // 8 independent loads in flight per thread (the tile minima stream from HBM once), then the rare inserts
@@ -493,13 +495,46 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
     const int m0 = overflow ? 0 : c0, m1 = overflow ? 0 : c1;
     for (int q = lane; q < TC_CAP; q += 32) keys[w][q] = kEmpty;
     __syncwarp();
+    // exact re-score, four candidates per warp pass: a group of 8 lanes IS ATen's 8 summation lanes
+    // (lane l owns elements 8k+l, partial k mod 4), so the order is reproduced with 4 registers per lane
     const float *xi = E + (row0 + r) * ldE;
-    for (int q = 0; q < m0 + m1; ++q) {
-      const int j = q < m0 ? cand[(2 * r) * TC_CAPH + q] : cand[(2 * r + 1) * TC_CAPH + (q - m0)];
-      const float mm = warp_mdot(xi, E + (int64_t)j * ldE, D, lane);
-      if (lane == 0) {
-        const float dv = dist_from_mdot(mm, sgn, sqrt_c);
-        if (dv == dv) keys[w][q] = ((unsigned long long)__float_as_uint(dv) << 32) | (unsigned int)j;
+    const int N = D - 1, vs = N >> 3, full = vs >> 2;
+    const int grp = lane >> 3, l8 = lane & 7;
+    if (N >= 8) {
+      for (int q0 = 0; q0 < m0 + m1; q0 += 4) {
+        const int q = q0 + grp;
+        const bool live = q < m0 + m1;
+        const int qq = live ? q : 0;
+        const int j = qq < m0 ? cand[(2 * r) * TC_CAPH + qq] : cand[(2 * r + 1) * TC_CAPH + (qq - m0)];
+        const float *xj = E + (int64_t)j * ldE;
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < 4 * full; ++k) {
+          const int e = 1 + 8 * k + l8;
+          part[k & 3] = __fadd_rn(part[k & 3], __fmul_rn(__ldg(xi + e), __ldg(xj + e)));
+        }
+        for (int k = 4 * full; k < vs; ++k) {
+          const int e = 1 + 8 * k + l8;
+          part[0] = __fadd_rn(part[0], __fmul_rn(__ldg(xi + e), __ldg(xj + e)));
+        }
+        const float Ll = __fadd_rn(__fadd_rn(__fadd_rn(part[0], part[1]), part[2]), part[3]);
+        float acc = 0.f;
+        for (int e = 8 * vs; e < N; ++e) acc = __fadd_rn(acc, __fmul_rn(__ldg(xi + 1 + e), __ldg(xj + 1 + e)));
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, __shfl_sync(HYP_FULL_MASK, Ll, (lane & 24) + t));
+        if (live && l8 == 0) {
+          const float mm = __fsub_rn(__fmul_rn(__ldg(xi), __ldg(xj)), acc);
+          const float dv = dist_from_mdot(mm, sgn, sqrt_c);
+          if (dv == dv) keys[w][q] = ((unsigned long long)__float_as_uint(dv) << 32) | (unsigned int)j;
+        }
+      }
+    } else {
+      for (int q = 0; q < m0 + m1; ++q) {
+        const int j = q < m0 ? cand[(2 * r) * TC_CAPH + q] : cand[(2 * r + 1) * TC_CAPH + (q - m0)];
+        const float mm = warp_mdot(xi, E + (int64_t)j * ldE, D, lane);
+        if (lane == 0) {
+          const float dv = dist_from_mdot(mm, sgn, sqrt_c);
+          if (dv == dv) keys[w][q] = ((unsigned long long)__float_as_uint(dv) << 32) | (unsigned int)j;
+        }
       }
     }
     __syncwarp();
