@@ -25,7 +25,7 @@
 // Warp roles per CTA (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
 // warps 2..9 epilogue (one thread per accumulator row = TMEM lane and 64-column half of the tile).  A CTA owns a 128-row block (its A
 // tile stays in shared memory) and streams all column tiles through a 2-stage B ring; accumulators are
-// double-buffered in TMEM (2 x 128 columns) so the epilogue of tile t overlaps the MMA of tile t+1.
+// quadruple-buffered in TMEM (4 x 128 columns) so the epilogue of tile t overlaps the MMA of tile t+1.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -40,6 +40,7 @@ constexpr int TC_KSLAB = 32;       // fp32 elements per 128-byte swizzle row
 constexpr int TC_SLAB_BYTES = TC_M * 128;   // 16 KiB: 128 rows x 128 B
 constexpr int TC_MAX_SLABS = 4;    // K padded up to 128
 constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_ACC = 4;           // accumulator buffers in TMEM (4 x 128 columns = all 512)
 constexpr int TC_EPI_WARPS = 8;    // 2 per TMEM lane quadrant: each handles one 64-column half of the tile
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_HALF = TC_N / 2;
@@ -229,16 +230,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail,
                const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // layout: A tile | B stages | colx0[2][128] | barriers | tmem ptr
+  // layout: A tile | B stages | colx0[TC_ACC][128] | barriers | tmem ptr
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *sA = base;
   uint8_t *sB = sA + p.stage_bytes;
   float *colx0 = reinterpret_cast<float *>(sB + (size_t)p.n_stages * p.stage_bytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(colx0 + 2 * TC_N);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(colx0 + TC_ACC * TC_N);
   uint64_t *a_full = bars + 0, *a_empty = bars + 1;
-  uint64_t *acc_full = bars + 2, *acc_empty = bars + 4;                  // [2] each
-  uint64_t *b_full = bars + 6, *b_empty = bars + 6 + TC_MAX_STAGES;     // [n_stages] each
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 6 + 2 * TC_MAX_STAGES);
+  uint64_t *acc_full = bars + 2, *acc_empty = bars + 2 + TC_ACC;                        // [TC_ACC] each
+  uint64_t *b_full = bars + 2 + 2 * TC_ACC, *b_empty = bars + 2 + 2 * TC_ACC + TC_MAX_STAGES;   // [n_stages] each
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 2 + 2 * TC_ACC + 2 * TC_MAX_STAGES);
   const uint32_t tile_tx = p.n_slabs * TC_SLAB_BYTES + TC_M * p.tail_row_bytes;
   const int tail_elem0 = p.n_slabs * TC_KSLAB;
 
@@ -249,7 +250,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < TC_ACC; ++s) {
       mbar_init(acc_full + s, 1);
       mbar_init(acc_empty + s, TC_EPI_WARPS);   // one arrival per epilogue warp
     }
@@ -259,7 +260,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 2 * TC_N);
+  if (warp == 1) tmem_alloc(tmem_ptr, TC_ACC * TC_N);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -331,7 +332,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           umma_commit(b_empty + bstage);     // B stage reusable once these MMAs have read it
           umma_commit(acc_full + abuf);      // accumulator ready for the epilogue
           if (++bstage == (uint32_t)p.n_stages) { bstage = 0; bphase ^= 1; }
-          if (++abuf == 2) { abuf = 0; accphase ^= 1; }
+          if (++abuf == TC_ACC) { abuf = 0; accphase ^= 1; }
         }
         umma_commit(a_empty);                // A tile reusable
       }
@@ -391,7 +392,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
         for (int chunk = 0; chunk < ((p.debug & 1) ? 0 : 2); ++chunk) {
           const float (&v)[32] = chunk == 0 ? v0 : v1;
-          const float *cxc = cx + chunk * 32;
+          float cxc[32];                                   // 8 x LDS.128 (broadcast) instead of 32 scalar loads
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 t4 = reinterpret_cast<const float4 *>(cx + chunk * 32)[c4];
+            cxc[4 * c4 + 0] = t4.x; cxc[4 * c4 + 1] = t4.y; cxc[4 * c4 + 2] = t4.z; cxc[4 * c4 + 3] = t4.w;
+          }
           if (PASS == 1) {
             if (!checked) {
               float m4[4] = {inf, inf, inf, inf};      // four independent min chains
@@ -431,7 +437,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + abuf);
         if (PASS == 1 && row_ok) p.tilemin[(2 * ct + half) * p.ld_tm + (gi - p.row0)] = fmaxf(tmin, 1.0f);
-        if (++abuf == 2) { abuf = 0; accphase ^= 1; }
+        if (++abuf == TC_ACC) { abuf = 0; accphase ^= 1; }
       }
       if (PASS == 2 && row_ok) p.cand_cnt[(gi - p.row0) * 2 + half] = cnt;
     }
@@ -441,7 +447,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 2 * TC_N);
+    tmem_dealloc(tmem_base, TC_ACC * TC_N);
   }
 }
 
@@ -602,10 +608,11 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
   L.stage_bytes = ((L.n_slabs * TC_SLAB_BYTES + TC_M * L.tail_row_bytes + 1023) / 1024) * 1024;
   const int budget = 220 * 1024 - 4096;
   L.n_stages = (budget - L.stage_bytes) / L.stage_bytes;
-  if (L.n_stages > TC_MAX_STAGES) L.n_stages = TC_MAX_STAGES;
+  if (L.n_stages > 2) L.n_stages = 2;      // measured: a deeper B ring does not help (the MMA issue rate and the
+                                            // TMEM drain, not TMA latency, bound the tile loop); HYP_TC_STAGES overrides
   if (const char *e = getenv("HYP_TC_STAGES")) {
     const int want = atoi(e);
-    if (want >= 1 && want < L.n_stages) L.n_stages = want;
+    if (want >= 1 && want <= TC_MAX_STAGES && (1 + want) * L.stage_bytes <= budget) L.n_stages = want;
   }
   if (L.n_stages < 1) L.n_stages = 1;
   L.col_tiles = (n + TC_N - 1) / TC_N;
@@ -711,7 +718,8 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   p.debug = getenv("HYP_TC_DEBUG") ? atoi(getenv("HYP_TC_DEBUG")) : 0;
   p.sgn = semantics == HYP_SEM_REFERENCE ? -1.f : 1.f;
   p.x0 = x0; p.tilemin = tilemin; p.ld_tm = L.ld_tm; p.thr = thr; p.cand = cand; p.cand_cnt = cnt;
-  const size_t smem = 1024 + (size_t)(1 + L.n_stages) * L.stage_bytes + 2 * TC_N * 4 + (8 + 2 * TC_MAX_STAGES) * 8;
+  const size_t smem = 1024 + (size_t)(1 + L.n_stages) * L.stage_bytes + TC_ACC * TC_N * 4 +
+                      (4 + 2 * TC_ACC + 2 * TC_MAX_STAGES) * 8;
   const bool pos = p.sgn > 0.f;
   auto k1 = pos ? gram_tc_kernel<1, true> : gram_tc_kernel<1, false>;
   auto k2 = pos ? gram_tc_kernel<2, true> : gram_tc_kernel<2, false>;
