@@ -200,11 +200,7 @@ def run_ours(a):
         dist.barrier()
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    mprof = ws_lp[96:160].cpu().numpy().view(np.int64)
     prof = ws_lp[32:96].cpu().numpy().view(np.int64)
-    if rank == 0 and prof[3] > 0:
-        print("[midpoint sub-phases] mdot, coef, w(fp64 div), v loop, expmap, norm+x0, out:",
-              [int(x / max(int(prof[3]), 1)) for x in mprof[:7]], file=sys.stderr)
     if rank == 0 and prof[3] > 0:
         for name, base in (("cta0", 0), ("ctaN", 4)):
             n_ = max(int(prof[base + 3]), 1)

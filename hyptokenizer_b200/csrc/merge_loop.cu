@@ -393,6 +393,55 @@ __device__ __forceinline__ float resident_mdot_static(const float4 *__restrict__
   return __fsub_rn(__fmul_rn(T0[slot], q0), acc);
 }
 
+// Same product, one row split over TWO adjacent threads (sub = 0/1).  Thread `sub` takes the float4 groups
+// g = sub, sub+2, ...; group g feeds the partials 4(g mod 8)..+3, so each thread owns 16 of the 32 partials
+// outright (in-order accumulation preserved), owns the lane sums L[4 sub .. 4 sub + 3] outright, and only the
+// final 8-term chain needs four shuffles.  Halves the dependent chain that bounds the scan phase while the CTA
+// holds at most half as many rows as it has scanning threads.
+// The result is valid on the even lane (sub == 0).  All 32 lanes must call it (shuffles).
+template <int N>
+__device__ __forceinline__ float resident_mdot_static2(const float4 *__restrict__ T4, const float *__restrict__ T0, int S,
+                                                       int slot, const float4 *__restrict__ q4, float q0, int sub) {
+  constexpr int vs = N / 8, full = vs / 4, G4 = (N + 3) / 4;
+  static_assert(N >= 8 && N - 8 * vs <= 4, "tail must fit the first tail group (owned by sub 0)");
+  float P[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) P[k] = 0.f;
+  float tail = 0.f;
+#pragma unroll
+  for (int j = 0; j < (G4 + 1) / 2; ++j) {
+    const int g = 2 * j + sub;
+    if (g < G4) {
+      const float4 a = T4[(size_t)g * S + slot];
+      const float4 b = q4[g];
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float pr = __fmul_rn(av[c], bv[c]);
+        if (8 * j < 32 * full) {                       // full rounds: partial (g mod 8) * 4 + c
+          P[(j & 3) * 4 + c] = __fadd_rn(P[(j & 3) * 4 + c], pr);
+        } else if (8 * j < 8 * vs) {                   // left-over lane vectors join partial 0 of their lane
+          P[c] = __fadd_rn(P[c], pr);
+        } else if (8 * j + 4 * sub + c < N) {          // scalar tail (only sub 0 has any)
+          tail = __fadd_rn(tail, pr);
+        }
+      }
+    }
+  }
+  float L[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) L[c] = __fadd_rn(__fadd_rn(__fadd_rn(P[c], P[4 + c]), P[8 + c]), P[12 + c]);
+  float Lo[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) Lo[c] = __shfl_down_sync(HYP_FULL_MASK, L[c], 1);   // L[4..7] from the odd lane
+  float acc = tail;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc = __fadd_rn(acc, L[c]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc = __fadd_rn(acc, Lo[c]);
+  return __fsub_rn(__fmul_rn(T0[slot], q0), acc);
+}
+
 // any N (including N < 8): scalar reads of the same layout
 __device__ __forceinline__ float resident_mdot_dynamic(const float4 *__restrict__ T4, const float *__restrict__ T0, int S,
                                                        int slot, const float4 *__restrict__ q4, float q0, int N) {
@@ -482,10 +531,15 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   __syncthreads();
   if (threadIdx.x == 0) t_mark = clock64();
 
+  // loop-carried bookkeeping without integer division: rows this CTA owns below n, and whether/where row n lands here
+  int owned = (n > b) ? (n - b + G - 1) / G : 0;
+  int n_mod = n % G, n_div = n / G;
+  float thr_f = (float)thr;
+
   for (int k = 0; k < p.max_steps; ++k) {
     // invariant: qrow[cur] / qq4[cur] hold the merged row for `best`, computed from xi, xj, s_len
-    const bool cmp_double = n <= 100;
-    const bool have = best.i >= 0 && (cmp_double ? ((double)best.d < thr) : (best.d < (float)thr));
+    bool have = best.i >= 0;
+    if (have) have = (n <= 100) ? ((double)best.d < thr) : (best.d < thr_f);   // hyperbolic_merge.py:288 vs :262
     if (!have) { stop = 1; break; }
     if (n >= cap) { stop = 2; break; }
     const float *q = qrow + cur * D;
@@ -493,12 +547,7 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
     unsigned long long win = kNoKey;
 
     if (spec_warp) {
-      // ---- speculation: if this step's scan does not produce a better pair, `best` (and so its rows)
-      // stays, and the NEXT merged row is the midpoint of the same operands.  It is recomputed here, in
-      // full, while the other warps scan and exchange; it is used only if the guess holds.
-      midpoint_into(cur ^ 1, scratch + 2 * D);
-    } else {
-      if (b == 0 && warp == 0) {
+      if (b == 0) {
         // append row n = q to the table in global memory (the caller's `embeddings`), log the merge
         for (int e = lane; e < D; e += 32) p.E[(int64_t)n * p.ldE + e] = q[e];
         if (lane == 0) {
@@ -506,25 +555,44 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
           p.log[k] = hyp_merge_record{best.i, best.j, best.d, n};
         }
       }
-      // ---- score row n against the resident rows (< n) of this CTA: one thread per row ------------
-      const int owned = (n > b) ? (n - b + G - 1) / G : 0;
+      // ---- speculation: if this step's scan does not produce a better pair, `best` (and so its rows)
+      // stays, and the NEXT merged row is the midpoint of the same operands.  It is recomputed here, in
+      // full, while the other warps scan and exchange; it is used only if the guess holds.
+      midpoint_into(cur ^ 1, scratch + 2 * D);
+      // (row n / len / log become visible to the other CTAs through the CTA barrier below + thread 0's release in
+      //  the next exchange; nobody reads row n from global memory before that)
+    } else {
+      // ---- score row n against the resident rows (< n) of this CTA ---------------------------------------
       const float q0 = q[0];
       unsigned long long mine = kNoKey;
-      for (int t = threadIdx.x; t < owned; t += kWork) {
-        const float m = (NS > 0) ? resident_mdot_static<(NS > 0 ? NS : 8)>(T4, T0, S, t, q4, q0)
-                                 : resident_mdot_dynamic(T4, T0, S, t, q4, q0, N);
-        const float d = dist_from_mdot(m, p.sgn, p.sqrt_c);
-        if (d == d) {
-          const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)(t * G + b);
-          mine = key < mine ? key : mine;
+      if (NS > 0 && owned <= kWork / 2) {
+        // few rows: two adjacent threads per row (warp-uniform trip count; idle pairs recompute slot 0, discarded)
+        const int sub = threadIdx.x & 1;
+        const int t = threadIdx.x >> 1;
+        if ((threadIdx.x & ~31) >> 1 < owned) {
+          const bool live = t < owned;
+          const float m = resident_mdot_static2<(NS > 0 ? NS : 8)>(T4, T0, S, live ? t : 0, q4, q0, sub);
+          if (live && sub == 0) {
+            const float d = dist_from_mdot(m, p.sgn, p.sqrt_c);
+            if (d == d) mine = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)(t * G + b);
+          }
+        }
+      } else {
+        for (int t = threadIdx.x; t < owned; t += kWork) {
+          const float m = (NS > 0) ? resident_mdot_static<(NS > 0 ? NS : 8)>(T4, T0, S, t, q4, q0)
+                                   : resident_mdot_dynamic(T4, T0, S, t, q4, q0, N);
+          const float d = dist_from_mdot(m, p.sgn, p.sqrt_c);
+          if (d == d) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)(t * G + b);
+            mine = key < mine ? key : mine;
+          }
         }
       }
       // the owner of row n appends it (its slot is beyond `owned`, so nobody reads it this step)
-      if (n % G == b) {
-        const int sl = n / G;
+      if (n_mod == b) {
         for (int e = threadIdx.x; e < D; e += kWork) {
-          if (e == 0) T0[sl] = q[0];
-          else Tf[((size_t)((e - 1) >> 2) * S + sl) * 4 + ((e - 1) & 3)] = q[e];
+          if (e == 0) T0[n_div] = q[0];
+          else Tf[((size_t)((e - 1) >> 2) * S + n_div) * 4 + ((e - 1) & 3)] = q[e];
         }
       }
 #pragma unroll
@@ -578,10 +646,12 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
     }
     cur ^= 1;
     if (threadIdx.x == 0) { long long t = clock64(); t_mid += t - t_mark; t_mark = t; }
+    if (n_mod == b) ++owned;
     ++n;
+    if (++n_mod == G) { n_mod = 0; ++n_div; }
     ++done;
     const int step = p.step0 + k;
-    if (p.thr_every > 0 && step > 0 && step % p.thr_every == 0) thr *= p.thr_mul;
+    if (p.thr_every > 0 && step > 0 && step % p.thr_every == 0) { thr *= p.thr_mul; thr_f = (float)thr; }
   }
 
   if (threadIdx.x == 0 && (b == 0 || b == G - 1)) {
