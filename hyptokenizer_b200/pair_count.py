@@ -24,7 +24,10 @@ def to_device_bytes(data: Union[bytes, bytearray, memoryview, np.ndarray, torch.
             raise TypeError("corpus tensor must be uint8")
         return t.to(device).contiguous()
     arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
-    host = torch.from_numpy(np.ascontiguousarray(arr))
+    arr = np.ascontiguousarray(arr)
+    if not arr.flags.writeable:
+        arr = arr.copy()             # torch refuses read-only buffers (bytes objects)
+    host = torch.from_numpy(arr)
     if host.numel() and torch.cuda.is_available():
         host = host.pin_memory()
     return host.to(device, non_blocking=True)
@@ -38,6 +41,8 @@ def count_pairs_device(text: torch.Tensor, hash_capacity: int = 1 << 20):
     dev = text.device
     _lib.check_device(dev)
     text = text.contiguous()
+    if text.data_ptr() % 16:
+        text = text.clone()          # the kernel stages the stream with 16-byte vector loads
     ascii_counts = torch.empty(128 * 128, dtype=torch.int64, device=dev)
     keys = torch.empty(hash_capacity, dtype=torch.int64, device=dev)
     vals = torch.empty(hash_capacity, dtype=torch.int64, device=dev)

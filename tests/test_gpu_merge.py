@@ -298,3 +298,55 @@ def test_default_max_vocab_uses_resident_loop_and_matches(monkeypatch):
         tok.optimize_merges(steps=300)
         res.append((tok.last_trace.copy(), tok.embeddings[:1500].detach().cpu()))
     assert np.array_equal(res[0][0], res[1][0]) and same_bits(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("d,c,sem,scale,thr", [(3, 0.7, "lorentz", 0.5, 3.0), (7, 2.5, "lorentz", 0.3, 1.0),
+                                               (16, 0.7, "lorentz", 0.2, 1.5), (50, 1.3, "lorentz", 0.1, 1.0),
+                                               (33, 1.0, "reference", 0.1, 0.1), (8, 1.0, "lorentz", 0.2, 2.0)])
+def test_device_loop_vs_oracle_other_shapes(monkeypatch, d, c, sem, scale, thr):
+    """Row lengths that exercise the N < 8 summation path, odd tails, the dynamic-N resident kernel and the
+    L2 kernel, with curvature != 1: merge sequence identical to the oracle's brute-force loop."""
+    from hyptokenizer_b200.tokenizer.hyperbolic_merge import HyperbolicTokenizer
+    from oracle import lorentz as OL
+    from oracle import merge as OM
+    torch.manual_seed(d)
+    # 24 steps: when the argmin keeps involving the newest token, token strings grow like Fibonacci numbers
+    # (reference behaviour: vocab.append(token_i + token_j)); 60 steps would need 2^40 characters
+    n0, steps = 150, 24
+    emb = OL.initialize_embeddings(n0, d, c=c, scale=scale)
+    vocab = [f"t{k}" * (1 + k % 3) for k in range(n0)]           # uneven token lengths -> uneven midpoint weights
+    ora = OM.OracleTokenizer(vocab, emb, c, thr, 256, sem)
+    ora.optimize_merges(steps)
+    for variant in ("resident", "l2"):
+        monkeypatch.setenv("HYP_MERGE_LOOP", variant)
+        tok = HyperbolicTokenizer(vocab, torch.nn.Parameter(emb.clone()), curvature=c, merge_threshold=thr,
+                                  max_vocab_size=256, semantics=sem)
+        tok.optimize_merges(steps=steps)
+        got = [(int(a), int(b)) for a, b in zip(tok.last_trace["i"], tok.last_trace["j"])]
+        assert got == [(a, b) for a, b, _ in ora.trace], variant
+        assert tok.vocab == ora.vocab
+        want = np.array([t[2] for t in ora.trace], dtype=np.float32)
+        assert np.all(np.abs(tok.last_trace["d"] - want) <= REL * np.abs(want) + 1e-12)
+
+
+def test_threshold_schedule_and_regime_switch():
+    """train(): threshold *= 1.05 after every 1000th step (scripts/train_hyperbolic_tokenizer.py:282-283) is applied
+    on the device; crossing n = 100 switches the comparison regime (hyperbolic_merge.py:247 vs :270)."""
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    from hyptokenizer_b200.tokenizer.hyperbolic_merge import HyperbolicTokenizer
+    emb = synthetic_embeddings(60, 20, scale=0.05, seed=2, device="cuda")
+    tok = HyperbolicTokenizer([f"w{k}" for k in range(60)], torch.nn.Parameter(emb), merge_threshold=0.5,
+                              max_vocab_size=4000, semantics="lorentz")
+    rec = tok.train(merge_steps=100000, target_vocab_size=2200)
+    assert len(rec) == 2140 and len(tok.vocab) == 2200
+    assert abs(tok.merge_threshold - 0.5 * 1.05 * 1.05) < 1e-12          # steps 1000 and 2000
+    # a reference-style host replay of the same loop gives the same tokenizer
+    emb = synthetic_embeddings(60, 20, scale=0.05, seed=2, device="cuda")
+    ref = HyperbolicTokenizer([f"w{k}" for k in range(60)], torch.nn.Parameter(emb), merge_threshold=0.5,
+                              max_vocab_size=4000, semantics="lorentz")
+    for step in range(300):
+        cands = ref._find_merge_candidates()
+        cands.sort(key=lambda x: x[2])
+        ref._merge_tokens(cands[0][0], cands[0][1])
+    assert ref.vocab == tok.vocab[:360]
+    assert same_bits(ref.embeddings[:360], tok.embeddings[:360])
