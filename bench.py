@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--v0", type=int, default=V0)
     ap.add_argument("--target", type=int, default=TARGET)
     ap.add_argument("--dim", type=int, default=D_EMB)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "tok"],
                     help="c2: merge loop (headline, merges/s); c3: all-pairs Lorentz distance + top-k=32 over V=100k, "
                          "row-sharded over the ranks with an all-gather (TFLOP/s)")
     ap.add_argument("--engine", default="tc", choices=["tc", "exact"])
@@ -503,10 +503,80 @@ def run_c4(a):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------
+# batched tokenize: what scripts/benchmark_efficiency.py measures, tokens/s
+# ------------------------------------------------------------------------------------------------
+def run_tok(a):
+    import random
+    from hyptokenizer_b200 import _lib
+    from hyptokenizer_b200._lib import check, ptr
+    from hyptokenizer_b200.synth import synthetic_corpus, synthetic_embeddings
+    from hyptokenizer_b200.tokenizer.batch_tokenize import RuleTable
+    from hyptokenizer_b200.tokenizer.hyperbolic_merge import HyperbolicTokenizer
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    L = _lib.lib()
+    chars = list("abcdefghijklmnopqrstuvwxyz ")
+    vocab = ["<pad>", "<bos>", "<eos>", "<unk>"] + chars
+    rng = random.Random(0)
+    pool, history = list(chars[:-1]), []
+    for _ in range(2000):                           # 2000 BPE-like rules over the synthetic alphabet
+        x, y = rng.choice(pool), rng.choice(pool)
+        if len(x + y) <= 6:
+            history.append((x, y, x + y))
+            pool.append(x + y)
+    tok = HyperbolicTokenizer(vocab + [h[2] for h in history], torch.nn.Parameter(
+        synthetic_embeddings(len(vocab) + len(history), 8)), max_vocab_size=len(vocab) + len(history) + 1, device=dev)
+    tok.merge_history = history
+    rules = {(x, y): z for x, y, z in history}
+    table = RuleTable(rules, tok.vocab, tok.token2idx, dev)
+    nbytes = 256 << 20
+    host = synthetic_corpus(nbytes, seed=0)
+    nl = np.flatnonzero(host == 10)
+    offsets = np.concatenate([[0], nl + 1, [nbytes]]).astype(np.int64)       # newline stays at the end of each text
+    d_text = torch.from_numpy(host).to(dev)
+    d_off = torch.from_numpy(offsets).to(dev)
+    n_texts = len(offsets) - 1
+    d_tok = torch.empty(nbytes, dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros(n_texts, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for it in range(a.warmup + a.steps):
+        e0.record(stream)
+        check(L.hyp_apply_merges(ptr(d_text), ptr(d_off), n_texts, ptr(table.d_ascii), ptr(table.d_cp), ptr(table.d_cp_sym),
+                                 table.n_cp, ptr(table.d_keys), ptr(table.d_vals), table.capacity, ptr(d_tok), ptr(d_cnt),
+                                 stream.cuda_stream))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if it >= a.warmup:
+            ts.append(e0.elapsed_time(e1))
+    n_tokens = int(d_cnt.sum().item())
+    ms = float(np.mean(ts))
+    line = {"metric": "tokenize tokens/s (batched apply-merges)", "value": n_tokens / (ms * 1e-3), "unit": "tokens/s",
+            "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+            "config": {"workload": f"tok: {nbytes >> 20} MiB ASCII, {n_texts} lines, {len(rules)} merge rules",
+                       "input_GBps": nbytes / (ms * 1e-3) / 1e9, "tokens_out": n_tokens}, "gpu_launches": a.steps}
+    if not a.no_cpu_baseline:
+        from oracle.merge import OracleTokenizer
+        ora = OracleTokenizer(tok.vocab, synthetic_embeddings(len(tok.vocab), 8), max_vocab_size=len(tok.vocab) + 1)
+        ora.merge_history = history
+        sample = host[: int(offsets[20000])].tobytes().decode("ascii").split("\n")[:20000]
+        t0 = time.perf_counter()
+        cnt = sum(len(ora.tokenize(ln + "\n")) for ln in sample)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": cnt / dt, "unit": "tokens/s", "cores": 1, "kind": "port",
+                                "sample": "first 20 000 lines through the oracle's tokenize() (the reference's Python loop)"}
+    print(json.dumps(line))
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "tok":
+        run_tok(args)
     elif args.workload == "c4":
         run_c4(args)
     elif args.workload == "c3":

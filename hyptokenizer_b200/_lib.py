@@ -65,6 +65,7 @@ _SIGNATURES = {
                         C.c_int),
     "hyp_row_min": ([_p, _i64, _i64, _i64, _i32, _f, _i32, _f, _p, _p, _i64, _p], C.c_int),
     "hyp_coherence_distances": ([_p, _i64, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _f, _i32, _p], C.c_int),
+    "hyp_apply_merges": ([_p, _p, _i64, _p, _p, _p, _i32, _p, _p, _i64, _p, _p, _p], C.c_int),
     "hyp_pair_count": ([_p, _i64, _p, _p, _p, _i64, _p, _p], C.c_int),
 }
 

@@ -274,6 +274,16 @@ class HyperbolicTokenizer:
                     k += 1
         return tokens
 
+    def tokenize_batch(self, texts) -> List[List[str]]:
+        """`[self.tokenize(t) for t in texts]` in one device launch (csrc/apply_merges.cu)."""
+        from .batch_tokenize import tokenize_batch
+        return tokenize_batch(self, texts)
+
+    def encode_batch(self, texts) -> List[List[int]]:
+        """`[self.encode(t) for t in texts]` in one device launch."""
+        from .batch_tokenize import encode_batch
+        return encode_batch(self, texts)
+
     def encode(self, text: str) -> List[int]:
         """reference hyperbolic_merge.py:448-459."""
         unk = self.token2idx.get("<unk>", 3)

@@ -201,6 +201,20 @@ int hyp_pair_count(const uint8_t *text, int64_t n_bytes, unsigned long long *asc
                    unsigned long long *hash_keys, unsigned long long *hash_vals,
                    int64_t hash_capacity, int *overflow, void *stream);
 
+/* ---- batched tokenize (tokenizer/hyperbolic_merge.py:414-446; what scripts/benchmark_efficiency.py
+ * :58-94 measures) -------------------------------------------------------------------------------
+ * n_texts UTF-8 texts, text t = bytes [offsets[t], offsets[t+1]).  Tokens are host-assigned symbol ids
+ * (one per distinct string in a rule or single-character vocabulary entry): ascii_sym[128] maps ASCII
+ * code points to ids (-1: none), (cp_sorted, cp_sym)[n_cp] the other code points (sorted).  Rules live
+ * in an open-addressing table: rule_keys[h] = (a << 32 | b), 0xFFFF.. = empty, rule_vals[h] = merged id;
+ * capacity a power of two; duplicates already resolved last-wins.  Output: tokens[offsets[t] ..
+ * offsets[t] + n_tokens[t]) = the text's final token ids (characters without an id as -(cp+1)).
+ * `tokens` needs one int32 per input byte. */
+int hyp_apply_merges(const uint8_t *text, const int64_t *offsets, int64_t n_texts,
+                     const int32_t *ascii_sym, const uint32_t *cp_sorted, const int32_t *cp_sym,
+                     int32_t n_cp, const unsigned long long *rule_keys, const int32_t *rule_vals,
+                     int64_t rule_capacity, int32_t *tokens, int32_t *n_tokens, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
