@@ -98,7 +98,78 @@ pair_count_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long lon
     __syncthreads();
     Text T{text, n, win, w0, w1};
 
-    for (int64_t p = c0 + threadIdx.x; p < c1; p += blockDim.x) {
+    // One thread takes 16 consecutive bytes.  ASCII fast path: the 16 bytes plus 4 bytes of context on either
+    // side sit in six registers, and a pair (a, b) is counted when neither is a line break and
+    //   left : a is not a space, or the byte before a is neither space nor break        (else: scan back)
+    //   right: b is not a space, or the byte after  b is neither space nor break        (else: scan ahead)
+    // Anything else in the 24-byte neighbourhood (a non-ASCII byte, a run of two or more spaces next to the
+    // pair) takes the general per-position path below.
+    for (int64_t base = c0 + 16 * (int64_t)threadIdx.x; base < c1; base += 16 * (int64_t)blockDim.x) {
+      uint32_t W[6];
+      {
+        const uint4 mid = *reinterpret_cast<const uint4 *>(win + (base - w0));
+        W[1] = mid.x; W[2] = mid.y; W[3] = mid.z; W[4] = mid.w;
+        W[0] = (base - 4 >= w0) ? *reinterpret_cast<const uint32_t *>(win + (base - 4 - w0)) : 0x0a0a0a0au;
+        W[5] = (base + 20 <= w1) ? *reinterpret_cast<const uint32_t *>(win + (base + 16 - w0)) : 0x0a0a0a0au;
+      }
+      const int64_t valid = n - base;                      // bytes of this 16-byte group that exist
+      bool fast = valid >= 20 && base - 4 >= w0;           // groups touching either end of the text go slow
+      fast = fast && (((W[0] | W[1] | W[2] | W[3] | W[4] | W[5]) & 0x80808080u) == 0);
+      if (fast) {
+        auto byte_at = [&](int j) -> uint32_t { return (W[(j + 4) >> 2] >> (8 * ((j + 4) & 3))) & 0xffu; };
+        const unsigned long long space_mask = (0x1fULL << 9) | (0x1fULL << 28);   // 9..13, 28..32
+        auto sp = [&](uint32_t c) -> bool { return c < 64 && ((space_mask >> c) & 1ULL); };
+        auto nl = [&](uint32_t c) -> bool { return c == 0x0a || c == 0x0d; };
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t a = byte_at(i), bch = byte_at(i + 1);
+          if (nl(a) || nl(bch)) continue;
+          bool ok = true;
+          bool slow = false;
+          if (sp(a)) {
+            const uint32_t pa = byte_at(i - 1);
+            if (nl(pa)) ok = false;
+            else if (sp(pa)) slow = true;
+          }
+          if (ok && sp(bch)) {
+            const uint32_t nb = byte_at(i + 2);
+            if (nl(nb)) ok = false;
+            else if (sp(nb)) slow = true;
+          }
+          if (!ok) continue;
+          if (slow) {
+            // a run of spaces next to the pair: resolve with the general scans
+            const int64_t pp = base + i;
+            bool left = !sp(a), right = !sp(bch);
+            if (!left) {
+              int64_t q = pp - 1;
+              while (q >= 0) {
+                const uint32_t cq = T.at(q);
+                if (cq >= 0x80) { int l2; const int64_t qs = T.is_start(q) ? q : T.prev_start(q); const uint32_t cp = T.decode(qs, l2);
+                                  if (!is_space(cp)) { left = true; break; } q = qs - 1; continue; }
+                if (nl(cq)) break;
+                if (!sp(cq)) { left = true; break; }
+                --q;
+              }
+            }
+            if (left && !right) {
+              int64_t q = pp + 2;
+              while (q < n) {
+                int l2;
+                const uint32_t cq = T.decode(q, l2);
+                if (is_nl(cq)) break;
+                if (!is_space(cq)) { right = true; break; }
+                q += l2;
+              }
+            }
+            if (!(left && right)) continue;
+          }
+          atomicAdd(&hist[a * 128 + bch], 1u);
+        }
+        continue;
+      }
+      const int64_t p_end = (base + 16 < c1) ? base + 16 : c1;
+      for (int64_t p = base; p < p_end; ++p) {
       if (!T.is_start(p)) continue;
       int la, lb;
       const uint32_t a = T.decode(p, la);
@@ -136,6 +207,7 @@ pair_count_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long lon
         atomicAdd(&hist[a * 128 + b], 1u);
       } else {
         hash_add(hkeys, hvals, cap_mask, ((unsigned long long)a << 32) | b, overflow);
+      }
       }
     }
   }
