@@ -203,9 +203,16 @@ class HyperbolicTokenizer:
         rec = log[: out.steps_done].cpu().numpy().view(_RECORD_DTYPE).reshape(-1)
         self._last_state = out
         self.merge_threshold = out.threshold if threshold_every > 0 else self.merge_threshold
-        vocab = self.vocab
+        # host strings from the (i, j) log, exactly what _merge_tokens does per merge (:347-355), inlined
+        vocab, t2i, hist, n = self.vocab, self.token2idx, self.merge_history, self.current_vocab_size
         for i, j in zip(rec["i"].tolist(), rec["j"].tolist()):
-            self._append_token(vocab[i], vocab[j])
+            a, b = vocab[i], vocab[j]
+            m = a + b
+            vocab.append(m)
+            t2i[m] = n
+            n += 1
+            hist.append((a, b, m))
+        self.current_vocab_size = n
         assert self.current_vocab_size == out.n
         return rec, out.stop
 
