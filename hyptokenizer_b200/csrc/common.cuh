@@ -51,8 +51,9 @@ __device__ __forceinline__ float dist_from_mdot(float m, float sgn, float sqrt_c
 // part[0]; lanes[l] = ((part0+part1)+part2)+part3; acc = scalar tail (from 0) then += lanes[0..7].
 // Thread t = 8c + l therefore owns exactly the elements t + 32r  -- a coalesced stride.
 // ---------------------------------------------------------------------------------------------
-template <typename ProdFn>
-__device__ __forceinline__ float warp_sum_aten(ProdFn prod, int N, int lane) {
+template <int NS = 0, typename ProdFn>
+__device__ __forceinline__ float warp_sum_aten(ProdFn prod, int Nrt, int lane) {
+  const int N = NS > 0 ? NS : Nrt;   // NS > 0: trip counts are compile-time constants, every loop unrolls
   if (N < 8) {
     // scalar row_sum with 4 interleaved partials; every lane computes it redundantly.
     float part[4] = {0.f, 0.f, 0.f, 0.f};
@@ -69,19 +70,33 @@ __device__ __forceinline__ float warp_sum_aten(ProdFn prod, int N, int lane) {
   const int full = vs >> 2;
   const int c = lane >> 3, l = lane & 7;
   float P = 0.f;
+  if (NS > 0) {
+#pragma unroll
+    for (int r = 0; r < (NS > 0 ? (NS >> 3) >> 2 : 1); ++r) P = __fadd_rn(P, prod(32 * r + lane));
+    if (c == 0) {
+#pragma unroll
+      for (int k = 4 * ((NS >> 3) >> 2); k < (NS >> 3); ++k) P = __fadd_rn(P, prod(8 * k + l));
+    }
+  } else {
 #pragma unroll 4
-  for (int r = 0; r < full; ++r) P = __fadd_rn(P, prod(32 * r + lane));
-  if (c == 0) {
+    for (int r = 0; r < full; ++r) P = __fadd_rn(P, prod(32 * r + lane));
+    if (c == 0) {
 #pragma unroll 3
-    for (int k = 4 * full; k < vs; ++k) P = __fadd_rn(P, prod(8 * k + l));
+      for (int k = 4 * full; k < vs; ++k) P = __fadd_rn(P, prod(8 * k + l));
+    }
   }
   float p1 = __shfl_down_sync(HYP_FULL_MASK, P, 8);
   float p2 = __shfl_down_sync(HYP_FULL_MASK, P, 16);
   float p3 = __shfl_down_sync(HYP_FULL_MASK, P, 24);
   float L = __fadd_rn(__fadd_rn(__fadd_rn(P, p1), p2), p3);  // valid on lanes 0..7
   float acc = 0.f;
+  if (NS > 0) {
+#pragma unroll
+    for (int k = 8 * (NS >> 3); k < NS; ++k) acc = __fadd_rn(acc, prod(k));
+  } else {
 #pragma unroll 7
-  for (int k = 8 * vs; k < N; ++k) acc = __fadd_rn(acc, prod(k));
+    for (int k = 8 * vs; k < N; ++k) acc = __fadd_rn(acc, prod(k));
+  }
   float Lq[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) Lq[q] = __shfl_sync(HYP_FULL_MASK, L, q);   // independent shuffles first
@@ -91,25 +106,38 @@ __device__ __forceinline__ float warp_sum_aten(ProdFn prod, int N, int lane) {
 }
 
 // <x,y> with signature (+,-,...,-), lorentz_model.py:25:  fl(fl(x0*y0) - sum_fp32(fl(xs*ys))).
+template <int NS = 0>
 __device__ __forceinline__ float warp_mdot(const float *__restrict__ x, const float *__restrict__ y,
                                            int D, int lane) {
   const float *xs = x + 1, *ys = y + 1;
-  float s = warp_sum_aten([&](int e) { return __fmul_rn(xs[e], ys[e]); }, D - 1, lane);
+  float s = warp_sum_aten<NS>([&](int e) { return __fmul_rn(xs[e], ys[e]); }, D - 1, lane);
   return __fsub_rn(__fmul_rn(x[0], y[0]), s);
 }
 
 // torch.norm(v, dim=-1) of N contiguous floats (lorentz_model.py:53): 8 lane accumulators
 // (rounded products, no FMA) over k in order, lanes folded 0..7, tail in groups of 4 with rounded
 // products, then a <= 3 element remainder with FMA, then sqrt.
-template <typename ElemFn>
-__device__ __forceinline__ float warp_norm_aten(ElemFn elem, int N, int lane) {
+template <int NS = 0, typename ElemFn>
+__device__ __forceinline__ float warp_norm_aten(ElemFn elem, int Nrt, int lane) {
+  const int N = NS > 0 ? NS : Nrt;
   const int vs = N >> 3;
   float a = 0.f;
   if (lane < 8) {
+    if (NS > 0) {
+      float sq[NS > 0 ? (NS >> 3) + 1 : 1];             // all loads and squares first, then the ordered adds
+#pragma unroll
+      for (int k = 0; k < (NS >> 3); ++k) {
+        const float v = elem(8 * k + lane);
+        sq[k] = __fmul_rn(v, v);
+      }
+#pragma unroll
+      for (int k = 0; k < (NS >> 3); ++k) a = __fadd_rn(a, sq[k]);
+    } else {
 #pragma unroll 4
-    for (int k = 0; k < vs; ++k) {
-      float v = elem(8 * k + lane);
-      a = __fadd_rn(a, __fmul_rn(v, v));
+      for (int k = 0; k < vs; ++k) {
+        float v = elem(8 * k + lane);
+        a = __fadd_rn(a, __fmul_rn(v, v));
+      }
     }
   }
   float b = __shfl_sync(HYP_FULL_MASK, a, 0);
@@ -223,11 +251,11 @@ __device__ __forceinline__ float logmap_coef(float m, int semantics, float *m_si
 }
 
 // out = exp_x(v) (lorentz_model.py:85-93); v holds D floats readable by the whole warp.
-template <typename OutFn>
+template <int NS = 0, typename OutFn>
 __device__ __forceinline__ void warp_expmap(const float *__restrict__ x, const float *v, int D,
                                             int lane, OutFn out) {
   const float *vs = v + 1;
-  float sq = warp_sum_aten([&](int e) { return __fmul_rn(vs[e], vs[e]); }, D - 1, lane);
+  float sq = warp_sum_aten<NS>([&](int e) { return __fmul_rn(vs[e], vs[e]); }, D - 1, lane);
   float vn = __fsqrt_rn(clamp_min(sq, 1e-8f));
   float small = (vn < 1e-6f) ? 1.f : 0.f;
   float den = __fadd_rn(vn, small);
@@ -242,14 +270,14 @@ __device__ __forceinline__ void warp_expmap(const float *__restrict__ x, const f
 
 // Full chain; `buf` = 2*D floats of shared scratch private to the warp. Result row left in
 // buf[0..D) and returned through out(k, value).
-template <typename OutFn>
+template <int NS = 0, typename OutFn>
 __device__ __forceinline__ void warp_midpoint(const float *__restrict__ xi, const float *__restrict__ xj,
                                               int len_i, int len_j, int D, float c, int semantics,
                                               bool project, float *buf, int lane, OutFn out,
                                               long long *tp = nullptr) {
   float *v = buf, *m_row = buf + D;
   long long tc0 = tp ? clock64() : 0;
-  float m = warp_mdot(xi, xj, D, lane);
+  float m = warp_mdot<NS>(xi, xj, D, lane);
   if (tp) { long long t = clock64(); tp[0] += t - tc0; tc0 = t; }
   float ms;
   float coef = logmap_coef(m, semantics, &ms);
@@ -262,12 +290,12 @@ __device__ __forceinline__ void warp_midpoint(const float *__restrict__ xi, cons
   }
   __syncwarp();
   if (tp) { long long t = clock64(); tp[3] += t - tc0; tc0 = t; }
-  warp_expmap(xi, v, D, lane, [&](int k, float val) { m_row[k] = val; });
+  warp_expmap<NS>(xi, v, D, lane, [&](int k, float val) { m_row[k] = val; });
   __syncwarp();
   if (tp) { long long t = clock64(); tp[4] += t - tc0; tc0 = t; }
   if (project) {
     // lorentz_model.py:52-55: x0 = sqrt(1 + (c*r)*r)
-    float r = warp_norm_aten([&](int e) { return m_row[1 + e]; }, D - 1, lane);
+    float r = warp_norm_aten<NS>([&](int e) { return m_row[1 + e]; }, D - 1, lane);
     float x0 = __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(__fmul_rn(c, r), r)));
     if (tp) { long long t = clock64(); tp[5] += t - tc0; tc0 = t; }
     for (int k = lane; k < D; k += 32) out(k, k == 0 ? x0 : m_row[k]);

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   auto midpoint_into = [&](int which, float *scr) {
     float *qr = qrow + which * D;
     float *qf = reinterpret_cast<float *>(qq4 + which * G4);
-    warp_midpoint(xi, xj, s_len[0], s_len[1], D, p.c, p.semantics, true, scr, lane, [&](int e, float v) {
+    warp_midpoint<NS>(xi, xj, s_len[0], s_len[1], D, p.c, p.semantics, true, scr, lane, [&](int e, float v) {
       qr[e] = v;
       if (e) qf[e - 1] = v;
     });
