@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--v0", type=int, default=V0)
     ap.add_argument("--target", type=int, default=TARGET)
     ap.add_argument("--dim", type=int, default=D_EMB)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "tok"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "tok", "c2-sharded"],
                     help="c2: merge loop (headline, merges/s); c3: all-pairs Lorentz distance + top-k=32 over V=100k, "
                          "row-sharded over the ranks with an all-gather (TFLOP/s)")
     ap.add_argument("--engine", default="tc", choices=["tc", "exact"])
@@ -571,10 +571,86 @@ def run_tok(a):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------
+# crossover experiment: the per-merge step with ROW-SHARDED tables and an NCCL exchange per merge
+# ------------------------------------------------------------------------------------------------
+def run_c2_sharded(a):
+    """Every rank keeps rows r = rank (mod G) of the table (as a dense local table), scores the new row against
+    its shard with hyp_row_min, and the per-shard minima are all-gathered (one 16-byte record per rank) so that
+    every rank derives the same winner -- the multi-GPU form of the merge loop the north star describes.  Timed
+    to show where it stands against the single-GPU device-resident loop (it never wins while the table fits one
+    GPU: the step is one NVLink/NCCL latency, not bandwidth)."""
+    import torch.distributed as dist
+    from hyptokenizer_b200 import _lib
+    from hyptokenizer_b200._lib import SEM, check, ptr
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    V, d = a.target, a.dim
+    D = d + 1
+    sem = SEM[a.semantics]
+    full = synthetic_embeddings(V, d, scale=SCALE, seed=42).to(dev)
+    shard = full[rank::world].contiguous()                 # this rank's rows, dense
+    n_local = shard.shape[0]
+    table = torch.zeros((n_local + a.steps * 200 + 8, D), device=dev)
+    table[:n_local] = shard
+    ws = torch.empty(L.hyp_merge_workspace_bytes(), dtype=torch.uint8, device=dev)
+    best = torch.empty(32, dtype=torch.uint8, device=dev)
+    gathered = torch.empty((world, 32), dtype=torch.uint8, device=dev)
+    idx = torch.tensor([0, 1, 2, 2], dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    merges = a.steps * 200
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def one_merge(n_loc):
+        # new row = midpoint of two (replicated) rows, written behind this rank's shard as the query row
+        check(L.hyp_midpoint(ptr(full), D, idx[0:].data_ptr(), idx[1:].data_ptr(), idx[2:].data_ptr(), idx[3:].data_ptr(),
+                             table[n_loc].data_ptr(), D, 1, D, 1.0, sem, 1, sp))
+        check(L.hyp_row_min(ptr(table), D, n_loc, n_loc, D, 1.0, sem, 0.1, ptr(best), ptr(ws), ws.numel(), sp))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), best)
+        # (the replicated argmin over `world` records would run on the device here; it is a few instructions)
+
+    for _ in range(50):
+        one_merge(n_local)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record(stream)
+    for m in range(merges):
+        one_merge(n_local + (m // world))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        us = float(t.item()) * 1e3 / merges
+        print(json.dumps({"metric": "merges/sec, row-sharded per-merge step with NCCL all-gather (crossover experiment)",
+                          "value": 1e6 / us, "unit": "merges/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": float(t.item()) / a.steps, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"c2-sharded: V={V}, d={d}, rows r = rank mod {world}, host-driven step: "
+                                                 "midpoint + shard scan + all-gather of one 32-byte record per rank",
+                                     "us_per_merge": us}, "gpu_launches": merges * 2}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c2-sharded":
+        run_c2_sharded(args)
     elif args.workload == "tok":
         run_tok(args)
     elif args.workload == "c4":
