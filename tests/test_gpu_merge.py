@@ -350,3 +350,27 @@ def test_threshold_schedule_and_regime_switch():
         ref._merge_tokens(cands[0][0], cands[0][1])
     assert ref.vocab == tok.vocab[:360]
     assert same_bits(ref.embeddings[:360], tok.embeddings[:360])
+
+
+def test_degenerate_sizes():
+    """n = 0, 1, 2 tables, zero steps, a table that is already full."""
+    from hyptokenizer_b200.knn import lorentz_topk
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    from hyptokenizer_b200.tokenizer.hyperbolic_merge import HyperbolicTokenizer
+    for n in (1, 2):
+        emb = synthetic_embeddings(n, 10, scale=0.1, seed=n, device="cuda")
+        tok = HyperbolicTokenizer([f"w{k}" for k in range(n)], torch.nn.Parameter(emb), merge_threshold=5.0,
+                                  max_vocab_size=8, semantics="lorentz")
+        cands = tok._find_merge_candidates()
+        assert len(cands) == (1 if n == 2 else 0)
+        tok.optimize_merges(steps=0)
+        assert tok.current_vocab_size == n
+        tok.optimize_merges(steps=3)
+        assert tok.current_vocab_size == (n + 3 if n == 2 else 1)
+        idx, dist = lorentz_topk(emb, 4, 1.0, "lorentz")
+        assert idx.shape == (n, 4) and int((idx >= 0).sum()) == n * (n - 1)
+    emb = synthetic_embeddings(4, 10, scale=0.1, seed=9, device="cuda")
+    tok = HyperbolicTokenizer(list("abcd"), torch.nn.Parameter(emb), merge_threshold=5.0, max_vocab_size=4, semantics="lorentz")
+    with pytest.raises(ValueError):
+        tok.optimize_merges(steps=1)
+    assert tok.current_vocab_size == 4 and tok.vocab == list("abcd")
