@@ -23,7 +23,7 @@
 //           CUDA-core kernel, so the result is ALWAYS the exact one.
 //
 // Warp roles per CTA (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
-// warps 2..9 epilogue (one thread per accumulator row = TMEM lane and 64-column half of the tile).  A CTA owns a 128-row block (its A
+// warps 2..9 epilogue: two groups of four warps drain alternate accumulator tiles (thread <-> row = TMEM lane).  A CTA owns a 128-row block (its A
 // tile stays in shared memory) and streams all column tiles through a 2-stage B ring; accumulators are
 // quadruple-buffered in TMEM (4 x 128 columns) so the epilogue of tile t overlaps the MMA of tile t+1.
 #include <cuda.h>
@@ -43,7 +43,6 @@ constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_ACC = 4;           // accumulator buffers in TMEM (4 x 128 columns = all 512)
 constexpr int TC_EPI_WARPS = 8;    // 2 per TMEM lane quadrant: each handles one 64-column half of the tile
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr int TC_HALF = TC_N / 2;
 constexpr int TC_CAPH = 48;        // candidate capacity per row and column half
 constexpr int TC_CAP = 2 * TC_CAPH;
 
@@ -252,7 +251,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     mbar_init(a_empty, 1);
     for (int s = 0; s < TC_ACC; ++s) {
       mbar_init(acc_full + s, 1);
-      mbar_init(acc_empty + s, TC_EPI_WARPS);   // one arrival per epilogue warp
+      mbar_init(acc_empty + s, TC_EPI_WARPS / 2);   // one arrival per warp of the draining group
     }
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(b_full + s, 1);
@@ -338,60 +337,78 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       }
     }
   } else {
-    // ================= epilogue: warps 2..9; thread <-> (accumulator row, 64-column half) =============
-    // u' = sgn * (x0_i x0_j - S).  Pass 1 keeps min(u') per half tile (fminf drops NaN operands, and
+    // ================= epilogue: warps 2..9 = two groups of four warps =================
+    // Group g drains the accumulator tiles with sequence number T = g (mod 2): two tiles are in flight, so the
+    // latency of one drain (barrier, TMEM loads, 256 FFMA/FMNMX per thread) overlaps the other's instead of
+    // stalling the MMA issuer.  Within a group, thread <-> accumulator row (TMEM lane), all 128 columns.
+    // u' = sgn * (x0_i x0_j - S).  Pass 1 keeps min(u') per tile (fminf drops NaN operands, and
     // min_j max(u',1) == max(min_j u', 1), so the clamp is applied once per tile).  Pass 2 tests u' <= thr_i
     // (thr_i >= 1, so the clamped region always passes) into a 32-bit hit mask and only walks set bits.
     // Tiles that contain out-of-range columns or the row block's own diagonal take the checked path.
     const int quad = warp & 3;                       // TMEM lanes [32*quad, +32) are readable by this warp
-    const int half = (warp - 2) >> 2;                // column half of the tile
+    const int grp = (warp - 2) >> 2;                 // which of the two tile streams
     const int lane_base = 32 * quad;
-    const int r_in_block = lane_base + lane;
-    const int ep_tid = (warp - 2) * 32 + lane;       // 0..255
+    const int r_in_block = lane_base + lane;         // row of the tile, also the thread's index in its group
     const float inf = __int_as_float(0x7f800000);
-    uint32_t abuf = 0, accphase = 0;
-    for (int64_t rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
-      const int64_t blk0 = p.row0 + rb * TC_M;
-      const int64_t gi = blk0 + r_in_block;
-      const bool row_ok = gi < p.row0 + p.nrows;
-      const float x0i = row_ok ? __ldg(p.x0 + gi) : 0.f;
-      const float xs = SGN_POS ? x0i : -x0i;
-      float thr = 0.f;
-      int cnt = 0;
-      if (PASS == 2) thr = row_ok ? __ldg(p.thr + (gi - p.row0)) : -1.f;
-      int32_t *my_cand = p.cand + ((gi - p.row0) * 2 + half) * TC_CAPH;
-      // time components of the next tile's columns are fetched one tile ahead (an L2 round trip that would
-      // otherwise sit on the critical path of every tile)
-      float x0_next = 0.f;
-      if (ep_tid < TC_N) x0_next = ep_tid < p.n ? __ldg(p.x0 + ep_tid) : 0.f;
-      for (int64_t ct = 0; ct < col_tiles; ++ct) {
-        const int64_t j0 = ct * TC_N;
-        if (ep_tid < TC_N) {
-          colx0[abuf * TC_N + ep_tid] = x0_next;
-          const int64_t gjn = j0 + TC_N + ep_tid;
-          x0_next = gjn < p.n ? __ldg(p.x0 + gjn) : 0.f;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        mbar_wait(acc_full + abuf, accphase);
-        tc_fence_after();
-        const bool checked = (j0 + TC_N > p.n) || (j0 < blk0 + TC_M && j0 + TC_N > blk0);
-        const float *cx = colx0 + abuf * TC_N + half * TC_HALF;
-        const int64_t jh = j0 + half * TC_HALF;
-        float tmin = inf;
-        // both 32-column chunks of this thread's half are requested before the first is consumed
+    const int64_t my_blocks = (row_blocks > blockIdx.x) ? (row_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_blocks * col_tiles;
+    int64_t cur_rbi = -1, blk0 = 0, gi = 0;
+    bool row_ok = false;
+    float xs = 0.f, thr = 0.f;
+    int cnt = 0;
+    int32_t *my_cand = p.cand;
+    float x0_next = 0.f;
+    if (grp < total) {
+      const int64_t ct0 = grp % col_tiles;
+      const int64_t gj0 = ct0 * TC_N + r_in_block;
+      x0_next = gj0 < p.n ? __ldg(p.x0 + gj0) : 0.f;
+    }
+    for (int64_t T = grp; T < total; T += 2) {
+      const int64_t rbi = T / col_tiles, ct = T - rbi * col_tiles;
+      if (rbi != cur_rbi) {
+        if (PASS == 2 && cur_rbi >= 0 && row_ok) p.cand_cnt[(gi - p.row0) * 2 + grp] = cnt;
+        cur_rbi = rbi;
+        blk0 = p.row0 + (blockIdx.x + rbi * gridDim.x) * TC_M;
+        gi = blk0 + r_in_block;
+        row_ok = gi < p.row0 + p.nrows;
+        const float x0i = row_ok ? __ldg(p.x0 + gi) : 0.f;
+        xs = SGN_POS ? x0i : -x0i;
+        if (PASS == 2) thr = row_ok ? __ldg(p.thr + (gi - p.row0)) : -1.f;
+        cnt = 0;
+        my_cand = p.cand + ((gi - p.row0) * 2 + grp) * TC_CAPH;
+      }
+      const uint32_t abuf = (uint32_t)(T & (TC_ACC - 1)), accphase = (uint32_t)((T / TC_ACC) & 1);
+      const int64_t j0 = ct * TC_N;
+      // time components of this tile's columns (fetched one tile of this group ahead)
+      colx0[abuf * TC_N + r_in_block] = x0_next;
+      if (T + 2 < total) {
+        const int64_t ctn = (T + 2) % col_tiles;
+        const int64_t gjn = ctn * TC_N + r_in_block;
+        x0_next = gjn < p.n ? __ldg(p.x0 + gjn) : 0.f;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      mbar_wait(acc_full + abuf, accphase);
+      tc_fence_after();
+      const bool checked = (j0 + TC_N > p.n) || (j0 < blk0 + TC_M && j0 + TC_N > blk0);
+      const float *cx = colx0 + abuf * TC_N;
+      float tmin = inf;
+      const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + abuf * TC_N;
+#pragma unroll 1
+      for (int pairc = 0; pairc < 2; ++pairc) {
+        // two 32-column chunks are requested before the first is consumed
         float v0[32], v1[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + abuf * TC_N + half * TC_HALF;
         if (!(p.debug & 1)) {
-          tmem_ld32_nowait(taddr, v0);
-          tmem_ld32_nowait(taddr + 32, v1);
+          tmem_ld32_nowait(taddr + pairc * 64, v0);
+          tmem_ld32_nowait(taddr + pairc * 64 + 32, v1);
           tmem_ld_wait();
         } else {
 #pragma unroll
           for (int c = 0; c < 32; ++c) { v0[c] = 0.f; v1[c] = 0.f; }
         }
 #pragma unroll
-        for (int chunk = 0; chunk < ((p.debug & 1) ? 0 : 2); ++chunk) {
-          const float (&v)[32] = chunk == 0 ? v0 : v1;
+        for (int sub = 0; sub < ((p.debug & 1) ? 0 : 2); ++sub) {
+          const int chunk = pairc * 2 + sub;
+          const float (&v)[32] = sub == 0 ? v0 : v1;
           float cxc[32];                                   // 8 x LDS.128 (broadcast) instead of 32 scalar loads
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
@@ -408,7 +425,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             } else {
 #pragma unroll
               for (int c = 0; c < 32; ++c) {
-                const int64_t gj = jh + chunk * 32 + c;
+                const int64_t gj = j0 + chunk * 32 + c;
                 const float u = SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]);
                 if (gj < p.n && gj != gi) tmin = fminf(tmin, u);
               }
@@ -424,7 +441,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             while (hits) {
               const int c = __ffs(hits) - 1;
               hits &= hits - 1;
-              const int64_t gj = jh + chunk * 32 + c;
+              const int64_t gj = j0 + chunk * 32 + c;
               if (!checked || (gj < p.n && gj != gi)) {
                 if (cnt < TC_CAPH) my_cand[cnt] = (int32_t)gj;
                 ++cnt;
@@ -432,15 +449,15 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             }
           }
         }
-        // release the accumulator buffer
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty + abuf);
-        if (PASS == 1 && row_ok) p.tilemin[(2 * ct + half) * p.ld_tm + (gi - p.row0)] = fmaxf(tmin, 1.0f);
-        if (++abuf == TC_ACC) { abuf = 0; accphase ^= 1; }
       }
-      if (PASS == 2 && row_ok) p.cand_cnt[(gi - p.row0) * 2 + half] = cnt;
+      // release the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + abuf);
+      if (PASS == 1 && row_ok) p.tilemin[ct * p.ld_tm + (gi - p.row0)] = fmaxf(tmin, 1.0f);
     }
+    if (PASS == 2 && cur_rbi >= 0 && row_ok) p.cand_cnt[(gi - p.row0) * 2 + grp] = cnt;
+    // a group that saw no tile of a row block leaves its candidate count at the zero the host wrote
   }
 
   tc_fence_before();
@@ -623,7 +640,7 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
   L.off_x0 = take((size_t)n * 4);
   L.off_nrm = take((size_t)n * 4);
   L.off_max = take(256);
-  L.off_tilemin = take((size_t)2 * L.col_tiles * L.ld_tm * 4);
+  L.off_tilemin = take((size_t)L.col_tiles * L.ld_tm * 4);
   L.off_thr = take((size_t)nrows * 4);
   L.off_cand = take((size_t)nrows * TC_CAP * 4);
   L.off_cnt = take((size_t)nrows * 2 * 4);
@@ -682,6 +699,7 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
   cudaMemsetAsync(maxn, 0, 4, st);
+  cudaMemsetAsync(cnt, 0, (size_t)nrows * 2 * sizeof(int32_t), st);
   tc_pack_kernel<<<sms * 4, 256, 0, st>>>(E, ldE, n, D, L.Kp, XP, x0, nrm, maxn);
   int rc = check_launch("hyp_gram_topk(pack)");
   if (rc) return rc;
@@ -731,7 +749,7 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   k1<<<grid, TC_THREADS, smem, st>>>(tmap, tmap_tail, p);
   rc = check_launch("hyp_gram_topk(pass 1)");
   if (rc) return rc;
-  kth_select_kernel<<<(int)((nrows + 127) / 128), 128, 0, st>>>(tilemin, L.ld_tm, 2 * L.col_tiles, nrows, row0, k, nrm, maxn,
+  kth_select_kernel<<<(int)((nrows + 127) / 128), 128, 0, st>>>(tilemin, L.ld_tm, L.col_tiles, nrows, row0, k, nrm, maxn,
                                                                 thr);
   rc = check_launch("hyp_gram_topk(select)");
   if (rc) return rc;

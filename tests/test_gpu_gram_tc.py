@@ -42,3 +42,16 @@ def test_tc_degenerate_inputs_fall_back():
     ei, ed = lorentz_topk(E, k, 1.0, "lorentz", engine="exact")
     ti, td = lorentz_topk(E, k, 1.0, "lorentz", engine="tc")
     assert torch.equal(ti, ei) and same_bits(td, ed)
+
+
+def test_tc_full_size_shard_equals_exact():
+    """BASELINE configs[2] size: a 2048-row shard of V=100k, d=100, k=32 through the tensor-core path is bit-identical to
+    the exact CUDA-core kernel, with no row needing the fallback."""
+    from hyptokenizer_b200.knn import lorentz_topk
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    n, k, row0, nrows = 100000, 32, 77000, 2048
+    E = synthetic_embeddings(n, 100, scale=0.01, seed=42, device="cuda")
+    ei, ed = lorentz_topk(E, k, 1.0, "lorentz", n, row0, nrows, engine="exact")
+    ti, td = lorentz_topk(E, k, 1.0, "lorentz", n, row0, nrows, engine="tc")
+    assert torch.equal(ti, ei) and same_bits(td, ed)
+    assert lorentz_topk.last_flagged == 0
