@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import shutil
 import subprocess
 from typing import Optional
 
@@ -87,6 +88,9 @@ def build(verbose: bool = False) -> str:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
+        if not os.path.exists(LIB_PATH) and shutil.which("nvcc") or (
+                not os.path.exists(LIB_PATH) and os.path.exists("/usr/local/cuda/bin/nvcc")):
+            build()                      # building the product is not a fallback; a missing compiler still raises below
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: the CUDA library has not been built. Run "
