@@ -10,7 +10,9 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("n,d,k,scale,nrows,row0", [(1024, 100, 32, 0.05, None, 0), (4500, 100, 32, 0.01, None, 0),
                                                     (4500, 50, 16, 0.3, 1000, 777), (9000, 100, 32, 0.01, 3000, 6000),
-                                                    (2100, 128, 8, 0.1, None, 0), (1500, 7, 4, 0.2, None, 0)])
+                                                    (2100, 128, 8, 0.1, None, 0), (1500, 7, 4, 0.2, None, 0),
+                                                    (3000, 48, 8, 0.1, None, 0), (2000, 16, 4, 0.2, 700, 1300),
+                                                    (2500, 90, 8, 0.1, None, 0), (2500, 64, 8, 0.1, None, 0)])
 def test_tc_equals_exact(n, d, k, scale, nrows, row0):
     from hyptokenizer_b200.knn import lorentz_topk
     from hyptokenizer_b200.synth import synthetic_embeddings
