@@ -201,6 +201,9 @@ def run_ours(a):
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     prof = ws_lp[32:96].cpu().numpy().view(np.int64)
+    mprof = ws_lp[96:160].cpu().numpy().view(np.int64)
+    if rank == 0 and mprof.any():      # only with -DHYP_LOOP_PROF builds
+        print(f"[scan marks cta0] cycles/merge: {[round(int(v) / max(int(prof[3]), 1)) for v in mprof]}", file=sys.stderr)
     if rank == 0 and prof[3] > 0:
         for name, base in (("cta0", 0), ("ctaN", 4)):
             n_ = max(int(prof[base + 3]), 1)

@@ -15,7 +15,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhyptok_b200.so")
+# HYPTOK_B200_LIB points at another build of the same library (used to A/B kernel variants on one GPU box)
+LIB_PATH = os.environ.get("HYPTOK_B200_LIB") or os.path.join(_HERE, "lib", "libhyptok_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 HYP_OK = 0

@@ -250,6 +250,21 @@ __device__ __forceinline__ float logmap_coef(float m, int semantics, float *m_si
   return coef;
 }
 
+// f(k) for k = lane, lane + 32, ... < D.  With NS > 0 (D == NS + 1 known at compile time) the trip count is a
+// constant and the iterations unroll, so their loads and divisions overlap instead of running back to back.
+template <int NS, typename F>
+__device__ __forceinline__ void warp_for_elems(int D, int lane, F f) {
+  if (NS > 0) {
+#pragma unroll
+    for (int it = 0; it < (NS > 0 ? (NS + 1 + 31) / 32 : 1); ++it) {
+      const int k = lane + 32 * it;
+      if (k < NS + 1) f(k);
+    }
+  } else {
+    for (int k = lane; k < D; k += 32) f(k);
+  }
+}
+
 // out = exp_x(v) (lorentz_model.py:85-93); v holds D floats readable by the whole warp.
 template <int NS = 0, typename OutFn>
 __device__ __forceinline__ void warp_expmap(const float *__restrict__ x, const float *v, int D,
@@ -261,11 +276,11 @@ __device__ __forceinline__ void warp_expmap(const float *__restrict__ x, const f
   float den = __fadd_rn(vn, small);
   float ch = coshf(vn), sh = sinhf(vn);
   float keep = __fsub_rn(1.0f, small);
-  for (int k = lane; k < D; k += 32) {
+  warp_for_elems<NS>(D, lane, [&](int k) {
     float dir = __fdiv_rn(v[k], den);
     dir = __fadd_rn(__fmul_rn(small, 0.0f), __fmul_rn(keep, dir));
     out(k, __fadd_rn(__fmul_rn(ch, x[k]), __fmul_rn(sh, dir)));
-  }
+  });
 }
 
 // Full chain; `buf` = 2*D floats of shared scratch private to the warp. Result row left in
@@ -284,10 +299,10 @@ __device__ __forceinline__ void warp_midpoint(const float *__restrict__ xi, cons
   if (tp) { long long t = clock64(); tp[1] += t - tc0; tc0 = t; }
   const float w = (float)((double)len_j / (double)(len_i + len_j));  // Python float, cast to fp32 by `*`
   if (tp) { long long t = clock64(); tp[2] += t - tc0; tc0 = t; }
-  for (int k = lane; k < D; k += 32) {
+  warp_for_elems<NS>(D, lane, [&](int k) {
     float lg = __fmul_rn(coef, __fadd_rn(xj[k], __fmul_rn(ms, xi[k])));
     v[k] = __fmul_rn(lg, w);
-  }
+  });
   __syncwarp();
   if (tp) { long long t = clock64(); tp[3] += t - tc0; tc0 = t; }
   warp_expmap<NS>(xi, v, D, lane, [&](int k, float val) { m_row[k] = val; });
@@ -298,10 +313,10 @@ __device__ __forceinline__ void warp_midpoint(const float *__restrict__ xi, cons
     float r = warp_norm_aten<NS>([&](int e) { return m_row[1 + e]; }, D - 1, lane);
     float x0 = __fsqrt_rn(__fadd_rn(1.0f, __fmul_rn(__fmul_rn(c, r), r)));
     if (tp) { long long t = clock64(); tp[5] += t - tc0; tc0 = t; }
-    for (int k = lane; k < D; k += 32) out(k, k == 0 ? x0 : m_row[k]);
+    warp_for_elems<NS>(D, lane, [&](int k) { out(k, k == 0 ? x0 : m_row[k]); });
     if (tp) { long long t = clock64(); tp[6] += t - tc0; tc0 = t; }
   } else {
-    for (int k = lane; k < D; k += 32) out(k, m_row[k]);
+    warp_for_elems<NS>(D, lane, [&](int k) { out(k, m_row[k]); });
   }
   __syncwarp();
 }

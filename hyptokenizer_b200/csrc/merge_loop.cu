@@ -22,6 +22,7 @@ constexpr int kLoopThreads = 512;
 constexpr int kLoopWarps = kLoopThreads / 32;
 constexpr int kMaxLoopBlocks = 148 * 4;
 constexpr int kRowsPerIter = 4;  // rows a warp keeps in flight (independent reduction chains)
+constexpr int kXRing = 1024;     // exchange slots of the resident loop (step k uses slot k mod kXRing)
 
 struct LoopWorkspace {
   unsigned int barrier;  // monotonically increasing arrival counter
@@ -29,15 +30,14 @@ struct LoopWorkspace {
   unsigned int pad[6];
   long long prof[8];               // resident loop: phase cycle counters of CTA 0 and CTA G-1
   long long mprof[8];              // debug: midpoint sub-phase cycles of CTA 0
-  unsigned long long key_ring[4];  // (unused by the current kernels; keeps the header layout stable)
+  unsigned long long reserved[4];
   struct alignas(16) XSlot {       // resident loop: per-step exchange word, polled with ONE 128-bit load
-    unsigned long long key;        //   RED.MIN target: d_bits << 32 | row
-    unsigned int count;            //   arrivals of this step
+    unsigned long long key;        //   RED.MIN target: d_bits << 32 | row (kNoKey when nobody improved on `best`)
+    unsigned int count;            //   arrivals, never reset: use u of a slot completes at count == G * u
     unsigned int pad;
-  } xring[4];
+  } xring[kXRing];
   Key slot[2][kMaxLoopBlocks];     // L2 loop: per-CTA minima, double-buffered by step parity
   unsigned long long below[kMaxLoopBlocks];
-  unsigned long long flag[4][kMaxLoopBlocks];  // resident loop: per-step, per-CTA (key | 1<<63), 0 = not yet written
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
@@ -58,6 +58,9 @@ __device__ __forceinline__ void ld_acquire_v2_u64(const void *p, unsigned long l
 }
 __device__ __forceinline__ void red_release_add_u32(unsigned int *p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_relaxed_add_u32(unsigned int *p, unsigned int v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // All CTAs of a cooperative launch (co-resident by construction).
@@ -356,31 +359,42 @@ constexpr unsigned long long kNoKey = 0xffffffffffffffffULL;
 struct ResidentParams {
   LoopParams lp;
   int slots;     // slot capacity per CTA (odd)
-  int exchange;  // 0: atomicMin + arrival counter, 1: per-CTA flags polled by one warp
 };
+
+// Two fp32 products in one instruction (FMUL2): each half is an IEEE round-to-nearest product, bit-identical to
+// __fmul_rn.  Only the PRODUCTS are packed: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (single
+// rounding) even under --fmad=false, which would break the torch summation order, so the adds stay scalar FADDs.
+__device__ __forceinline__ void fmul2_rn(unsigned long long a, unsigned long long b, float &lo, float &hi) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(d));
+}
 
 // exact-order Minkowski product of the row in `slot` with q; N known at compile time.
 template <int N>
 __device__ __forceinline__ float resident_mdot_static(const float4 *__restrict__ T4, const float *__restrict__ T0, int S,
                                                       int slot, const float4 *__restrict__ q4, float q0) {
   constexpr int vs = N / 8, full = vs / 4, G4 = (N + 3) / 4;
+  const ulonglong2 *T2 = reinterpret_cast<const ulonglong2 *>(T4);
+  const ulonglong2 *q2 = reinterpret_cast<const ulonglong2 *>(q4);
   float P[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) P[k] = 0.f;
   float tail = 0.f;
 #pragma unroll
   for (int g = 0; g < G4; ++g) {
-    const float4 a = T4[(size_t)g * S + slot];
-    const float4 b = q4[g];
-    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    const ulonglong2 a = T2[(size_t)g * S + slot];
+    const ulonglong2 b = q2[g];
+    float pr[4];
+    fmul2_rn(a.x, b.x, pr[0], pr[1]);
+    if (4 * g + 2 < N) fmul2_rn(a.y, b.y, pr[2], pr[3]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int e = 4 * g + c;
       if (e < N) {
-        const float pr = __fmul_rn(av[c], bv[c]);
-        if (e < 32 * full) P[e & 31] = __fadd_rn(P[e & 31], pr);
-        else if (e < 8 * vs) P[e & 7] = __fadd_rn(P[e & 7], pr);   // left-over lane vectors join partial 0
-        else tail = __fadd_rn(tail, pr);
+        if (e < 32 * full) P[e & 31] = __fadd_rn(P[e & 31], pr[c]);
+        else if (e < 8 * vs) P[e & 7] = __fadd_rn(P[e & 7], pr[c]);   // left-over lane vectors join partial 0
+        else tail = __fadd_rn(tail, pr[c]);
       }
     }
   }
@@ -390,55 +404,6 @@ __device__ __forceinline__ float resident_mdot_static(const float4 *__restrict__
     const float L = __fadd_rn(__fadd_rn(__fadd_rn(P[l], P[8 + l]), P[16 + l]), P[24 + l]);
     acc = __fadd_rn(acc, L);
   }
-  return __fsub_rn(__fmul_rn(T0[slot], q0), acc);
-}
-
-// Same product, one row split over TWO adjacent threads (sub = 0/1).  Thread `sub` takes the float4 groups
-// g = sub, sub+2, ...; group g feeds the partials 4(g mod 8)..+3, so each thread owns 16 of the 32 partials
-// outright (in-order accumulation preserved), owns the lane sums L[4 sub .. 4 sub + 3] outright, and only the
-// final 8-term chain needs four shuffles.  Halves the dependent chain that bounds the scan phase while the CTA
-// holds at most half as many rows as it has scanning threads.
-// The result is valid on the even lane (sub == 0).  All 32 lanes must call it (shuffles).
-template <int N>
-__device__ __forceinline__ float resident_mdot_static2(const float4 *__restrict__ T4, const float *__restrict__ T0, int S,
-                                                       int slot, const float4 *__restrict__ q4, float q0, int sub) {
-  constexpr int vs = N / 8, full = vs / 4, G4 = (N + 3) / 4;
-  static_assert(N >= 8 && N - 8 * vs <= 4, "tail must fit the first tail group (owned by sub 0)");
-  float P[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) P[k] = 0.f;
-  float tail = 0.f;
-#pragma unroll
-  for (int j = 0; j < (G4 + 1) / 2; ++j) {
-    const int g = 2 * j + sub;
-    if (g < G4) {
-      const float4 a = T4[(size_t)g * S + slot];
-      const float4 b = q4[g];
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float pr = __fmul_rn(av[c], bv[c]);
-        if (8 * j < 32 * full) {                       // full rounds: partial (g mod 8) * 4 + c
-          P[(j & 3) * 4 + c] = __fadd_rn(P[(j & 3) * 4 + c], pr);
-        } else if (8 * j < 8 * vs) {                   // left-over lane vectors join partial 0 of their lane
-          P[c] = __fadd_rn(P[c], pr);
-        } else if (8 * j + 4 * sub + c < N) {          // scalar tail (only sub 0 has any)
-          tail = __fadd_rn(tail, pr);
-        }
-      }
-    }
-  }
-  float L[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) L[c] = __fadd_rn(__fadd_rn(__fadd_rn(P[c], P[4 + c]), P[8 + c]), P[12 + c]);
-  float Lo[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) Lo[c] = __shfl_down_sync(HYP_FULL_MASK, L[c], 1);   // L[4..7] from the odd lane
-  float acc = tail;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) acc = __fadd_rn(acc, L[c]);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) acc = __fadd_rn(acc, Lo[c]);
   return __fsub_rn(__fmul_rn(T0[slot], q0), acc);
 }
 
@@ -456,6 +421,28 @@ __device__ __forceinline__ float resident_mdot_dynamic(const float4 *__restrict_
 __device__ __forceinline__ void bar_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// -DHYP_LOOP_PROF (make EXTRA=-DHYP_LOOP_PROF): thread 0 of CTA 0 accumulates the cycles between consecutive marks
+// into ws->mprof[0..7], and CTA 0 / CTA G-1 the three phases into ws->prof; the product build reads no clocks.
+#ifdef HYP_LOOP_PROF
+#define HYP_PROF_MARK(id)                                                     \
+  do {                                                                        \
+    if (threadIdx.x == 0 && b == 0) {                                         \
+      const long long t_ = clock64();                                         \
+      a_prof[id] += t_ - t_prof;                                              \
+      t_prof = t_;                                                            \
+    }                                                                         \
+  } while (0)
+#define HYP_PHASE(acc)                                                        \
+  do {                                                                        \
+    const long long t_ = clock64();                                           \
+    acc += t_ - t_mark;                                                       \
+    t_mark = t_;                                                              \
+  } while (0)
+#else
+#define HYP_PROF_MARK(id) do { } while (0)
+#define HYP_PHASE(acc) do { } while (0)
+#endif
 
 template <int NS>
 __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(const ResidentParams rp) {
@@ -487,15 +474,21 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   double thr = p.state->threshold;
   int done = 0, stop = 0, cur = 0;
   unsigned int arrivals = (unsigned int)G;
+#ifdef HYP_MID_PROF
+  long long m_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sub-phases of the speculating warp's midpoint (CTA 0, lane 0)
+#endif
+#ifdef HYP_LOOP_PROF
   long long t_mid = 0, t_scan = 0, t_bar = 0, t_mark = 0;
+  long long t_prof = clock64(), a_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
-  auto midpoint_into = [&](int which, float *scr) {
+  auto midpoint_into = [&](int which, float *scr, long long *tp = nullptr) {
     float *qr = qrow + which * D;
     float *qf = reinterpret_cast<float *>(qq4 + which * G4);
     warp_midpoint<NS>(xi, xj, s_len[0], s_len[1], D, p.c, p.semantics, true, scr, lane, [&](int e, float v) {
       qr[e] = v;
       if (e) qf[e - 1] = v;
-    });
+    }, tp);
   };
 
   // ---- load the rows this CTA owns: a warp reads one row (coalesced), scatters it conflict-free --
@@ -521,20 +514,29 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
       if (threadIdx.x == 1) s_len[1] = __ldcg(p.len + best.j);
     }
   }
-  if (b == 0 && threadIdx.x < 4) {
-    p.ws->xring[threadIdx.x].key = kNoKey;
-    p.ws->xring[threadIdx.x].count = 0u;
+  if (b == 0) {
+    for (int sl = threadIdx.x; sl < kXRing; sl += blockDim.x) {
+      p.ws->xring[sl].key = kNoKey;
+      p.ws->xring[sl].count = 0u;
+    }
   }
   grid_barrier(&p.ws->barrier, arrivals);
   // midpoint row of the initial best pair (hyperbolic_merge.py:317-340)
   if (warp == 0 && best.i >= 0) midpoint_into(cur, scratch);
   __syncthreads();
+#ifdef HYP_LOOP_PROF
   if (threadIdx.x == 0) t_mark = clock64();
+#endif
 
   // loop-carried bookkeeping without integer division: rows this CTA owns below n, and whether/where row n lands here
   int owned = (n > b) ? (n - b + G - 1) / G : 0;
   int n_mod = n % G, n_div = n / G;
   float thr_f = (float)thr;
+  long long next_thr = -1;                   // first k at which the threshold is multiplied
+  if (p.thr_every > 0) {
+    next_thr = (p.thr_every - p.step0 % p.thr_every) % p.thr_every;
+    if (p.step0 + next_thr == 0) next_thr = p.thr_every;
+  }
 
   for (int k = 0; k < p.max_steps; ++k) {
     // invariant: qrow[cur] / qq4[cur] hold the merged row for `best`, computed from xi, xj, s_len
@@ -545,47 +547,46 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
     const float *q = qrow + cur * D;
     const float4 *q4 = qq4 + cur * G4;
     unsigned long long win = kNoKey;
+    HYP_PROF_MARK(7);
 
     if (spec_warp) {
-      if (b == 0) {
-        // append row n = q to the table in global memory (the caller's `embeddings`), log the merge
+      // ---- speculation: if this step's scan does not produce a better pair, `best` (and so its rows)
+      // stays, and the NEXT merged row is the midpoint of the same operands.  It is recomputed here, in
+      // full, while the other warps scan and exchange; it is used only if the guess holds.
+#ifdef HYP_MID_PROF
+      midpoint_into(cur ^ 1, scratch + 2 * D, m_prof);
+#else
+      midpoint_into(cur ^ 1, scratch + 2 * D);
+#endif
+    } else {
+      // ---- score row n against the resident rows (< n) of this CTA ---------------------------------------
+      const float q0 = q[0];
+      unsigned int my_d = 0xffffffffu, my_r = 0xffffffffu;   // (distance bits, row): d >= 0, so the bits order like d
+      if (b == 0 && warp == kWorkWarps - 1) {
+        // append row n = q to the table in global memory (the caller's `embeddings`) and log the merge.  Done by the
+        // last scanning warp (it has the fewest rows) BEFORE its scan: thread 0's release below waits for the
+        // CTA's outstanding stores, so they have to be long gone by then (issuing them next to the exchange
+        // cost 13 % of the merge rate).  The named barrier + that release publish row n / len / log and the
+        // recycled slot with this step's exchange; nobody reads them earlier.
         for (int e = lane; e < D; e += 32) p.E[(int64_t)n * p.ldE + e] = q[e];
         if (lane == 0) {
           p.len[n] = s_len[0] + s_len[1];
           p.log[k] = hyp_merge_record{best.i, best.j, best.d, n};
+          // recycle the exchange slot used kXRing/2 steps ago (every CTA is past it) for its next use kXRing/2
+          // steps from now
+          p.ws->xring[(k + kXRing / 2) & (kXRing - 1)].key = kNoKey;
         }
       }
-      // ---- speculation: if this step's scan does not produce a better pair, `best` (and so its rows)
-      // stays, and the NEXT merged row is the midpoint of the same operands.  It is recomputed here, in
-      // full, while the other warps scan and exchange; it is used only if the guess holds.
-      midpoint_into(cur ^ 1, scratch + 2 * D);
-      // (row n / len / log become visible to the other CTAs through the CTA barrier below + thread 0's release in
-      //  the next exchange; nobody reads row n from global memory before that)
-    } else {
-      // ---- score row n against the resident rows (< n) of this CTA ---------------------------------------
-      const float q0 = q[0];
-      unsigned long long mine = kNoKey;
-      if (NS > 0 && owned <= kWork / 2) {
-        // few rows: two adjacent threads per row (warp-uniform trip count; idle pairs recompute slot 0, discarded)
-        const int sub = threadIdx.x & 1;
-        const int t = threadIdx.x >> 1;
-        if ((threadIdx.x & ~31) >> 1 < owned) {
-          const bool live = t < owned;
-          const float m = resident_mdot_static2<(NS > 0 ? NS : 8)>(T4, T0, S, live ? t : 0, q4, q0, sub);
-          if (live && sub == 0) {
-            const float d = dist_from_mdot(m, p.sgn, p.sqrt_c);
-            if (d == d) mine = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)(t * G + b);
-          }
-        }
-      } else {
-        for (int t = threadIdx.x; t < owned; t += kWork) {
-          const float m = (NS > 0) ? resident_mdot_static<(NS > 0 ? NS : 8)>(T4, T0, S, t, q4, q0)
-                                   : resident_mdot_dynamic(T4, T0, S, t, q4, q0, N);
-          const float d = dist_from_mdot(m, p.sgn, p.sqrt_c);
-          if (d == d) {
-            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)(t * G + b);
-            mine = key < mine ? key : mine;
-          }
+      for (int t = threadIdx.x; t < owned; t += kWork) {
+        HYP_PROF_MARK(0);
+        const float m = (NS > 0) ? resident_mdot_static<(NS > 0 ? NS : 8)>(T4, T0, S, t, q4, q0)
+                                 : resident_mdot_dynamic(T4, T0, S, t, q4, q0, N);
+        HYP_PROF_MARK(1);
+        const float d = dist_from_mdot(m, p.sgn, p.sqrt_c);
+        HYP_PROF_MARK(2);
+        if (d == d && __float_as_uint(d) < my_d) {           // rows ascend with t: strict < keeps the smallest row
+          my_d = __float_as_uint(d);
+          my_r = (unsigned int)(t * G + b);
         }
       }
       // the owner of row n appends it (its slot is beyond `owned`, so nobody reads it this step)
@@ -595,31 +596,44 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
           else Tf[((size_t)((e - 1) >> 2) * S + n_div) * 4 + ((e - 1) & 3)] = q[e];
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long other = __shfl_xor_sync(HYP_FULL_MASK, mine, o);
-        mine = other < mine ? other : mine;
-      }
-      if (lane == 0) s_key[warp] = mine;
+      HYP_PROF_MARK(6);
+      // lexicographic (d, row) minimum of the warp with two REDUX instructions
+      const unsigned int w_d = __reduce_min_sync(HYP_FULL_MASK, my_d);
+      const unsigned int w_r = __reduce_min_sync(HYP_FULL_MASK, my_d == w_d ? my_r : 0xffffffffu);
+      HYP_PROF_MARK(3);
+      if (lane == 0) s_key[warp] = ((unsigned long long)w_d << 32) | w_r;
       bar_named(1, kWork);
-      // ---- exchange: one 64-bit RED.MIN + one release RED.ADD per CTA on the SAME 16-byte slot, which
-      // every CTA then polls with a single 128-bit acquire load: the load that sees count == G also carries
-      // the final minimum (each CTA's RED.MIN is ordered before its arrival), so no second round trip.
-      const int gen = k & 3;
-      if (threadIdx.x == 0) {
-        unsigned long long m2 = s_key[0];
-        for (int w = 1; w < kWorkWarps; ++w) m2 = s_key[w] < m2 ? s_key[w] : m2;
-        LoopWorkspace::XSlot *xr = &p.ws->xring[gen];
-        LoopWorkspace::XSlot *recycle = &p.ws->xring[(k + 2) & 3];   // every CTA writes the same reset values
-        recycle->key = kNoKey;
-        recycle->count = 0u;
-        if (m2 != kNoKey) atomicMin(&xr->key, m2);
-        long long t = clock64(); t_scan += t - t_mark; t_mark = t;
-        red_release_add_u32(&xr->count, 1u);
-        unsigned long long kk, cc;
-        do { ld_acquire_v2_u64(xr, kk, cc); } while ((unsigned int)(cc & 0xffffffffu) < (unsigned int)G);
-        s_win[k & 1] = kk;
-        t = clock64(); t_bar += t - t_mark; t_mark = t;
+      HYP_PROF_MARK(4);
+      // ---- exchange on ONE 16-byte slot per step.  A CTA posts its minimum (64-bit RED.MIN) only when it
+      // beats `best` -- every CTA holds the same `best`, so a key that does not beat it cannot change the
+      // outcome -- and then arrives (RED.ADD).  Arrival is a release only where there is something to
+      // publish: a posted key, or CTA 0's appended row / recycled slot; the other CTAs arrive relaxed and
+      // go straight to polling.  Every CTA polls the slot with a single 128-bit acquire load: the load that
+      // sees the full count also carries the final minimum (a RED.MIN is ordered before its CTA's arrival,
+      // and the arrivals form one RMW chain on `count`), so there is no second round trip.
+      if (warp == 0) {
+        const unsigned long long wk = lane < kWorkWarps ? s_key[lane] : kNoKey;
+        const unsigned int k_d = (unsigned int)(wk >> 32), k_r = (unsigned int)(wk & 0xffffffffu);
+        const unsigned int c_d = __reduce_min_sync(HYP_FULL_MASK, k_d);
+        const unsigned int c_r = __reduce_min_sync(HYP_FULL_MASK, k_d == c_d ? k_r : 0xffffffffu);
+        if (lane == 0) {
+          LoopWorkspace::XSlot *xr = &p.ws->xring[k & (kXRing - 1)];
+          const unsigned int target = (unsigned int)G * (unsigned int)((k / kXRing) + 1);
+          const bool post = c_r != 0xffffffffu && key_less(Key{__uint_as_float(c_d), (int)c_r, n}, best);
+          if (post) atomicMin(&xr->key, ((unsigned long long)c_d << 32) | c_r);
+          HYP_PROF_MARK(5);
+          HYP_PHASE(t_scan);
+#ifdef HYP_X_B0RELAXED   // measurement only: what CTA 0's fence costs
+          if (post) red_release_add_u32(&xr->count, 1u);
+#else
+          if (post || b == 0) red_release_add_u32(&xr->count, 1u);
+#endif
+          else red_relaxed_add_u32(&xr->count, 1u);
+          unsigned long long kk, cc;
+          do { ld_acquire_v2_u64(xr, kk, cc); } while ((unsigned int)(cc & 0xffffffffu) < target);
+          s_win[k & 1] = kk;
+          HYP_PHASE(t_bar);
+        }
       }
     }
     __syncthreads();
@@ -645,21 +659,34 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
       __syncthreads();
     }
     cur ^= 1;
-    if (threadIdx.x == 0) { long long t = clock64(); t_mid += t - t_mark; t_mark = t; }
+    if (threadIdx.x == 0) HYP_PHASE(t_mid);
     if (n_mod == b) ++owned;
     ++n;
     if (++n_mod == G) { n_mod = 0; ++n_div; }
     ++done;
-    const int step = p.step0 + k;
-    if (p.thr_every > 0 && step > 0 && step % p.thr_every == 0) { thr *= p.thr_mul; thr_f = (float)thr; }
+    if ((long long)k == next_thr) {          // step0 + k is a positive multiple of thr_every
+      thr *= p.thr_mul;
+      thr_f = (float)thr;
+      next_thr += p.thr_every;
+    }
   }
 
+#ifdef HYP_LOOP_PROF
   if (threadIdx.x == 0 && (b == 0 || b == G - 1)) {
-    // phase cycle counters of the first and last CTA (diagnostics; read by bench.py):
+    // phase cycle counters of the first and last CTA (read by bench.py):
     // [0] wait for the speculating warp + recompute on a failed guess, [1] scan, [2] exchange
     long long *prof = p.ws->prof + (b == 0 ? 0 : 4);
     prof[0] = t_mid; prof[1] = t_scan; prof[2] = t_bar; prof[3] = done;
   }
+  if (b == 0 && threadIdx.x == 0)
+    for (int q_ = 0; q_ < 8; ++q_) p.ws->mprof[q_] = a_prof[q_];
+#endif
+#ifdef HYP_MID_PROF
+  if (b == 0 && spec_warp && lane == 0) {
+    for (int q_ = 0; q_ < 8; ++q_) p.ws->mprof[q_] = m_prof[q_];
+    p.ws->prof[3] = done;
+  }
+#endif
   if (b == 0 && threadIdx.x == 0) {
     p.state->n = n;
     p.state->best_d = best.d;
@@ -776,8 +803,6 @@ extern "C" int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float
     ResidentParams rp;
     rp.lp = p;
     rp.slots = slots;
-    const char *ex = getenv("HYP_EXCHANGE");
-    rp.exchange = ex ? atoi(ex) : 0;
     const size_t smem = ((size_t)8 * G4 + (size_t)4 * G4 * slots + slots + (size_t)8 * D) * sizeof(float);
     const void *fn = Nsp == 100 ? (const void *)merge_loop_resident_kernel<100>
                      : Nsp == 50 ? (const void *)merge_loop_resident_kernel<50>
