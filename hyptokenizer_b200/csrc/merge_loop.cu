@@ -25,9 +25,10 @@ constexpr int kRowsPerIter = 4;  // rows a warp keeps in flight (independent red
 constexpr int kXRing = 1024;     // exchange slots of the resident loop (step k uses slot k mod kXRing)
 
 struct LoopWorkspace {
-  unsigned int barrier;  // monotonically increasing arrival counter
-  unsigned int ticket;   // hyp_row_min: last-block-done
-  unsigned int pad[6];
+  unsigned int barrier;    // monotonically increasing arrival counter
+  unsigned int ticket;     // hyp_row_min: last-block-done
+  unsigned int published;  // resident loop: scans whose global appends CTA 0 has fenced (release sequence number)
+  unsigned int pad[5];
   long long prof[8];               // resident loop: phase cycle counters of CTA 0 and CTA G-1
   long long mprof[8];              // debug: midpoint sub-phase cycles of CTA 0
   unsigned long long reserved[4];
@@ -58,6 +59,17 @@ __device__ __forceinline__ void ld_acquire_v2_u64(const void *p, unsigned long l
 }
 __device__ __forceinline__ void red_release_add_u32(unsigned int *p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_v2_u64(const void *p, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned int *p, unsigned int v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void red_relaxed_add_u32(unsigned int *p, unsigned int v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -422,17 +434,10 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// -DHYP_LOOP_PROF (make EXTRA=-DHYP_LOOP_PROF): thread 0 of CTA 0 accumulates the cycles between consecutive marks
-// into ws->mprof[0..7], and CTA 0 / CTA G-1 the three phases into ws->prof; the product build reads no clocks.
+// -DHYP_LOOP_PROF (make EXTRA=-DHYP_LOOP_PROF): thread 0 of CTA 0 and of CTA G-1 accumulate the cycles of the
+// three phases of an iteration into ws->prof (read by bench.py); -DHYP_MID_PROF: the speculating warp of CTA 0
+// accumulates the sub-phases of its midpoint into ws->mprof.  The product build reads no clocks.
 #ifdef HYP_LOOP_PROF
-#define HYP_PROF_MARK(id)                                                     \
-  do {                                                                        \
-    if (threadIdx.x == 0 && b == 0) {                                         \
-      const long long t_ = clock64();                                         \
-      a_prof[id] += t_ - t_prof;                                              \
-      t_prof = t_;                                                            \
-    }                                                                         \
-  } while (0)
 #define HYP_PHASE(acc)                                                        \
   do {                                                                        \
     const long long t_ = clock64();                                           \
@@ -440,10 +445,21 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
     t_mark = t_;                                                              \
   } while (0)
 #else
-#define HYP_PROF_MARK(id) do { } while (0)
 #define HYP_PHASE(acc) do { } while (0)
 #endif
 
+// Software pipeline of the loop.  Merge k appends q_k = midpoint(best_k), scans it against the rows below it
+// (scan_k), and the grid exchange of the per-CTA minima (exchange_k) gives best_{k+1}.  The exchange is a round
+// trip through L2 that nothing can shorten, so it is overlapped with the NEXT merge's work under the guess that
+// exchange_k will not beat best_k (the reference's loop settles on one pair after a few merges):
+//   iteration k:   scan warps:        scan_{k+1} with q'_{k+1} = midpoint(best_k), then thread 0 polls exchange_k
+//                  speculating warp:  q''_{k+2} = midpoint(best_k)
+//   decide:        unchanged -> commit merge k, post the arrival of exchange_{k+1}, rotate the three q buffers
+//                  changed   -> commit merge k with the new best, recompute q_{k+1}, redo scan_{k+1} and q'_{k+2}
+// Every scan and every midpoint is computed in full each merge; a wrong guess only costs the redo.  What a
+// speculative scan writes (row n+1 of the table in shared and global memory, its len and log entry) lies beyond the
+// committed state and is rewritten by the redo; a guess is only made when merge k+1 is due under it, and a changed
+// best (smaller distance) cannot make it undue, so nothing speculative survives the launch.
 template <int NS>
 __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(const ResidentParams rp) {
   extern __shared__ __align__(16) float smem[];
@@ -453,12 +469,12 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   const int G = gridDim.x, b = blockIdx.x;
   constexpr int kWork = kResThreads - 32;      // threads that scan; the last warp speculates
   constexpr int kWorkWarps = kWork / 32;
-  // layout (floats): qq4[2][4*G4] | T4[4*G4*S] | T0[S] | qrow[2][D] | xi[D] xj[D] scratch[2][2D]
+  // layout (floats): qq4[3][4*G4] | T4[4*G4*S] | T0[S] | qrow[3][D] | xi[D] xj[D] scratch[2][2D]
   float4 *qq4 = reinterpret_cast<float4 *>(smem);
-  float4 *T4 = qq4 + 2 * G4;
+  float4 *T4 = qq4 + 3 * G4;
   float *T0 = reinterpret_cast<float *>(T4 + (size_t)G4 * S);
   float *qrow = T0 + S;
-  float *xi = qrow + 2 * D;
+  float *xi = qrow + 3 * D;
   float *xj = xi + D;
   float *scratch = xj + D;
   float *Tf = reinterpret_cast<float *>(T4);
@@ -472,14 +488,14 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   const int cap = p.state->capacity;
   Key best{p.state->best_d, p.state->best_i, p.state->best_j};
   double thr = p.state->threshold;
-  int done = 0, stop = 0, cur = 0;
+  int done = 0, stop = 0;
+  int cur = 0, nx1 = 1, nx2 = 2;               // q buffers: q_k | q'_{k+1} | q''_{k+2}
   unsigned int arrivals = (unsigned int)G;
 #ifdef HYP_MID_PROF
-  long long m_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // sub-phases of the speculating warp's midpoint (CTA 0, lane 0)
+  long long m_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
 #ifdef HYP_LOOP_PROF
   long long t_mid = 0, t_scan = 0, t_bar = 0, t_mark = 0;
-  long long t_prof = clock64(), a_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
 
   auto midpoint_into = [&](int which, float *scr, long long *tp = nullptr) {
@@ -493,8 +509,8 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
 
   // ---- load the rows this CTA owns: a warp reads one row (coalesced), scatters it conflict-free --
   {
-    const int owned = (n > b) ? (n - b + G - 1) / G : 0;
-    for (int sl = warp; sl < owned; sl += kResWarps) {
+    const int owned0 = (n > b) ? (n - b + G - 1) / G : 0;
+    for (int sl = warp; sl < owned0; sl += kResWarps) {
       const float *row = p.E + ((int64_t)sl * G + b) * p.ldE;
       for (int k = lane; k < D; k += 32) {
         const float v = __ldcg(row + k);
@@ -503,7 +519,7 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
       }
     }
     float *qf = reinterpret_cast<float *>(qq4);
-    for (int k = threadIdx.x; k < 8 * G4; k += blockDim.x) qf[k] = 0.f;   // padding lanes of both q4 stay zero
+    for (int k = threadIdx.x; k < 12 * G4; k += blockDim.x) qf[k] = 0.f;   // padding lanes of the q4 buffers stay zero
     // operand rows of the current best pair (kept in shared memory until the best pair changes)
     if (best.i >= 0) {
       for (int e = threadIdx.x; e < D; e += blockDim.x) {
@@ -521,165 +537,218 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
     }
   }
   grid_barrier(&p.ws->barrier, arrivals);
-  // midpoint row of the initial best pair (hyperbolic_merge.py:317-340)
-  if (warp == 0 && best.i >= 0) midpoint_into(cur, scratch);
-  __syncthreads();
-#ifdef HYP_LOOP_PROF
-  if (threadIdx.x == 0) t_mark = clock64();
-#endif
 
   // loop-carried bookkeeping without integer division: rows this CTA owns below n, and whether/where row n lands here
   int owned = (n > b) ? (n - b + G - 1) / G : 0;
   int n_mod = n % G, n_div = n / G;
   float thr_f = (float)thr;
-  long long next_thr = -1;                   // first k at which the threshold is multiplied
+  long long next_thr = -1;                   // first k after which the threshold is multiplied
   if (p.thr_every > 0) {
     next_thr = (p.thr_every - p.step0 % p.thr_every) % p.thr_every;
     if (p.step0 + next_thr == 0) next_thr = p.thr_every;
   }
 
-  for (int k = 0; k < p.max_steps; ++k) {
-    // invariant: qrow[cur] / qq4[cur] hold the merged row for `best`, computed from xi, xj, s_len
-    bool have = best.i >= 0;
-    if (have) have = (n <= 100) ? ((double)best.d < thr) : (best.d < thr_f);   // hyperbolic_merge.py:288 vs :262
-    if (!have) { stop = 1; break; }
-    if (n >= cap) { stop = 2; break; }
-    const float *q = qrow + cur * D;
-    const float4 *q4 = qq4 + cur * G4;
-    unsigned long long win = kNoKey;
-    HYP_PROF_MARK(7);
+  // is merge kk due?  0: yes; -1: max_steps reached; 1: no pair under the threshold; 2: vocabulary full
+  auto due = [&](int kk, int nn, const Key &bb, double th, float th_f) -> int {
+    if (kk >= p.max_steps) return -1;
+    bool have = bb.i >= 0;
+    if (have) have = (nn <= 100) ? ((double)bb.d < th) : (bb.d < th_f);     // hyperbolic_merge.py:288 vs :262
+    if (!have) return 1;
+    if (nn >= cap) return 2;
+    return 0;
+  };
+
+  // scan_kk: score row nn (= the q buffer `qb`) against the resident rows below it, append it, and leave the CTA's
+  // (distance bits, row) minimum in (c_d, c_r) on warp 0.  Called by the scanning warps only.
+  unsigned int c_d = 0xffffffffu, c_r = 0xffffffffu;
+  unsigned long long e_key = 0, e_cnt = 0;     // thread 0: the early poll of the previous exchange (see scan)
+  bool e_issued = false;
+  unsigned int nscan = 0;                      // scans started so far; identical in every CTA
+  auto scan = [&](int qb, int nn, int own, int nmod, int ndiv, int kk, const LoopWorkspace::XSlot *early) {
+    ++nscan;
+    const float *q = qrow + qb * D;
+    const float4 *q4 = qq4 + qb * G4;
+    const float q0 = q[0];
+    unsigned int my_d = 0xffffffffu, my_r = 0xffffffffu;   // d >= 0, so the bits order like d
+    if (b == 0 && warp == kWorkWarps - 1) {
+      // append row nn to the table in global memory (the caller's `embeddings`) and log the merge.  Done by the
+      // last scanning warp (it has the fewest rows), which then fences and publishes the scan's sequence number:
+      // the arrivals of the exchange stay free of fences (a fence next to the arrival cost 13 % of the merge
+      // rate).  Readers (the failed-guess path, and every CTA once per kXRing/4 merges for the recycled slots)
+      // wait for `published` before they touch what was written here.
+      for (int e = lane; e < D; e += 32) p.E[(int64_t)nn * p.ldE + e] = q[e];
+      if (lane == 0) {
+        p.len[nn] = s_len[0] + s_len[1];
+        p.log[kk] = hyp_merge_record{best.i, best.j, best.d, nn};
+        // recycle the exchange slot used kXRing/2 merges ago (every CTA is past it) for its use kXRing/2 merges on
+        p.ws->xring[(kk + kXRing / 2) & (kXRing - 1)].key = kNoKey;
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_relaxed_u32(&p.ws->published, nscan);
+    }
+    for (int t = threadIdx.x; t < own; t += kWork) {
+      const float m = (NS > 0) ? resident_mdot_static<(NS > 0 ? NS : 8)>(T4, T0, S, t, q4, q0)
+                               : resident_mdot_dynamic(T4, T0, S, t, q4, q0, N);
+      if (early && t == 0) {
+        // thread 0, half way through its scan: every CTA posted its arrival for the PREVIOUS exchange before it
+        // started this scan, so by now the slot is almost surely complete.  The load's round trip through L2
+        // hides behind the rest of the scan; poll() takes the value if the count is full.
+        ld_relaxed_v2_u64(early, e_key, e_cnt);
+        e_issued = true;
+      }
+      const float d = dist_from_mdot(m, p.sgn, p.sqrt_c);
+      if (d == d && __float_as_uint(d) < my_d) {           // rows ascend with t: strict < keeps the smallest row
+        my_d = __float_as_uint(d);
+        my_r = (unsigned int)(t * G + b);
+      }
+    }
+    // the owner of row nn appends it (its slot is beyond `own`, so nobody reads it during this scan)
+    if (nmod == b) {
+      for (int e = threadIdx.x; e < D; e += kWork) {
+        if (e == 0) T0[ndiv] = q[0];
+        else Tf[((size_t)((e - 1) >> 2) * S + ndiv) * 4 + ((e - 1) & 3)] = q[e];
+      }
+    }
+    // lexicographic (d, row) minimum of the warp with two REDUX instructions, then of the CTA on warp 0
+    const unsigned int w_d = __reduce_min_sync(HYP_FULL_MASK, my_d);
+    const unsigned int w_r = __reduce_min_sync(HYP_FULL_MASK, my_d == w_d ? my_r : 0xffffffffu);
+    if (lane == 0) s_key[warp] = ((unsigned long long)w_d << 32) | w_r;
+    bar_named(1, kWork);
+    if (warp == 0) {
+      const unsigned long long wk = lane < kWorkWarps ? s_key[lane] : kNoKey;
+      const unsigned int k_d = (unsigned int)(wk >> 32), k_r = (unsigned int)(wk & 0xffffffffu);
+      c_d = __reduce_min_sync(HYP_FULL_MASK, k_d);
+      c_r = __reduce_min_sync(HYP_FULL_MASK, k_d == c_d ? k_r : 0xffffffffu);
+    }
+  };
+
+  // ---- exchange on ONE 16-byte slot per merge (slot kk mod kXRing; its counter is never reset, use u completes at
+  // G * u).  A CTA posts its minimum (64-bit RED.MIN) only when it beats `best` -- every CTA holds the same `best`,
+  // so a key that does not beat it cannot change the outcome -- and then arrives (RED.ADD).  Arrival is a release
+  // only behind a posted key; everything else arrives relaxed (CTA 0's appends are published separately, see scan).  Every CTA reads the slot with a single 128-bit load: the load that sees the full count also
+  // carries the final minimum (a RED.MIN is ordered before its CTA's arrival, and the arrivals form one RMW chain
+  // on `count`), so there is no second round trip.  Thread 0 only.
+  auto arrive = [&](int kk, int nn) {
+    LoopWorkspace::XSlot *xr = &p.ws->xring[kk & (kXRing - 1)];
+    const bool post = c_r != 0xffffffffu && key_less(Key{__uint_as_float(c_d), (int)c_r, nn}, best);
+    if (post) atomicMin(&xr->key, ((unsigned long long)c_d << 32) | c_r);
+    if (post) red_release_add_u32(&xr->count, 1u);
+    else red_relaxed_add_u32(&xr->count, 1u);
+  };
+  auto poll = [&](int kk) {
+    const LoopWorkspace::XSlot *xr = &p.ws->xring[kk & (kXRing - 1)];
+    const unsigned int target = (unsigned int)G * (unsigned int)((kk / kXRing) + 1);
+    unsigned long long key = e_key, cc = e_cnt;
+    if (!e_issued) ld_relaxed_v2_u64(xr, key, cc);
+    while ((unsigned int)(cc & 0xffffffffu) < target) ld_relaxed_v2_u64(xr, key, cc);
+    e_issued = false;
+    s_win[kk & 1] = key;
+  };
+  // Thread 0: wait until CTA 0 has fenced the appends of every scan before the one in flight, then fence: what those
+  // scans wrote (rows / len below n, recycled exchange slots) may be read after the next CTA barrier.
+  auto wait_published = [&]() {
+    while (ld_relaxed_u32(&p.ws->published) + 1u < nscan) {
+    }
+    __threadfence();
+  };
+
+  // ---- prologue: q_0, then scan_0 + arrival 0 next to q'_1 (hyperbolic_merge.py:317-340) -------------------------
+  int code = due(0, n, best, thr, thr_f);
+  if (code == 0) {
+    if (warp == 0) midpoint_into(cur, scratch);
+    __syncthreads();
+    if (spec_warp) {
+      midpoint_into(nx1, scratch + 2 * D);
+    } else {
+      scan(cur, n, owned, n_mod, n_div, 0, nullptr);
+      if (threadIdx.x == 0) arrive(0, n);
+    }
+    __syncthreads();
+  }
+#ifdef HYP_LOOP_PROF
+  if (threadIdx.x == 0) t_mark = clock64();
+#endif
+
+  for (int k = 0; code == 0; ++k) {
+    // invariant: merge k is due; `best`, q_k (buffer cur) are final; scan_k is done and its arrival posted;
+    // q'_{k+1} (buffer nx1) is the merged row for `best`, computed from xi, xj, s_len
+    const bool bump = (long long)k == next_thr;            // step0 + k is a positive multiple of thr_every
+    const double thr_n = bump ? thr * p.thr_mul : thr;
+    const float thr_nf = bump ? (float)thr_n : thr_f;
+    const int own1 = owned + (n_mod == b ? 1 : 0);
+    const bool wrap = n_mod + 1 == G;
+    const int nmod1 = wrap ? 0 : n_mod + 1, ndiv1 = n_div + (wrap ? 1 : 0);
+    code = due(k + 1, n + 1, best, thr_n, thr_nf);         // is merge k+1 due if `best` stays?
 
     if (spec_warp) {
-      // ---- speculation: if this step's scan does not produce a better pair, `best` (and so its rows)
-      // stays, and the NEXT merged row is the midpoint of the same operands.  It is recomputed here, in
-      // full, while the other warps scan and exchange; it is used only if the guess holds.
 #ifdef HYP_MID_PROF
-      midpoint_into(cur ^ 1, scratch + 2 * D, m_prof);
+      if (code == 0) midpoint_into(nx2, scratch + 2 * D, m_prof);
 #else
-      midpoint_into(cur ^ 1, scratch + 2 * D);
+      if (code == 0) midpoint_into(nx2, scratch + 2 * D);
 #endif
     } else {
-      // ---- score row n against the resident rows (< n) of this CTA ---------------------------------------
-      const float q0 = q[0];
-      unsigned int my_d = 0xffffffffu, my_r = 0xffffffffu;   // (distance bits, row): d >= 0, so the bits order like d
-      if (b == 0 && warp == kWorkWarps - 1) {
-        // append row n = q to the table in global memory (the caller's `embeddings`) and log the merge.  Done by the
-        // last scanning warp (it has the fewest rows) BEFORE its scan: thread 0's release below waits for the
-        // CTA's outstanding stores, so they have to be long gone by then (issuing them next to the exchange
-        // cost 13 % of the merge rate).  The named barrier + that release publish row n / len / log and the
-        // recycled slot with this step's exchange; nobody reads them earlier.
-        for (int e = lane; e < D; e += 32) p.E[(int64_t)n * p.ldE + e] = q[e];
-        if (lane == 0) {
-          p.len[n] = s_len[0] + s_len[1];
-          p.log[k] = hyp_merge_record{best.i, best.j, best.d, n};
-          // recycle the exchange slot used kXRing/2 steps ago (every CTA is past it) for its next use kXRing/2
-          // steps from now
-          p.ws->xring[(k + kXRing / 2) & (kXRing - 1)].key = kNoKey;
-        }
-      }
-      for (int t = threadIdx.x; t < owned; t += kWork) {
-        HYP_PROF_MARK(0);
-        const float m = (NS > 0) ? resident_mdot_static<(NS > 0 ? NS : 8)>(T4, T0, S, t, q4, q0)
-                                 : resident_mdot_dynamic(T4, T0, S, t, q4, q0, N);
-        HYP_PROF_MARK(1);
-        const float d = dist_from_mdot(m, p.sgn, p.sqrt_c);
-        HYP_PROF_MARK(2);
-        if (d == d && __float_as_uint(d) < my_d) {           // rows ascend with t: strict < keeps the smallest row
-          my_d = __float_as_uint(d);
-          my_r = (unsigned int)(t * G + b);
-        }
-      }
-      // the owner of row n appends it (its slot is beyond `owned`, so nobody reads it this step)
-      if (n_mod == b) {
-        for (int e = threadIdx.x; e < D; e += kWork) {
-          if (e == 0) T0[n_div] = q[0];
-          else Tf[((size_t)((e - 1) >> 2) * S + n_div) * 4 + ((e - 1) & 3)] = q[e];
-        }
-      }
-      HYP_PROF_MARK(6);
-      // lexicographic (d, row) minimum of the warp with two REDUX instructions
-      const unsigned int w_d = __reduce_min_sync(HYP_FULL_MASK, my_d);
-      const unsigned int w_r = __reduce_min_sync(HYP_FULL_MASK, my_d == w_d ? my_r : 0xffffffffu);
-      HYP_PROF_MARK(3);
-      if (lane == 0) s_key[warp] = ((unsigned long long)w_d << 32) | w_r;
-      bar_named(1, kWork);
-      HYP_PROF_MARK(4);
-      // ---- exchange on ONE 16-byte slot per step.  A CTA posts its minimum (64-bit RED.MIN) only when it
-      // beats `best` -- every CTA holds the same `best`, so a key that does not beat it cannot change the
-      // outcome -- and then arrives (RED.ADD).  Arrival is a release only where there is something to
-      // publish: a posted key, or CTA 0's appended row / recycled slot; the other CTAs arrive relaxed and
-      // go straight to polling.  Every CTA polls the slot with a single 128-bit acquire load: the load that
-      // sees the full count also carries the final minimum (a RED.MIN is ordered before its CTA's arrival,
-      // and the arrivals form one RMW chain on `count`), so there is no second round trip.
-      if (warp == 0) {
-        const unsigned long long wk = lane < kWorkWarps ? s_key[lane] : kNoKey;
-        const unsigned int k_d = (unsigned int)(wk >> 32), k_r = (unsigned int)(wk & 0xffffffffu);
-        const unsigned int c_d = __reduce_min_sync(HYP_FULL_MASK, k_d);
-        const unsigned int c_r = __reduce_min_sync(HYP_FULL_MASK, k_d == c_d ? k_r : 0xffffffffu);
-        if (lane == 0) {
-          LoopWorkspace::XSlot *xr = &p.ws->xring[k & (kXRing - 1)];
-          const unsigned int target = (unsigned int)G * (unsigned int)((k / kXRing) + 1);
-          const bool post = c_r != 0xffffffffu && key_less(Key{__uint_as_float(c_d), (int)c_r, n}, best);
-          if (post) atomicMin(&xr->key, ((unsigned long long)c_d << 32) | c_r);
-          HYP_PROF_MARK(5);
-          HYP_PHASE(t_scan);
-#ifdef HYP_X_B0RELAXED   // measurement only: what CTA 0's fence costs
-          if (post) red_release_add_u32(&xr->count, 1u);
-#else
-          if (post || b == 0) red_release_add_u32(&xr->count, 1u);
-#endif
-          else red_relaxed_add_u32(&xr->count, 1u);
-          unsigned long long kk, cc;
-          do { ld_acquire_v2_u64(xr, kk, cc); } while ((unsigned int)(cc & 0xffffffffu) < target);
-          s_win[k & 1] = kk;
-          HYP_PHASE(t_bar);
-        }
+      if (code == 0) scan(nx1, n + 1, own1, nmod1, ndiv1, k + 1, &p.ws->xring[k & (kXRing - 1)]);
+      if (threadIdx.x == 0) {
+        HYP_PHASE(t_scan);
+        poll(k);
+        HYP_PHASE(t_bar);
       }
     }
     __syncthreads();
-    win = s_win[k & 1];
+    const unsigned long long win = s_win[k & 1];
 
     bool changed = false;
     if (win != kNoKey) {
       Key r{__uint_as_float((unsigned int)(win >> 32)), (int)(win & 0xffffffffu), n};
       if (key_less(r, best)) { best = r; changed = true; }
     }
+    // commit merge k
+    ++done;
+    ++n;
+    owned = own1; n_mod = nmod1; n_div = ndiv1;
+    thr = thr_n; thr_f = thr_nf;
+    if (bump) next_thr += p.thr_every;
+
     if (changed) {
-      // new best pair = (i_win, n): row n is q (still in shared memory), row i_win comes from L2
+      // new best pair = (i_win, n-1): row n-1 is q_k (still in shared memory), row i_win comes from L2
+      const float *qk = qrow + cur * D;
       const int ln = s_len[0] + s_len[1];
+      if (threadIdx.x == 0) wait_published();
       __syncthreads();
       for (int e = threadIdx.x; e < D; e += blockDim.x) {
-        xj[e] = q[e];
+        xj[e] = qk[e];
         xi[e] = __ldcg(p.E + (int64_t)best.i * p.ldE + e);
       }
       if (threadIdx.x == 0) s_len[0] = __ldcg(p.len + best.i);
       if (threadIdx.x == 1) s_len[1] = ln;
+      code = due(k + 1, n, best, thr, thr_f);
       __syncthreads();
-      if (warp == 0) midpoint_into(cur ^ 1, scratch);     // the guess failed: compute the real next row
-      __syncthreads();
+      if (code == 0) {
+        // the guess failed: the real q_{k+1}, then scan_{k+1} next to the new q'_{k+2}
+        if (warp == 0) midpoint_into(nx1, scratch);
+        __syncthreads();
+        if (spec_warp) midpoint_into(nx2, scratch + 2 * D);
+        else scan(nx1, n, owned, n_mod, n_div, k + 1, nullptr);
+        __syncthreads();
+      }
     }
-    cur ^= 1;
+    if (code != 0) break;
+    if (threadIdx.x == 0) {
+      if ((k & (kXRing / 4 - 1)) == kXRing / 4 - 1) wait_published();   // recycled slots: see scan
+      arrive(k + 1, n);
+    }
+    const int t = cur; cur = nx1; nx1 = nx2; nx2 = t;
     if (threadIdx.x == 0) HYP_PHASE(t_mid);
-    if (n_mod == b) ++owned;
-    ++n;
-    if (++n_mod == G) { n_mod = 0; ++n_div; }
-    ++done;
-    if ((long long)k == next_thr) {          // step0 + k is a positive multiple of thr_every
-      thr *= p.thr_mul;
-      thr_f = (float)thr;
-      next_thr += p.thr_every;
-    }
   }
+  stop = code > 0 ? code : 0;
 
 #ifdef HYP_LOOP_PROF
   if (threadIdx.x == 0 && (b == 0 || b == G - 1)) {
-    // phase cycle counters of the first and last CTA (read by bench.py):
-    // [0] wait for the speculating warp + recompute on a failed guess, [1] scan, [2] exchange
+    // [0] decide + commit (+ redo on a failed guess), [1] scan, [2] poll
     long long *prof = p.ws->prof + (b == 0 ? 0 : 4);
     prof[0] = t_mid; prof[1] = t_scan; prof[2] = t_bar; prof[3] = done;
   }
-  if (b == 0 && threadIdx.x == 0)
-    for (int q_ = 0; q_ < 8; ++q_) p.ws->mprof[q_] = a_prof[q_];
 #endif
 #ifdef HYP_MID_PROF
   if (b == 0 && spec_warp && lane == 0) {
@@ -793,7 +862,7 @@ extern "C" int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float
 
   // table-resident variant when every row up to `capacity_hint` fits in the grid's shared memory
   const int Nsp = D - 1, G4 = (Nsp + 3) / 4;
-  const int64_t fixed = ((int64_t)8 * G4 + (int64_t)8 * D) * (int64_t)sizeof(float) + 1024;
+  const int64_t fixed = ((int64_t)12 * G4 + (int64_t)9 * D) * (int64_t)sizeof(float) + 1024;
   int slots = (int)(((int64_t)max_smem - fixed) / (((int64_t)4 * G4 + 1) * (int64_t)sizeof(float)));
   if ((slots & 1) == 0) --slots;  // odd stride: conflict-free scattered stores
   const char *force = getenv("HYP_MERGE_LOOP");
@@ -803,7 +872,7 @@ extern "C" int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float
     ResidentParams rp;
     rp.lp = p;
     rp.slots = slots;
-    const size_t smem = ((size_t)8 * G4 + (size_t)4 * G4 * slots + slots + (size_t)8 * D) * sizeof(float);
+    const size_t smem = ((size_t)12 * G4 + (size_t)4 * G4 * slots + slots + (size_t)9 * D) * sizeof(float);
     const void *fn = Nsp == 100 ? (const void *)merge_loop_resident_kernel<100>
                      : Nsp == 50 ? (const void *)merge_loop_resident_kernel<50>
                                  : (const void *)merge_loop_resident_kernel<0>;
