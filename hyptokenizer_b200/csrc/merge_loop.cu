@@ -456,7 +456,10 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
 //                  speculating warp:  q''_{k+2} = midpoint(best_k)
 //   decide:        unchanged -> commit merge k, post the arrival of exchange_{k+1}, rotate the three q buffers
 //                  changed   -> commit merge k with the new best, recompute q_{k+1}, redo scan_{k+1} and q'_{k+2}
-// Every scan and every midpoint is computed in full each merge; a wrong guess only costs the redo.  What a
+// Every scan and every midpoint is computed in full each merge; a wrong guess only costs the redo.  (Guessing
+// only after a guess that held was tried: the extra branch cost 4 % of the steady-state rate, and wrong guesses are
+// confined to the first few dozen merges of a run -- each merge halves the best distance until it reaches 0 and
+// index order then pins one pair for good.)  What a
 // speculative scan writes (row n+1 of the table in shared and global memory, its len and log entry) lies beyond the
 // committed state and is rewritten by the redo; a guess is only made when merge k+1 is due under it, and a changed
 // best (smaller distance) cannot make it undue, so nothing speculative survives the launch.
@@ -534,6 +537,7 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
     for (int sl = threadIdx.x; sl < kXRing; sl += blockDim.x) {
       p.ws->xring[sl].key = kNoKey;
       p.ws->xring[sl].count = 0u;
+      p.ws->xring[sl].pad = 0u;
     }
   }
   grid_barrier(&p.ws->barrier, arrivals);
@@ -641,7 +645,9 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
     const unsigned int target = (unsigned int)G * (unsigned int)((kk / kXRing) + 1);
     unsigned long long key = e_key, cc = e_cnt;
     if (!e_issued) ld_relaxed_v2_u64(xr, key, cc);
-    while ((unsigned int)(cc & 0xffffffffu) < target) ld_relaxed_v2_u64(xr, key, cc);
+    // (the pad word, always 0, is added in so that all four registers of the early load stay live until here:
+    //  a register of an in-flight load that the compiler reuses stalls the scan for the whole round trip)
+    while ((unsigned int)(cc & 0xffffffffu) + (unsigned int)(cc >> 32) < target) ld_relaxed_v2_u64(xr, key, cc);
     e_issued = false;
     s_win[kk & 1] = key;
   };

@@ -263,6 +263,27 @@ def test_loop_variants_identical(monkeypatch):
         assert np.array_equal(logs[0][0], logs[1][0]) and same_bits(logs[0][1], logs[1][1])
 
 
+def test_pipelined_loop_long_run_and_no_speculative_leftovers(monkeypatch):
+    """The resident loop runs scan k+1 ahead of exchange k on a guess and recycles its 1024 exchange slots: a run
+    long enough to reuse every slot twice must still equal the L2 loop bit for bit, and nothing a speculative scan
+    wrote (table rows, lengths) may survive beyond the committed vocabulary."""
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    from hyptokenizer_b200.tokenizer.hyperbolic_merge import HyperbolicTokenizer
+    n0, steps, cap = 2000, 2600, 5000
+    outs = []
+    for variant in ("resident", "l2"):
+        monkeypatch.setenv("HYP_MERGE_LOOP", variant)
+        emb = synthetic_embeddings(n0, 100, scale=0.05, seed=11, device="cuda")
+        tok = HyperbolicTokenizer([f"w{k}" for k in range(n0)], torch.nn.Parameter(emb), merge_threshold=0.9,
+                                  max_vocab_size=cap, semantics="lorentz")
+        for part in (1100, 1500):                   # two launches: the second starts from the persisted state
+            tok.optimize_merges(steps=part)
+        assert tok.current_vocab_size == n0 + steps
+        outs.append((tok.vocab[-1], tok.embeddings.detach().cpu()))
+        assert torch.count_nonzero(tok.embeddings[n0 + steps:]).item() == 0
+    assert outs[0][0] == outs[1][0] and same_bits(outs[0][1], outs[1][1])
+
+
 def test_row_min_entry_point():
     """K4 as a standalone call: argmin over i != row of (d(E[i], E[row]), pair) and the count below threshold."""
     from hyptokenizer_b200 import _lib
