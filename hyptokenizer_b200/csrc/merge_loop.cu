@@ -271,6 +271,11 @@ __global__ void __launch_bounds__(kLoopThreads) merge_loop_l2_kernel(const LoopP
   __shared__ unsigned long long s_cnt[kLoopWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+  // a launch on a state that has already stopped does nothing (lets a caller queue several launches back to back)
+  if (p.state->stop != 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.state->steps_done = 0;
+    return;
+  }
   // replicated loop state (identical in every CTA)
   int n = p.state->n;
   const int cap = p.state->capacity;
@@ -487,6 +492,11 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool spec_warp = warp == kResWarps - 1;
 
+  // a launch on a state that has already stopped does nothing (lets a caller queue several launches back to back)
+  if (p.state->stop != 0) {
+    if (b == 0 && threadIdx.x == 0) p.state->steps_done = 0;
+    return;
+  }
   int n = p.state->n;
   const int cap = p.state->capacity;
   Key best{p.state->best_d, p.state->best_i, p.state->best_j};

@@ -31,6 +31,7 @@ TORCH_COMPILE_AVAILABLE = False
 USING_COMPILED = False
 
 _RECORD_DTYPE = np.dtype([("i", "<i4"), ("j", "<i4"), ("d", "<f4"), ("n_new", "<i4")])
+_SEGMENT = 8192   # merges per queued hyp_merge_steps call (see _device_loop)
 
 
 def _threshold_f32(thr: float, n: int) -> float:
@@ -193,28 +194,58 @@ class HyperbolicTokenizer:
         state = ws["state"]
         state.copy_(torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8))
         log = torch.empty((max_steps, 4), dtype=torch.int32, device=E.device)
+        # A long run is queued as segments of _SEGMENT merges, with no host round trip in between: a call on a
+        # stopped state is a no-op.  Each segment's log and state snapshot are copied to pinned memory behind it,
+        # so the host rebuilds the strings of segment s (what _merge_tokens does per merge, :347-355) while the
+        # device runs segment s+1.
+        segs = [(off, min(_SEGMENT, max_steps - off)) for off in range(0, max_steps, _SEGMENT)]
+        pin = self._pinned(max_steps, len(segs))
+        h_log, h_state = pin["log"], pin["state"]
+        events = []
+        hint = min(cap, n0 + max_steps)
         with torch.cuda.device(E.device):
-            check(_lib.lib().hyp_merge_steps(ptr(E), E.stride(0), ptr(lens), D, float(self.curvature),
-                                             SEM[self.semantics], ptr(state), ptr(log), max_steps, step0,
-                                             threshold_every, float(threshold_mul), min(cap, n0 + max_steps),
-                                             ptr(ws["loop"]),
-                                             ws["loop"].numel(), stream_ptr()))
-        out = HypMergeState.from_buffer_copy(state.cpu().numpy().tobytes())
-        rec = log[: out.steps_done].cpu().numpy().view(_RECORD_DTYPE).reshape(-1)
+            for s, (off, cnt) in enumerate(segs):
+                check(_lib.lib().hyp_merge_steps(ptr(E), E.stride(0), ptr(lens), D, float(self.curvature),
+                                                 SEM[self.semantics], ptr(state), log[off:].data_ptr(), cnt,
+                                                 step0 + off, threshold_every, float(threshold_mul), hint,
+                                                 ptr(ws["loop"]), ws["loop"].numel(), stream_ptr()))
+                h_state[s].copy_(state, non_blocking=True)
+                h_log[off:off + cnt].copy_(log[off:off + cnt], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                events.append(ev)
+        vocab, t2i, hist, n = self.vocab, self.token2idx, self.merge_history, self.current_vocab_size
+        recs, out = [], None
+        for s, (off, cnt) in enumerate(segs):
+            events[s].synchronize()
+            out = HypMergeState.from_buffer_copy(h_state[s].numpy().tobytes())
+            rec = h_log[off:off + out.steps_done].numpy().view(_RECORD_DTYPE).reshape(-1).copy()
+            recs.append(rec)
+            for i, j in zip(rec["i"].tolist(), rec["j"].tolist()):
+                a, b = vocab[i], vocab[j]
+                m = a + b
+                vocab.append(m)
+                t2i[m] = n
+                n += 1
+                hist.append((a, b, m))
+            if out.stop != 0:
+                break
+        torch.cuda.current_stream(E.device).synchronize()   # the queued no-op segments behind a stop
+        rec = np.concatenate(recs) if len(recs) > 1 else recs[0]
         self._last_state = out
         self.merge_threshold = out.threshold if threshold_every > 0 else self.merge_threshold
-        # host strings from the (i, j) log, exactly what _merge_tokens does per merge (:347-355), inlined
-        vocab, t2i, hist, n = self.vocab, self.token2idx, self.merge_history, self.current_vocab_size
-        for i, j in zip(rec["i"].tolist(), rec["j"].tolist()):
-            a, b = vocab[i], vocab[j]
-            m = a + b
-            vocab.append(m)
-            t2i[m] = n
-            n += 1
-            hist.append((a, b, m))
         self.current_vocab_size = n
         assert self.current_vocab_size == out.n
         return rec, out.stop
+
+    def _pinned(self, max_steps: int, nseg: int):
+        """Pinned landing buffers for the merge log and the per-segment state snapshots (grown on demand)."""
+        pin = getattr(self, "_pin", None)
+        if pin is None or pin["log"].shape[0] < max_steps or pin["state"].shape[0] < nseg:
+            pin = {"log": torch.empty((max(max_steps, 1024), 4), dtype=torch.int32).pin_memory(),
+                   "state": torch.empty((max(nseg, 8), 40), dtype=torch.uint8).pin_memory()}
+            self._pin = pin
+        return pin
 
     def _overrides_candidate_search(self) -> bool:
         return type(self)._find_merge_candidates is not HyperbolicTokenizer._find_merge_candidates

@@ -170,7 +170,10 @@ int hyp_merge_state_init(hyp_merge_state *state, const hyp_best *best, int32_t n
  * `capacity_hint` = an upper bound, known to the host, on the rows the table can reach during this
  * call (min(state->capacity, n + max_steps); the state itself lives on the device): when that many
  * rows fit in the shared memory of one persistent CTA per SM the table-resident kernel runs,
- * otherwise the L2-streaming one; both produce identical bits. */
+ * otherwise the L2-streaming one; both produce identical bits.
+ * A call on a state whose `stop` is already non-zero does nothing (steps_done = 0, stop kept), so a
+ * host may queue a long run as several calls (advancing `log` and `step0`) without a round trip in
+ * between and read each call's log while the next one runs. */
 int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float c, int semantics,
                     hyp_merge_state *state, hyp_merge_record *log, int32_t max_steps,
                     int32_t step0, int32_t threshold_every, double threshold_mul,
