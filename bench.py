@@ -271,7 +271,7 @@ def run_ours(a):
                          "merge_loop_resident_kernel<100> (cooperative, persistent)",
         "roofline": {"bound": "hbm", "kernel": "merge_loop_resident_kernel<100>", "achieved": achieved, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     "traffic": 4119552, "traffic_source": "profiles/r01_prof_merge_raw.csv: dram__bytes_read.sum + "
+                     "traffic": 4177408, "traffic_source": "profiles/r01_prof_merge_raw.csv: dram__bytes_read.sum + "
                                                            "dram__bytes_write.sum of one launch (ncu --set full)",
                      "peak_kind": pk_kind,
                      "algorithmic_bytes_per_launch": abytes, "kernel_ms": loop_ms,
@@ -451,16 +451,22 @@ def run_c3(a):
 # config 4 (pair counting part): 1 GB synthetic token stream
 # ------------------------------------------------------------------------------------------------
 def run_c4(a):
+    import torch.distributed as dist
     from hyptokenizer_b200 import _lib
     from hyptokenizer_b200._lib import check, ptr
     from hyptokenizer_b200.pair_count import pairs_to_dict
     from hyptokenizer_b200.synth import synthetic_corpus
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     _lib.check_device(dev)
-    nbytes = 1 << 30
-    host = torch.from_numpy(synthetic_corpus(nbytes, seed=0)).pin_memory()
+    nbytes = 1 << 30                                   # per rank: every GPU counts its own GiB (weak scaling)
+    host = torch.from_numpy(synthetic_corpus(nbytes, seed=rank)).pin_memory()
     text = host.to(dev)
     cap = 1 << 20
     asc = torch.empty(128 * 128, dtype=torch.int64, device=dev)
@@ -468,15 +474,36 @@ def run_c4(a):
     vals = torch.empty(cap, dtype=torch.int64, device=dev)
     ovf = torch.empty(1, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ts = []
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    ts, tk = [], []
+    sampler = None
     for it in range(a.warmup + a.steps):
+        if it == a.warmup:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            sampler = ClockSampler(local) if rank == 0 else None
         e0.record(stream)
         check(L.hyp_pair_count(ptr(text), nbytes, ptr(asc), ptr(keys), ptr(vals), cap, ptr(ovf), stream.cuda_stream))
         e1.record(stream)
+        if world > 1:
+            dist.all_reduce(asc, op=dist.ReduceOp.SUM)   # the shards' only exchange: the dense 128x128 histogram
+        e2.record(stream)
         torch.cuda.synchronize()
         if it >= a.warmup:
-            ts.append(e0.elapsed_time(e1))
+            ts.append(e0.elapsed_time(e2))
+            tk.append(e0.elapsed_time(e1))
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    tot = torch.tensor([float(sum(ts))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        dist.destroy_process_group()
+        return
     # end to end: pinned host bytes -> H2D -> kernel -> D2H of the tables -> dict
     t0 = time.perf_counter()
     t2 = host.to(dev, non_blocking=True)
@@ -484,16 +511,19 @@ def run_c4(a):
     counts = pairs_to_dict(asc, keys, vals)
     e2e_s = time.perf_counter() - t0
     pk, kind = peaks()
-    ms = float(np.mean(ts))
-    gbs = nbytes / (ms * 1e-3) / 1e9
-    line = {"metric": "pair counting GB/s (1 GB token stream)", "value": gbs, "unit": "GB/s", "n_gpus": 1,
+    ms = float(tot.item()) / a.steps
+    gbs = world * nbytes / (ms * 1e-3) / 1e9
+    kgbs = nbytes / (float(np.mean(tk)) * 1e-3) / 1e9
+    line = {"metric": "pair counting GB/s (1 GB token stream)", "value": gbs, "unit": "GB/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "c4 (pair-count part): 1 GiB ASCII stream, lines of 20 random words; input larger than L2",
+            "config": {"workload": "c4 (pair-count part): 1 GiB ASCII stream per GPU, lines of 20 random words; input "
+                                   "larger than L2" + ("; histograms summed with one all_reduce per step" if world > 1 else ""),
                        "distinct_pairs": len(counts), "total_pairs": int(sum(counts.values()))},
-            "gpu_launches": a.steps, "roofline": {"bound": "hbm", "kernel": "pair_count_kernel", "achieved": gbs,
-                                                  "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+            "gpu_launches": a.steps, "roofline": {"bound": "hbm", "kernel": "pair_count_kernel", "achieved": kgbs,
+                                                  "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": kgbs / pk["hbm_gbs"],
                                                   "traffic": None, "peak_kind": kind},
+            "clocks": clocks,
             "e2e": {"value": nbytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": int(asc.numel() * 8 + 2 * cap * 8)}}
     if not a.no_cpu_baseline:
@@ -506,6 +536,8 @@ def run_c4(a):
                                 "sample": "first 256 MiB of the same stream, C restatement (oracle/pair_count.c), one thread; "
                                           "the reference's Python dict loop measured 2.5 MB/s (BASELINE.md)"}
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -6,7 +6,7 @@ line/strip semantics that are reproduced).
 """
 from __future__ import annotations
 
-from typing import Dict, Tuple, Union
+from typing import Callable, Dict, Optional, Tuple, Union
 
 import numpy as np
 import torch
@@ -78,4 +78,96 @@ def pairs_to_dict(ascii_counts: torch.Tensor, keys: torch.Tensor, vals: torch.Te
         vv = vals[used].cpu().numpy()
         for key, v in zip(kk.tolist(), vv.tolist()):
             out[(chr(key >> 32), chr(key & 0xffffffff))] = int(v)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-GPU: byte-range shards aligned to line boundaries (SURVEY.md 8e)
+# ---------------------------------------------------------------------------------------------------------
+def shard_byte_range(buf: np.ndarray, rank: int, world: int) -> Tuple[int, int]:
+    """[start, end) of `rank`'s share of a corpus: the nominal cuts k*n//world, each moved forward to just behind
+    the next '\n' (or to n).  The reference counts pairs inside each line only (frequency_aware_hyperbolic_merge.py:
+    92-112), and a cut behind '\n' never splits a line (nor a "\r\n"), so the shards count independently."""
+    n = int(buf.size)
+
+    def cut(k: int) -> int:
+        pos = (k * n) // world
+        if pos <= 0 or pos >= n:
+            return max(0, min(pos, n))
+        if buf[pos - 1] == 0x0A:
+            return pos
+        nl = np.flatnonzero(buf[pos:] == 0x0A) if n - pos <= (1 << 20) else None
+        if nl is None:                                     # long corpus: look in growing windows
+            width = 1 << 16
+            while True:
+                w = np.flatnonzero(buf[pos:pos + width] == 0x0A)
+                if w.size or pos + width >= n:
+                    nl = w
+                    break
+                width *= 16
+        return pos + int(nl[0]) + 1 if nl.size else n
+
+    return cut(rank), cut(rank + 1)
+
+
+def reduce_pair_counts(ascii_counts: torch.Tensor, extra: Dict[Tuple[int, int], int], group=None):
+    """Sum the per-shard results over the process group: ONE all_reduce of the dense 128x128 histogram (128 KB,
+    the only data-path collective) and an object all-gather of the (rare) non-ASCII pairs.  Every rank returns
+    the same (ascii_counts, extra)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return ascii_counts, dict(extra)
+    dist.all_reduce(ascii_counts, op=dist.ReduceOp.SUM, group=group)
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, extra, group=group)
+    merged: Dict[Tuple[int, int], int] = {}
+    for part in parts:
+        for key, v in part.items():
+            merged[key] = merged.get(key, 0) + int(v)
+    return ascii_counts, merged
+
+
+def _device_counter(device: torch.device, hash_capacity: int):
+    def count(shard: np.ndarray):
+        text = to_device_bytes(shard, device)
+        cap = hash_capacity
+        while True:
+            ascii_counts, keys, vals, overflow = count_pairs_device(text, cap)
+            if int(overflow.item()) == 0:
+                break
+            cap *= 4
+        extra: Dict[Tuple[int, int], int] = {}
+        used = (keys != -1).nonzero(as_tuple=True)[0]
+        if used.numel():
+            kk = keys[used].cpu().numpy().astype(np.uint64)
+            vv = vals[used].cpu().numpy()
+            for key, v in zip(kk.tolist(), vv.tolist()):
+                extra[(key >> 32, key & 0xffffffff)] = int(v)
+        return ascii_counts, extra
+    return count
+
+
+def count_pairs_sharded(data, group=None, device: Optional[torch.device] = None, hash_capacity: int = 1 << 20,
+                        counter: Optional[Callable] = None) -> Dict[Tuple[str, str], int]:
+    """`count_pairs` over a process group: every rank holds (or can read) the corpus, counts its line-aligned
+    byte range on its own GPU and the histograms are summed.  `counter(shard_bytes) -> (int64[16384] tensor,
+    {(cp_a, cp_b): n})` replaces the device kernel in the CPU (gloo) tests of this host logic."""
+    import torch.distributed as dist
+    arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    if counter is None:
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        counter = _device_counter(device, hash_capacity)
+    start, end = shard_byte_range(arr, rank, world)
+    ascii_counts, extra = counter(arr[start:end])
+    ascii_counts, extra = reduce_pair_counts(ascii_counts, extra, group)
+    out: Dict[Tuple[str, str], int] = {}
+    a = ascii_counts.cpu().numpy()
+    for k in np.nonzero(a)[0].tolist():
+        out[(chr(k >> 7), chr(k & 127))] = int(a[k])
+    for (ca, cb), v in extra.items():
+        out[(chr(ca), chr(cb))] = int(v)
     return out

@@ -18,7 +18,7 @@ import torch
 
 from .. import _lib
 from .._lib import SEM, check, ptr, stream_ptr
-from ..pair_count import count_pairs
+from ..pair_count import count_pairs, count_pairs_sharded
 from .hyperbolic_merge import HyperbolicTokenizer
 
 logger = logging.getLogger(__name__)
@@ -26,6 +26,11 @@ logger = logging.getLogger(__name__)
 
 class FrequencyAwareHyperbolicTokenizer(HyperbolicTokenizer):
     """reference frequency_aware_hyperbolic_merge.py:29-396."""
+
+    # Set on the class or an instance when every rank of an initialised torch.distributed group constructs the
+    # tokenizer over the SAME corpus: each rank then counts a line-aligned byte range and the histograms are summed
+    # (pair_count.count_pairs_sharded).  Off by default: replicas over different corpora must not be mixed.
+    shard_pair_counts = False
 
     def __init__(self, vocab: List[str], embeddings: torch.nn.Parameter, corpus_path: Optional[str] = None,
                  alpha: float = 0.4, beta: float = 0.4, gamma: float = 0.2, curvature: float = 1.0,
@@ -54,7 +59,8 @@ class FrequencyAwareHyperbolicTokenizer(HyperbolicTokenizer):
             self._merge_rules = {}          # what the first self.tokenize() call would have done (:425-428)
         with open(corpus_path, "rb") as f:
             data = f.read()
-        counts = count_pairs(data, self.device)
+        counts = (count_pairs_sharded(data, device=self.device) if self.shard_pair_counts
+                  else count_pairs(data, self.device))
         total = 0
         for pair, cnt in counts.items():
             self.pair_frequencies[pair] = self.pair_frequencies.get(pair, 0) + cnt

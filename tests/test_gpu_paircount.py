@@ -71,3 +71,44 @@ def test_large_ascii_vs_oracle():
     assert sum(got.values()) == total
     sample = lines[:20000]
     assert count_pairs(("\n".join(sample)).encode("ascii")) == count_pairs_py(sample)
+
+
+def test_sharded_single_process_equals_plain():
+    """Without a process group the sharded entry point is the plain one (one shard = the whole corpus)."""
+    from hyptokenizer_b200.pair_count import count_pairs, count_pairs_sharded
+    from hyptokenizer_b200.synth import synthetic_corpus
+    data = synthetic_corpus(4 << 20, seed=2)
+    assert count_pairs_sharded(data) == count_pairs(data)
+
+
+def _pc_nccl_worker(rank, world, port, out):
+    import socket  # noqa: F401
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from hyptokenizer_b200.pair_count import count_pairs_sharded
+    from hyptokenizer_b200.synth import synthetic_corpus
+    data = synthetic_corpus(32 << 20, seed=4)
+    got = count_pairs_sharded(data, device=torch.device("cuda", rank))
+    torch.save(got, f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(__import__("torch").cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_sharded_pair_count_nccl(tmp_path):
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    from hyptokenizer_b200.pair_count import count_pairs
+    from hyptokenizer_b200.synth import synthetic_corpus
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    world = min(torch.cuda.device_count(), 8)
+    out = str(tmp_path / "pc")
+    mp.spawn(_pc_nccl_worker, args=(world, port, out), nprocs=world, join=True)
+    want = count_pairs(synthetic_corpus(32 << 20, seed=4))
+    for rank in range(world):
+        assert torch.load(f"{out}.{rank}") == want

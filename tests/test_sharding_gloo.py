@@ -80,3 +80,67 @@ def test_shard_rows_cover():
                 assert covered == list(range(n))
             else:
                 assert sum(nr for _, nr in covered) == n
+
+
+# ---- pair counting over line-aligned byte shards -------------------------------------------------
+def _corpus_bytes():
+    import random
+    rng = random.Random(3)
+    words = ["".join(rng.choice("abcdefghij") for _ in range(rng.randint(1, 7))) for _ in range(60)]
+    words += ["héllo", "naïve", "日本語", "x y"]
+    lines = []
+    for k in range(400):
+        line = " ".join(rng.choice(words) for _ in range(rng.randint(0, 12)))
+        lines.append(("  " if k % 7 == 0 else "") + line + ("\t " if k % 5 == 0 else ""))
+    seps = ["\n", "\r\n", "\r"]
+    text = "".join(ln + seps[k % 3] for k, ln in enumerate(lines)) + "tail without newline"
+    return text.encode("utf-8")
+
+
+def _oracle_counter(shard):
+    from oracle.pair_count import count_pairs_c
+    counts = count_pairs_c(np.ascontiguousarray(shard)) if shard.size else {}
+    asc = torch.zeros(128 * 128, dtype=torch.int64)
+    extra = {}
+    for (a, b), v in counts.items():
+        if ord(a) < 128 and ord(b) < 128:
+            asc[ord(a) * 128 + ord(b)] = v
+        else:
+            extra[(ord(a), ord(b))] = v
+    return asc, extra
+
+
+def _pc_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hyptokenizer_b200.pair_count import count_pairs_sharded
+    got = count_pairs_sharded(_corpus_bytes(), counter=_oracle_counter)
+    torch.save(got, f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_pair_count_host_logic(tmp_path, world):
+    from oracle.pair_count import count_pairs_c
+    out = str(tmp_path / "pc")
+    mp.spawn(_pc_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    want = count_pairs_c(_corpus_bytes())
+    assert len(want) > 50 and any(ord(a) > 127 for a, _ in want)
+    for rank in range(world):
+        assert torch.load(f"{out}.{rank}") == want
+
+
+def test_shard_byte_ranges_are_line_aligned_and_cover():
+    from hyptokenizer_b200.pair_count import shard_byte_range
+    buf = np.frombuffer(_corpus_bytes(), dtype=np.uint8)
+    for world in (1, 2, 3, 8, 64, 5000):
+        cuts = [shard_byte_range(buf, r, world) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == buf.size
+        for (s0, e0), (s1, e1) in zip(cuts, cuts[1:]):
+            assert e0 == s1 and s0 <= e0
+        for s, e in cuts:
+            assert s == 0 or s == buf.size or buf[s - 1] == 0x0A
+    empty = np.zeros(0, dtype=np.uint8)
+    assert shard_byte_range(empty, 0, 2) == (0, 0) and shard_byte_range(empty, 1, 2) == (0, 0)
+    one_line = np.frombuffer(b"abcdef", dtype=np.uint8)
+    assert [shard_byte_range(one_line, r, 2) for r in range(2)] == [(0, 6), (6, 6)]
