@@ -61,6 +61,9 @@ _SIGNATURES = {
     "hyp_allpairs_topk": ([_p, _i64, _i64, _i64, _i64, _i32, _f, _i32, _i32, _p, _p, _p], C.c_int),
     "hyp_gram_topk_workspace_bytes": ([_i64, _i64, _i32], _i64),
     "hyp_gram_topk": ([_p, _i64, _i64, _i64, _i64, _i32, _f, _i32, _i32, _p, _p, _p, _p, _i64, _p], C.c_int),
+    "hyp_distance_backward": ([_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _f, _i32, _p], C.c_int),
+    "hyp_batch_distance_backward_coef": ([_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i32, _f, _i32, _p],
+                                         C.c_int),
     "hyp_merge_workspace_bytes": ([], _i64),
     "hyp_merge_state_init": ([_p, _p, _i32, _i32, C.c_double, _p], C.c_int),
     "hyp_merge_steps": ([_p, _i64, _p, _i32, _f, _i32, _p, _p, _i32, _i32, _i32, C.c_double, _i32, _p, _i64, _p],

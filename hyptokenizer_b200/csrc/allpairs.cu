@@ -20,7 +20,7 @@ namespace hyp {
 constexpr int TM = 64, TN = 64, TPAD = 68, NTHREADS = 256;
 constexpr int kMaxBlocks = 148 * 8;
 
-enum Mode { kDense = 0, kMin = 1, kEmit = 2 };
+enum Mode { kDense = 0, kMin = 1, kEmit = 2, kGradCoef = 3 };
 
 struct MinWorkspace {
   unsigned int ticket;
@@ -38,9 +38,11 @@ struct Params {
   int64_t n2;
   int D;
   float sqrt_c, sgn, thr;
-  // dense
+  // dense / grad-coef (out = W)
   float *out;
   int64_t ldo;
+  const float *gout;   // grad-coef: incoming gradient of the distance matrix
+  int64_t ldg;
   // min
   MinWorkspace *ws;
   hyp_best *best;
@@ -186,7 +188,20 @@ __global__ void __launch_bounds__(NTHREADS) allpairs_tile_kernel(const Params p)
         const float m = __fsub_rn(__fmul_rn(a0[4 * ty + r], b0[4 * tx + c]), S[r][c]);
         dist[c] = dist_from_mdot(m, p.sgn, p.sqrt_c);
       }
-      if (MODE == kDense) {
+      if (MODE == kGradCoef) {
+        // backward of the dense mode: W[i][j] = g[i][j] * d(distance)/d<x_i, y_j>; the caller turns W into the
+        // row gradients with two plain GEMMs (W @ Y', W^T @ X')
+        if (gi < p.n1) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int64_t gj = j0 + 4 * tx + c;
+            if (gj < p.n2) {
+              const float m = __fsub_rn(__fmul_rn(a0[4 * ty + r], b0[4 * tx + c]), S[r][c]);
+              p.out[gi * p.ldo + gj] = dist_grad_from_mdot(m, p.sgn, p.sqrt_c, p.gout[gi * p.ldg + gj]);
+            }
+          }
+        }
+      } else if (MODE == kDense) {
         if (gi < p.n1) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -443,6 +458,21 @@ extern "C" int hyp_batch_distance(const float *x, int64_t ldx, int64_t n1, const
   p.out = out;
   p.ldo = ldo;
   return launch_tiles<kDense>(p, (cudaStream_t)stream, "hyp_batch_distance");
+}
+
+extern "C" int hyp_batch_distance_backward_coef(const float *x, int64_t ldx, int64_t n1, const float *y, int64_t ldy,
+                                                int64_t n2, const float *grad_out, int64_t ldg, float *w,
+                                                int64_t ldw, int D, float c, int semantics, void *stream) {
+  Params p;
+  int rc = fill_params(p, x, ldx, n1, y, ldy, n2, D, c, semantics, 0);
+  if (rc) return rc;
+  if (n1 == 0 || n2 == 0) return HYP_OK;
+  if (!grad_out || !w) return HYP_ERR_ARG;
+  p.out = w;
+  p.ldo = ldw;
+  p.gout = grad_out;
+  p.ldg = ldg;
+  return launch_tiles<kGradCoef>(p, (cudaStream_t)stream, "hyp_batch_distance_backward_coef");
 }
 
 extern "C" int64_t hyp_allpairs_workspace_bytes(int64_t) { return (int64_t)sizeof(MinWorkspace); }

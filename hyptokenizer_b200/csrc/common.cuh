@@ -43,6 +43,18 @@ __device__ __forceinline__ float dist_from_mdot(float m, float sgn, float sqrt_c
   return __fdiv_rn(acosh_ge1(u), sqrt_c);
 }
 
+// d(distance)/d<x,y> times the incoming gradient g, as autograd derives it through
+// acosh(clamp(sgn*m, min=1.0f)) / sqrt(c): division first (g / sqrt_c), acosh' = rsqrt(u*u - 1), the clamp passes
+// the gradient where its input >= min (inclusive; NaN fails the test) and d(sgn*m)/dm = sgn.  u == 1 gives
+// g * inf exactly as torch does.
+__device__ __forceinline__ float dist_grad_from_mdot(float m, float sgn, float sqrt_c, float g) {
+  const float s = sgn < 0.f ? -m : m;
+  if (!(s >= 1.0f)) return 0.f;
+  const float r = __fdiv_rn(1.0f, __fsqrt_rn(__fsub_rn(__fmul_rn(s, s), 1.0f)));
+  const float gm = __fmul_rn(__fdiv_rn(g, sqrt_c), r);
+  return sgn < 0.f ? -gm : gm;
+}
+
 // ---------------------------------------------------------------------------------------------
 // ATen-order reductions, one WARP per vector (coalesced: lane t owns elements t, t+32, ...)
 //

@@ -32,6 +32,24 @@ distance_kernel(const float *__restrict__ x, int64_t ldx, const float *__restric
   }
 }
 
+// backward of distance_kernel: gx = w * (y0, -ys), gy = w * (x0, -xs), w = g * d(distance)/d<x,y>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+distance_bwd_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ y, int64_t ldy,
+                    const float *__restrict__ g, float *__restrict__ gx, float *__restrict__ gy, int64_t n, int D,
+                    float sqrt_c, float sgn) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = warp_global_id(); r < n; r += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const float *xr = x + r * ldx, *yr = y + r * ldy;
+    const float m = warp_mdot(xr, yr, D, lane);
+    const float w = dist_grad_from_mdot(m, sgn, sqrt_c, g[r]);
+    for (int k = lane; k < D; k += 32) {
+      const float wy = __fmul_rn(w, yr[k]), wx = __fmul_rn(w, xr[k]);
+      if (gx) gx[r * D + k] = k == 0 ? wy : -wy;
+      if (gy) gy[r * D + k] = k == 0 ? wx : -wx;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 rescore_kernel(const float *__restrict__ E, int64_t ldE, const int32_t *__restrict__ ii,
                const int32_t *__restrict__ jj, float *__restrict__ d_out, float *__restrict__ u_out,
@@ -137,6 +155,17 @@ extern "C" int hyp_distance(const float *x, int64_t ldx, const float *y, int64_t
   distance_kernel<<<grid_for(n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
       x, ldx, y, ldy, out, n, D, sqrtf(c), semantics == HYP_SEM_REFERENCE ? -1.f : 1.f);
   return check_launch("hyp_distance");
+}
+
+extern "C" int hyp_distance_backward(const float *x, int64_t ldx, const float *y, int64_t ldy, const float *grad_out,
+                                     float *grad_x, float *grad_y, int64_t n, int D, float c, int semantics,
+                                     void *stream) {
+  if (bad_dims(n, D)) return HYP_ERR_ARG;
+  if (n == 0) return HYP_OK;
+  if (!x || !y || !grad_out || (!grad_x && !grad_y)) return HYP_ERR_ARG;
+  distance_bwd_kernel<<<grid_for(n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      x, ldx, y, ldy, grad_out, grad_x, grad_y, n, D, sqrtf(c), semantics == HYP_SEM_REFERENCE ? -1.f : 1.f);
+  return check_launch("hyp_distance_backward");
 }
 
 extern "C" int hyp_rescore_pairs(const float *E, int64_t ldE, const int32_t *idx_i, const int32_t *idx_j,

@@ -2,8 +2,10 @@
 
 Same function names, argument order, broadcasting (`...` leading dims, last dim D = d+1)
 and return shapes as the reference; every function runs a hand-written sm_100a kernel
-through the C ABI (include/hyptok_b200.h).  CUDA fp32 tensors only -- no CPU fallback,
-no autograd (the merge loop never differentiates; multimodal losses are out of scope).
+through the C ABI (include/hyptok_b200.h).  CUDA fp32 tensors only -- no CPU fallback.
+`distance` and `batch_distance` are differentiable with respect to x and y (what the reference's
+multimodal losses need); the other functions return detached results (the merge
+loop never differentiates).
 
 `semantics` selects the arithmetic:
   "reference"  the shipped code, bit-faithful: distance == 0.0, log_map == NaN
@@ -117,19 +119,48 @@ def log_map(x: torch.Tensor, y: torch.Tensor, c: float = 1.0, semantics: Optiona
     return out.reshape(*bshape, D)
 
 
-def distance(x: torch.Tensor, y: torch.Tensor, c: float = 1.0, semantics: Optional[str] = None) -> torch.Tensor:
-    """reference embedding/lorentz_model.py:122-138."""
+def _distance_fwd(x: torch.Tensor, y: torch.Tensor, c: float, sem: int) -> torch.Tensor:
     dev, D, bshape, n, xr, ldx, yr, ldy = _pair(x, y)
     out = torch.empty(n, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.lib().hyp_distance(ptr(xr), ldx, ptr(yr), ldy, ptr(out), n, D, _curv(c), _sem(semantics),
-                                      stream_ptr()))
+        check(_lib.lib().hyp_distance(ptr(xr), ldx, ptr(yr), ldy, ptr(out), n, D, c, sem, stream_ptr()))
     return out.reshape(bshape)
 
 
-def batch_distance(x: torch.Tensor, y: torch.Tensor, c: float = 1.0, semantics: Optional[str] = None) -> torch.Tensor:
-    """reference embedding/lorentz_model.py:141-178: (n1, D) x (n2, D) -> (n1, n2), without the
-    (n1, n2, d) temporary."""
+class _Distance(torch.autograd.Function):
+    """distance with the gradient torch autograd derives for lorentz_model.py:122-138."""
+
+    @staticmethod
+    def forward(ctx, x, y, c, sem):
+        ctx.save_for_backward(x, y)
+        ctx.c, ctx.sem = c, sem
+        return _distance_fwd(x, y, c, sem)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        dev, D, bshape, n, xr, ldx, yr, ldy = _pair(x, y)
+        gr = g.detach().to(torch.float32).expand(bshape).reshape(-1).contiguous()
+        need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gx = torch.empty((n, D), dtype=torch.float32, device=dev) if need_x else None
+        gy = torch.empty((n, D), dtype=torch.float32, device=dev) if need_y else None
+        with torch.cuda.device(dev):
+            check(_lib.lib().hyp_distance_backward(ptr(xr), ldx, ptr(yr), ldy, ptr(gr), ptr(gx) if need_x else None,
+                                                   ptr(gy) if need_y else None, n, D, ctx.c, ctx.sem, stream_ptr()))
+        # rows that were broadcast receive the sum of their copies' gradients
+        gx = gx.reshape(*bshape, D).sum_to_size(x.shape) if need_x else None
+        gy = gy.reshape(*bshape, D).sum_to_size(y.shape) if need_y else None
+        return gx, gy, None, None
+
+
+def distance(x: torch.Tensor, y: torch.Tensor, c: float = 1.0, semantics: Optional[str] = None) -> torch.Tensor:
+    """reference embedding/lorentz_model.py:122-138.  Differentiable in x and y."""
+    if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad):
+        return _Distance.apply(x, y, _curv(c), _sem(semantics))
+    return _distance_fwd(x, y, _curv(c), _sem(semantics))
+
+
+def _batch_distance_fwd(x: torch.Tensor, y: torch.Tensor, c: float, sem: int) -> torch.Tensor:
     dev = require_cuda(x, y)
     _lib.check_device(dev)
     if x.dim() != 2 or y.dim() != 2 or x.shape[1] != y.shape[1]:
@@ -139,9 +170,45 @@ def batch_distance(x: torch.Tensor, y: torch.Tensor, c: float = 1.0, semantics: 
     n2 = yr.shape[0]
     out = torch.empty((n1, n2), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.lib().hyp_batch_distance(ptr(xr), D, n1, ptr(yr), D, n2, ptr(out), n2, D, _curv(c),
-                                            _sem(semantics), stream_ptr()))
+        check(_lib.lib().hyp_batch_distance(ptr(xr), D, n1, ptr(yr), D, n2, ptr(out), n2, D, c, sem, stream_ptr()))
     return out
+
+
+class _BatchDistance(torch.autograd.Function):
+    """batch_distance with autograd: W = g * d(dist)/d<x_i,y_j> from the tile kernel, then the row gradients are
+    two library GEMMs against the sign-flipped operands (d<x,y>/dx = (y0, -ys))."""
+
+    @staticmethod
+    def forward(ctx, x, y, c, sem):
+        ctx.save_for_backward(x, y)
+        ctx.c, ctx.sem = c, sem
+        return _batch_distance_fwd(x, y, c, sem)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        xr, yr = x.detach().contiguous(), y.detach().contiguous()
+        n1, D = xr.shape
+        n2 = yr.shape[0]
+        gr = g.detach().to(torch.float32).contiguous()
+        w = torch.empty((n1, n2), dtype=torch.float32, device=xr.device)
+        if n1 and n2:
+            with torch.cuda.device(xr.device):
+                check(_lib.lib().hyp_batch_distance_backward_coef(ptr(xr), D, n1, ptr(yr), D, n2, ptr(gr), n2, ptr(w), n2,
+                                                                  D, ctx.c, ctx.sem, stream_ptr()))
+        sig = torch.full((D,), -1.0, dtype=torch.float32, device=xr.device)
+        sig[0] = 1.0
+        gx = (w @ (yr * sig)) if ctx.needs_input_grad[0] else None
+        gy = (w.t() @ (xr * sig)) if ctx.needs_input_grad[1] else None
+        return gx, gy, None, None
+
+
+def batch_distance(x: torch.Tensor, y: torch.Tensor, c: float = 1.0, semantics: Optional[str] = None) -> torch.Tensor:
+    """reference embedding/lorentz_model.py:141-178: (n1, D) x (n2, D) -> (n1, n2), without the
+    (n1, n2, d) temporary.  Differentiable in x and y."""
+    if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad):
+        return _BatchDistance.apply(x, y, _curv(c), _sem(semantics))
+    return _batch_distance_fwd(x, y, _curv(c), _sem(semantics))
 
 
 def batch_distance_optimized(x: torch.Tensor, y: torch.Tensor, c: float = 1.0,

@@ -55,6 +55,13 @@ int hyp_minkowski_dot(const float *x, int64_t ldx, const float *y, int64_t ldy, 
 /* distance, lorentz_model.py:122-138: acosh(clamp(sgn*<x,y>, 1.0f)) / sqrt(c).  out[n] */
 int hyp_distance(const float *x, int64_t ldx, const float *y, int64_t ldy, float *out,
                  int64_t n, int D, float c, int semantics, void *stream);
+/* Backward of hyp_distance (what torch autograd derives for lorentz_model.py:122-138; used by
+ * multimodal/contrastive_loss.py:63-95 and by training loops that differentiate `distance`):
+ * grad_x[n][D], grad_y[n][D] (either may be NULL) from grad_out[n].  The clamp passes gradient where
+ * sgn*<x,y> >= 1 (inclusive), so the shipped semantics yields zeros, as the reference does. */
+int hyp_distance_backward(const float *x, int64_t ldx, const float *y, int64_t ldy,
+                          const float *grad_out, float *grad_x, float *grad_y, int64_t n, int D,
+                          float c, int semantics, void *stream);
 /* log_map, lorentz_model.py:96-119.  out[n][D] (ldo) */
 int hyp_log_map(const float *x, int64_t ldx, const float *y, int64_t ldy, float *out,
                 int64_t ldo, int64_t n, int D, int semantics, void *stream);
@@ -83,6 +90,14 @@ int hyp_rescore_pairs(const float *E, int64_t ldE, const int32_t *idx_i, const i
 int hyp_batch_distance(const float *x, int64_t ldx, int64_t n1, const float *y, int64_t ldy,
                        int64_t n2, float *out, int64_t ldo, int D, float c, int semantics,
                        void *stream);
+
+/* Backward of hyp_batch_distance, first half: w[n1][ldw] = grad_out[i][j] * d(distance)/d<x_i,y_j>
+ * (the B x B loop of multimodal/contrastive_loss.py:38-45 under autograd).  The row gradients are
+ * then two plain GEMMs, grad_x = w @ (y0, -ys), grad_y = w^T @ (x0, -xs). */
+int hyp_batch_distance_backward_coef(const float *x, int64_t ldx, int64_t n1, const float *y,
+                                     int64_t ldy, int64_t n2, const float *grad_out, int64_t ldg,
+                                     float *w, int64_t ldw, int D, float c, int semantics,
+                                     void *stream);
 
 /* Result record of the reductions below: the argmin over the key (d, i, j) -- what the
  * reference's stable sort on distance selects (hyperbolic_merge.py:378). i == -1: none. */
