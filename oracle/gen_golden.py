@@ -36,10 +36,11 @@ import embedding.lorentz_model as RL  # noqa: E402
 import tokenizer.hyperbolic_merge as RH  # noqa: E402
 import tokenizer.fast_hyperbolic_merge as RF  # noqa: E402
 import tokenizer.frequency_aware_hyperbolic_merge as RQ  # noqa: E402
+import tokenizer.hierarchical_hyperbolic_merge as RHI  # noqa: E402
 import tqdm as _tqdm  # noqa: E402
 
 # silence progress bars
-for _m in (RH, RF, RQ):
+for _m in (RH, RF, RQ, RHI):
     if hasattr(_m, "tqdm"):
         _m.tqdm = lambda it, **kw: _Quiet(it)
 
@@ -97,7 +98,7 @@ _PATCH = {"distance": _lz_distance, "batch_distance": _lz_batch_distance, "log_m
 def semantics(name: str):
     saved = []
     if name == "lorentz":
-        for mod in (RL, RH, RF, RQ):
+        for mod in (RL, RH, RF, RQ, RHI):
             for k, fn in _PATCH.items():
                 if hasattr(mod, k):
                     saved.append((mod, k, getattr(mod, k)))
@@ -371,7 +372,79 @@ def gen_trace_freq(tmpdir="/tmp"):
     dump("trace_freq.json", out)
 
 
-GENS = {"lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
+def hier_corpus_lines(n_lines=300, seed=5):
+    """Word-like text over a-z with a skewed word distribution, so that the hierarchical tokenizer's corpus
+    statistics (common words / common n-grams) are not degenerate."""
+    rng = random.Random(seed)
+    stems = ["the", "and", "ing", "tion", "er", "re", "un", "al", "ed", "in", "on", "at", "or", "st", "an",
+             "light", "house", "water", "stone", "green", "able", "ment", "ness", "play", "work", "read"]
+    words = stems + [a + b for a in stems[:12] for b in stems[12:]]
+    weights = [1.0 / (k + 1) for k in range(len(words))]
+    return [" ".join(rng.choices(words, weights=weights, k=rng.randint(3, 14))) for _ in range(n_lines)]
+
+
+def gen_trace_hier(tmpdir="/tmp"):
+    """HierarchicalHyperbolicTokenizer._hierarchical_merge_strategy (hierarchical_hyperbolic_merge.py:279-428) with
+    the three phase budgets shortened from 2000/5000/10000 to 25/30/30 steps (the ranges go through tqdm, which is
+    stubbed to truncate), so that all three phases, the threshold widening and both re-weighting filters run in
+    seconds.  NLTK is absent in this image: the corpus-statistics branches are the ones pinned."""
+    assert not RHI.NLTK_AVAILABLE
+    lines = hier_corpus_lines()
+    path = os.path.join(tmpdir, "hyp_golden_corpus3.txt")
+    with open(path, "w", encoding="utf-8") as f:
+        f.write("\n".join(lines) + "\n")
+    vocab = c1_vocab()
+    budgets = {2000: 25, 5000: 30, 10000: 30}
+    saved = _tqdm.tqdm
+    _tqdm.tqdm = lambda it=None, **kw: _Quiet(list(it)[:budgets.get(len(it), len(it))])
+    out = {"lines": lines, "vocab0": vocab, "d": 16, "phase_steps": [25, 30, 30], "runs": []}
+    try:
+        for sem, scale, target in (("reference", 0.3, None), ("lorentz", 0.3, None), ("lorentz", 0.02, 70)):
+            set_seeds(42)
+            emb = ref_init(len(vocab), 16, scale)
+            with semantics(sem):
+                tok = RHI.HierarchicalHyperbolicTokenizer(vocab, torch.nn.Parameter(emb.clone()), corpus_path=path,
+                                                          device=torch.device("cpu"), max_vocab_size=400)
+                rec = record_merges(tok)
+                thr_log = []
+                orig = tok._find_merge_candidates
+
+                def spy():
+                    c = orig()
+                    thr_log.append([len(c), tok.merge_threshold])
+                    return c
+
+                tok._find_merge_candidates = spy
+                tok.optimize_merges(hierarchical=True, target_vocab_size=target)
+            out["runs"].append({"semantics": sem, "scale": scale, "target": target, "init": bits(emb),
+                                "merges_ij": rec, "steps": thr_log, "final": tok_state(tok),
+                                "common_morphemes": sorted(tok.common_morphemes),
+                                "common_words": sorted(tok.common_words)})
+            print("hier", sem, scale, target, "merges", len(rec), "steps", len(thr_log), rec[:6], "thr", tok.merge_threshold)
+        # the string criteria on their own (they decide nothing in the collapsed traces above, where the repeated pair
+        # has distance 0): verdicts for a list of strings and both re-weighting filters on a fixed candidate list
+        probe_vocab = vocab + ["th", "he", "in", "ing", "tio", "wat", "er", "stone", "ligh", "t", "xq", "zzz", "andan", "re"]
+        emb = ref_init(len(probe_vocab), 16, 0.3)
+        tok = RHI.HierarchicalHyperbolicTokenizer(probe_vocab, torch.nn.Parameter(emb), corpus_path=path,
+                                                  device=torch.device("cpu"), max_vocab_size=400)
+        strings = sorted(set(probe_vocab[4:] + [a + b for a in probe_vocab[30:] for b in probe_vocab[30:]]))
+        rng = random.Random(9)
+        n = len(probe_vocab)
+        cands = [(i, j, rng.random()) for i in range(4, n) for j in range(i + 1, n) if rng.random() < 0.25]
+        out["criteria"] = {"vocab": probe_vocab, "strings": strings,
+                           "morpheme": [bool(tok._is_potential_morpheme(t)) for t in strings],
+                           "word": [bool(tok._is_valid_word(t)) for t in strings],
+                           "candidates": [[i, j, d] for i, j, d in cands],
+                           "morph_filtered": [[i, j, d] for i, j, d in tok._filter_morphologically_valid(cands)],
+                           "word_filtered": [[i, j, d] for i, j, d in tok._filter_word_valid(cands)]}
+        print("criteria:", sum(out["criteria"]["morpheme"]), "morphemes,", sum(out["criteria"]["word"]), "words of",
+              len(strings), "strings;", len(cands), "candidates")
+    finally:
+        _tqdm.tqdm = saved
+    dump("trace_hier.json", out)
+
+
+GENS = {"trace_hier": gen_trace_hier, "lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
         "trace_fast": gen_trace_fast, "pair_counts": gen_pair_counts, "trace_freq": gen_trace_freq}
 
 if __name__ == "__main__":
