@@ -30,6 +30,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <stdio.h>
+
 #include "common.cuh"
 
 namespace hyp {
@@ -43,7 +45,7 @@ constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_ACC = 4;           // accumulator buffers in TMEM (4 x 128 columns = all 512)
 constexpr int TC_EPI_WARPS = 8;    // 2 per TMEM lane quadrant: each handles one 64-column half of the tile
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr int TC_CAPH = 48;        // candidate capacity per row and column half
+constexpr int TC_CAPH = 128;       // candidate capacity per row and epilogue group
 constexpr int TC_CAP = 2 * TC_CAPH;
 
 // ---------------------------------------------------------------------------------------------
@@ -213,6 +215,8 @@ struct TcParams {
   int n_stages;       // depth of the B ring
   int n_ksteps;       // ceil(d / 8) MMAs per tile
   int debug;          // HYP_TC_DEBUG bit 0: epilogue skips TMEM loads + math, bit 1: no MMAs issued, bit 2: no TMA
+  int64_t n_ct;       // column tiles this pass visits: ct = t * ct_step, t in [0, n_ct)
+  int ct_step;        // 1 = every tile; pass 1 may sample (see hyp_gram_topk)
   float sgn;
   const float *x0;
   // pass 1
@@ -244,7 +248,6 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row_blocks = (p.nrows + TC_M - 1) / TC_M;
-  const int64_t col_tiles = (p.n + TC_N - 1) / TC_N;
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1);
@@ -277,7 +280,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         if (p.tail_row_bytes)
           tma_load_2d(&tmap_tail, a_full, sA + p.n_slabs * TC_SLAB_BYTES, tail_elem0, (int)(p.row0 + rb * TC_M));
         aphase ^= 1;
-        for (int64_t ct = 0; ct < col_tiles; ++ct) {
+        for (int64_t t = 0; t < p.n_ct; ++t) {
+          const int64_t ct = t * p.ct_step;
           mbar_wait(b_empty + bstage, bphase ^ 1);
           if (p.debug & 4) { mbar_arrive(b_full + bstage); if (++bstage == (uint32_t)p.n_stages) { bstage = 0; bphase ^= 1; } continue; }
           mbar_expect_tx(b_full + bstage, tile_tx);
@@ -314,7 +318,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       for (int64_t rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
         mbar_wait(a_full, aphase);
         aphase ^= 1;
-        for (int64_t ct = 0; ct < col_tiles; ++ct) {
+        for (int64_t t = 0; t < p.n_ct; ++t) {
           mbar_wait(b_full + bstage, bphase);
           mbar_wait(acc_empty + abuf, accphase ^ 1);
           tc_fence_after();
@@ -351,7 +355,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int r_in_block = lane_base + lane;         // row of the tile, also the thread's index in its group
     const float inf = __int_as_float(0x7f800000);
     const int64_t my_blocks = (row_blocks > blockIdx.x) ? (row_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total = my_blocks * col_tiles;
+    const int64_t total = my_blocks * p.n_ct;
     int64_t cur_rbi = -1, blk0 = 0, gi = 0;
     bool row_ok = false;
     float xs = 0.f, thr = 0.f;
@@ -359,12 +363,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     int32_t *my_cand = p.cand;
     float x0_next = 0.f;
     if (grp < total) {
-      const int64_t ct0 = grp % col_tiles;
+      const int64_t ct0 = (grp % p.n_ct) * p.ct_step;
       const int64_t gj0 = ct0 * TC_N + r_in_block;
       x0_next = gj0 < p.n ? __ldg(p.x0 + gj0) : 0.f;
     }
     for (int64_t T = grp; T < total; T += 2) {
-      const int64_t rbi = T / col_tiles, ct = T - rbi * col_tiles;
+      const int64_t rbi = T / p.n_ct, tix = T - rbi * p.n_ct, ct = tix * p.ct_step;
       if (rbi != cur_rbi) {
         if (PASS == 2 && cur_rbi >= 0 && row_ok) p.cand_cnt[(gi - p.row0) * 2 + grp] = cnt;
         cur_rbi = rbi;
@@ -382,7 +386,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       // time components of this tile's columns (fetched one tile of this group ahead)
       colx0[abuf * TC_N + r_in_block] = x0_next;
       if (T + 2 < total) {
-        const int64_t ctn = (T + 2) % col_tiles;
+        const int64_t ctn = ((T + 2) % p.n_ct) * p.ct_step;
         const int64_t gjn = ctn * TC_N + r_in_block;
         x0_next = gjn < p.n ? __ldg(p.x0 + gjn) : 0.f;
       }
@@ -454,7 +458,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + abuf);
-      if (PASS == 1 && row_ok) p.tilemin[ct * p.ld_tm + (gi - p.row0)] = fmaxf(tmin, 1.0f);
+      if (PASS == 1 && row_ok) p.tilemin[tix * p.ld_tm + (gi - p.row0)] = fmaxf(tmin, 1.0f);
     }
     if (PASS == 2 && cur_rbi >= 0 && row_ok) p.cand_cnt[(gi - p.row0) * 2 + grp] = cnt;
     // a group that saw no tile of a row block leaves its candidate count at the zero the host wrote
@@ -516,7 +520,7 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
     const int c0 = cand_cnt[2 * r], c1 = cand_cnt[2 * r + 1];
     const bool overflow = c0 > TC_CAPH || c1 > TC_CAPH || c0 < 0 || c1 < 0;
     const int m0 = overflow ? 0 : c0, m1 = overflow ? 0 : c1;
-    for (int q = lane; q < TC_CAP; q += 32) keys[w][q] = kEmpty;
+    for (int q = lane; q < m0 + m1; q += 32) keys[w][q] = kEmpty;
     __syncwarp();
     // exact re-score, four candidates per warp pass: a group of 8 lanes IS ATen's 8 summation lanes
     // (lane l owns elements 8k+l, partial k mod 4), so the order is reproduced with 4 registers per lane
@@ -524,30 +528,57 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
     const int N = D - 1, vs = N >> 3, full = vs >> 2;
     const int grp = lane >> 3, l8 = lane & 7;
     if (N >= 8) {
-      for (int q0 = 0; q0 < m0 + m1; q0 += 4) {
-        const int q = q0 + grp;
-        const bool live = q < m0 + m1;
-        const int qq = live ? q : 0;
-        const int j = qq < m0 ? cand[(2 * r) * TC_CAPH + qq] : cand[(2 * r + 1) * TC_CAPH + (qq - m0)];
-        const float *xj = E + (int64_t)j * ldE;
-        float part[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < 4 * full; ++k) {
-          const int e = 1 + 8 * k + l8;
-          part[k & 3] = __fadd_rn(part[k & 3], __fmul_rn(__ldg(xi + e), __ldg(xj + e)));
-        }
-        for (int k = 4 * full; k < vs; ++k) {
-          const int e = 1 + 8 * k + l8;
-          part[0] = __fadd_rn(part[0], __fmul_rn(__ldg(xi + e), __ldg(xj + e)));
-        }
-        const float Ll = __fadd_rn(__fadd_rn(__fadd_rn(part[0], part[1]), part[2]), part[3]);
-        float acc = 0.f;
-        for (int e = 8 * vs; e < N; ++e) acc = __fadd_rn(acc, __fmul_rn(__ldg(xi + 1 + e), __ldg(xj + 1 + e)));
+      // the query row's elements of this lane stay in registers for all candidates (up to 16 lane vectors: d <= 128)
+      constexpr int kInFlight = 2;   // 4 in flight was slower (128 registers, lower occupancy)
+      float xr[16];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, __shfl_sync(HYP_FULL_MASK, Ll, (lane & 24) + t));
-        if (live && l8 == 0) {
-          const float mm = __fsub_rn(__fmul_rn(__ldg(xi), __ldg(xj)), acc);
-          const float dv = dist_from_mdot(mm, sgn, sqrt_c);
-          if (dv == dv) keys[w][q] = ((unsigned long long)__float_as_uint(dv) << 32) | (unsigned int)j;
+      for (int kk = 0; kk < 16; ++kk) xr[kk] = kk < vs ? __ldg(xi + 1 + 8 * kk + l8) : 0.f;
+      const float xi0 = __ldg(xi);
+      for (int q0 = 0; q0 < m0 + m1; q0 += 4 * kInFlight) {
+        // kInFlight candidates per 8-lane group and pass: their loads are issued together
+        float Ll[kInFlight], tailv[kInFlight], xj0[kInFlight];
+        int jv[kInFlight];
+        bool livev[kInFlight];
+#pragma unroll
+        for (int h = 0; h < kInFlight; ++h) {
+          const int q = q0 + 4 * h + grp;
+          livev[h] = q < m0 + m1;
+          const int qq = livev[h] ? q : 0;
+          jv[h] = qq < m0 ? cand[(2 * r) * TC_CAPH + qq] : cand[(2 * r + 1) * TC_CAPH + (qq - m0)];
+        }
+        float yv[kInFlight][16];
+#pragma unroll
+        for (int h = 0; h < kInFlight; ++h) {
+          const float *xj = E + (int64_t)jv[h] * ldE;
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) yv[h][kk] = kk < vs ? __ldg(xj + 1 + 8 * kk + l8) : 0.f;
+          xj0[h] = __ldg(xj);
+        }
+#pragma unroll
+        for (int h = 0; h < kInFlight; ++h) {
+          const float *xj = E + (int64_t)jv[h] * ldE;
+          float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) {
+            if (kk < 4 * full) part[kk & 3] = __fadd_rn(part[kk & 3], __fmul_rn(xr[kk], yv[h][kk]));
+            else if (kk < vs) part[0] = __fadd_rn(part[0], __fmul_rn(xr[kk], yv[h][kk]));
+          }
+          Ll[h] = __fadd_rn(__fadd_rn(__fadd_rn(part[0], part[1]), part[2]), part[3]);
+          float acc = 0.f;
+          for (int e = 8 * vs; e < N; ++e) acc = __fadd_rn(acc, __fmul_rn(__ldg(xi + 1 + e), __ldg(xj + 1 + e)));
+          tailv[h] = acc;
+        }
+#pragma unroll
+        for (int h = 0; h < kInFlight; ++h) {
+          float acc = tailv[h];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, __shfl_sync(HYP_FULL_MASK, Ll[h], (lane & 24) + t));
+          if (livev[h] && l8 == 0) {
+            const float mm = __fsub_rn(__fmul_rn(xi0, xj0[h]), acc);
+            const float dv = dist_from_mdot(mm, sgn, sqrt_c);
+            if (dv == dv)
+              keys[w][q0 + 4 * h + grp] = ((unsigned long long)__float_as_uint(dv) << 32) | (unsigned int)jv[h];
+          }
         }
       }
     } else {
@@ -561,12 +592,13 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
       }
     }
     __syncwarp();
-    // rank sort of up to TC_CAP keys, all distinct (distinct j)
-    for (int q = lane; q < TC_CAP; q += 32) {
+    // rank sort of the m0 + m1 keys, all distinct (distinct j)
+    const int mtot = m0 + m1;
+    for (int q = lane; q < mtot; q += 32) {
       const unsigned long long mine = keys[w][q];
       if (mine == kEmpty) continue;
       int rank = 0;
-      for (int t = 0; t < TC_CAP; ++t) rank += keys[w][t] < mine;
+      for (int t = 0; t < mtot; ++t) rank += keys[w][t] < mine;
       if (rank < k) {
         out_idx[r * k + rank] = (int32_t)(mine & 0xffffffffu);
         out_d[r * k + rank] = __uint_as_float((unsigned int)(mine >> 32));
@@ -574,7 +606,7 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
     }
     // pad (fewer than k valid candidates can only happen with < k finite distances in the row)
     int valid = 0;
-    for (int t = lane; t < TC_CAP; t += 32) valid += keys[w][t] != kEmpty;
+    for (int t = lane; t < mtot; t += 32) valid += keys[w][t] != kEmpty;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(HYP_FULL_MASK, valid, o);
     for (int q = valid + lane; q < k; q += 32) {
@@ -698,11 +730,20 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
+  // HYP_TC_TIMING=1: per-stage device times on stderr (synchronises; for tuning only)
+  const bool timing = getenv("HYP_TC_TIMING") != nullptr;
+  cudaEvent_t tev[6];
+  if (timing) {
+    for (auto &e : tev) cudaEventCreate(&e);
+    cudaEventRecord(tev[0], st);
+  }
   cudaMemsetAsync(maxn, 0, 4, st);
   cudaMemsetAsync(cnt, 0, (size_t)nrows * 2 * sizeof(int32_t), st);
   tc_pack_kernel<<<sms * 4, 256, 0, st>>>(E, ldE, n, D, L.Kp, XP, x0, nrm, maxn);
   int rc = check_launch("hyp_gram_topk(pack)");
   if (rc) return rc;
+
+  if (timing) cudaEventRecord(tev[1], st);
 
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {(cuuint64_t)L.Kp, (cuuint64_t)n};
@@ -746,19 +787,44 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   const int64_t row_blocks = (nrows + TC_M - 1) / TC_M;
   const int grid = (int)(row_blocks < sms ? row_blocks : sms);
 
+  // Pass 1 only has to BOUND each row's k-th best from above, and the k-th smallest minimum over ANY >= k distinct
+  // column tiles does that: it visits every `step`-th tile.  The bound sits near rank k*step instead of k, so pass 2
+  // collects ~step times as many candidates for the exact re-score; step 3 is where the two costs balance at
+  // V=100k (HYP_TC_SUB overrides).  Small tables keep every tile (at least 4k sampled tiles are required).
+  int step = 3;
+  if (const char *e = getenv("HYP_TC_SUB")) step = atoi(e);
+  if (step < 1) step = 1;
+  while (step > 1 && (L.col_tiles + step - 1) / step < 4 * (int64_t)k) --step;
+  p.ct_step = step;
+  p.n_ct = (L.col_tiles + step - 1) / step;
   k1<<<grid, TC_THREADS, smem, st>>>(tmap, tmap_tail, p);
   rc = check_launch("hyp_gram_topk(pass 1)");
   if (rc) return rc;
-  kth_select_kernel<<<(int)((nrows + 127) / 128), 128, 0, st>>>(tilemin, L.ld_tm, L.col_tiles, nrows, row0, k, nrm, maxn,
+  if (timing) cudaEventRecord(tev[2], st);
+  kth_select_kernel<<<(int)((nrows + 127) / 128), 128, 0, st>>>(tilemin, L.ld_tm, p.n_ct, nrows, row0, k, nrm, maxn,
                                                                 thr);
   rc = check_launch("hyp_gram_topk(select)");
   if (rc) return rc;
+  if (timing) cudaEventRecord(tev[3], st);
+  p.ct_step = 1;
+  p.n_ct = L.col_tiles;
   k2<<<grid, TC_THREADS, smem, st>>>(tmap, tmap_tail, p);
   rc = check_launch("hyp_gram_topk(pass 2)");
   if (rc) return rc;
   int64_t fb = (nrows + 3) / 4;
   if (fb > sms * 16) fb = sms * 16;
+  if (timing) cudaEventRecord(tev[4], st);
   tc_finish_kernel<<<(int)fb, 128, 0, st>>>(E, ldE, D, row0, nrows, sqrtf(c), p.sgn, k, cand, cnt, out_idx, out_d,
                                            row_flags);
-  return check_launch("hyp_gram_topk(finish)");
+  rc = check_launch("hyp_gram_topk(finish)");
+  if (timing) {
+    cudaEventRecord(tev[5], st);
+    cudaEventSynchronize(tev[5]);
+    float ms[5];
+    for (int q = 0; q < 5; ++q) cudaEventElapsedTime(&ms[q], tev[q], tev[q + 1]);
+    fprintf(stderr, "[hyp_gram_topk] step=%d pack %.3f  pass1 %.3f  select %.3f  pass2 %.3f  finish %.3f ms\n", step, ms[0],
+            ms[1], ms[2], ms[3], ms[4]);
+    for (auto &e : tev) cudaEventDestroy(e);
+  }
+  return rc;
 }
