@@ -44,7 +44,7 @@ constexpr int TC_MAX_SLABS = 4;    // K padded up to 128
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_ACC = 4;           // accumulator buffers in TMEM (4 x 128 columns = all 512)
 constexpr int TC_EPI_WARPS = 8;    // 2 per TMEM lane quadrant: each handles one 64-column half of the tile
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS + 32;   // TMA, MMA issuer 0, 8 epilogue warps, MMA issuer 1
 constexpr int TC_CAPH = 128;       // candidate capacity per row and epilogue group
 constexpr int TC_CAP = 2 * TC_CAPH;
 
@@ -214,7 +214,8 @@ struct TcParams {
   int stage_bytes;    // bytes of one operand tile in shared memory (1024-aligned)
   int n_stages;       // depth of the B ring
   int n_ksteps;       // ceil(d / 8) MMAs per tile
-  int debug;          // HYP_TC_DEBUG bit 0: epilogue skips TMEM loads + math, bit 1: no MMAs issued, bit 2: no TMA
+  int debug;          // HYP_TC_DEBUG bit 0: epilogue skips TMEM loads + math, bit 1: no MMAs issued, bit 2: no TMA,
+                      //              bit 3: epilogue loads TMEM but skips the math
   int64_t n_ct;       // column tiles this pass visits: ct = t * ct_step, t in [0, n_ct)
   int ct_step;        // 1 = every tile; pass 1 may sample (see hyp_gram_topk)
   float sgn;
@@ -225,7 +226,7 @@ struct TcParams {
   // pass 2
   const float *thr;   // [nrows] tau + 2 eps
   int32_t *cand;      // [nrows][TC_CAP]
-  int32_t *cand_cnt;  // [nrows] (> TC_CAP == overflow)
+  int32_t *cand_cnt;  // [nrows][2]: the list as two halves of <= TC_CAPH entries (second > TC_CAPH == overflow)
 };
 
 template <int PASS, bool SGN_POS>
@@ -233,10 +234,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail,
                const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // layout: A tile | B stages | colx0[TC_ACC][128] | barriers | tmem ptr
+  // layout: A tile of row block 2rp | A tile of row block 2rp+1 | B stages | colx0[TC_ACC][128] | barriers | tmem ptr
+  // Two row blocks share every B tile: the kernel is bound by the L2 -> SM traffic of the B stream (ablation:
+  // TMA + barriers alone took 44 % of a pass, 6 TB/s), and this halves it.
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *sA = base;
-  uint8_t *sB = sA + p.stage_bytes;
+  uint8_t *sB = sA + 2 * (size_t)p.stage_bytes;
   float *colx0 = reinterpret_cast<float *>(sB + (size_t)p.n_stages * p.stage_bytes);
   uint64_t *bars = reinterpret_cast<uint64_t *>(colx0 + TC_ACC * TC_N);
   uint64_t *a_full = bars + 0, *a_empty = bars + 1;
@@ -248,17 +251,18 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row_blocks = (p.nrows + TC_M - 1) / TC_M;
+  const int64_t row_pairs = (row_blocks + 1) / 2;
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
+    mbar_init(a_empty, 2);                          // one commit per MMA issuer
     for (int s = 0; s < TC_ACC; ++s) {
       mbar_init(acc_full + s, 1);
       mbar_init(acc_empty + s, TC_EPI_WARPS / 2);   // one arrival per warp of the draining group
     }
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(b_full + s, 1);
-      mbar_init(b_empty + s, 1);
+      mbar_init(b_empty + s, 2);
     }
     fence_barrier_init();
   }
@@ -272,13 +276,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t bstage = 0, bphase = 0, aphase = 0;
-      for (int64_t rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
+      for (int64_t rp = blockIdx.x; rp < row_pairs; rp += gridDim.x) {
         mbar_wait(a_empty, aphase ^ 1);
-        mbar_expect_tx(a_full, tile_tx);
-        for (int s = 0; s < p.n_slabs; ++s)
-          tma_load_2d(&tmap, a_full, sA + s * TC_SLAB_BYTES, s * TC_KSLAB, (int)(p.row0 + rb * TC_M));
-        if (p.tail_row_bytes)
-          tma_load_2d(&tmap_tail, a_full, sA + p.n_slabs * TC_SLAB_BYTES, tail_elem0, (int)(p.row0 + rb * TC_M));
+        mbar_expect_tx(a_full, 2 * tile_tx);
+        for (int h = 0; h < 2; ++h) {
+          // (rows past the table are zero-filled by TMA; their results are never written)
+          uint8_t *dstA = sA + (size_t)h * p.stage_bytes;
+          const int arow = (int)(p.row0 + (2 * rp + h) * TC_M);
+          for (int s = 0; s < p.n_slabs; ++s) tma_load_2d(&tmap, a_full, dstA + s * TC_SLAB_BYTES, s * TC_KSLAB, arow);
+          if (p.tail_row_bytes) tma_load_2d(&tmap_tail, a_full, dstA + p.n_slabs * TC_SLAB_BYTES, tail_elem0, arow);
+        }
         aphase ^= 1;
         for (int64_t t = 0; t < p.n_ct; ++t) {
           const int64_t ct = t * p.ct_step;
@@ -294,8 +301,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (warp == 1 || warp == 2 + TC_EPI_WARPS) {
+    // ================= MMA issuers: warp 1 for row block 2rp, the last warp for row block 2rp + 1 =================
+    // A single thread issuing every tcgen05.mma ran at ~150 cycles per M128 x N128 x K8 instruction with TMA and
+    // the epilogue switched off (the tensor pipe needs 64): the issue path, not shared memory, was the limit.  The
+    // two row blocks of a pair have independent accumulators, so each gets its own issuing thread.
     // One thread issues every tcgen05.mma of the CTA, so its own instruction stream is the limit: the
     // descriptors of all k-steps are prepared once (low word = (address >> 4) + per-k-step offset, high word
     // constant per slab kind) and the tile loop only adds a base and issues.
@@ -312,81 +322,91 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         koff[ks] = (uint32_t)(((tail ? p.n_slabs : slab) * TC_SLAB_BYTES + within * 32) >> 4);
         khi[ks] = tail ? hitail : hi128;
       }
-      const uint32_t a_lo = ((smem_u32(sA) >> 4) & 0x3fff) | (1u << 16);
+      const int h = warp == 1 ? 0 : 1;
+      const uint32_t a_lo = ((smem_u32(sA + (size_t)h * p.stage_bytes) >> 4) & 0x3fff) | (1u << 16);
       const int nk = (p.debug & 2) ? 0 : p.n_ksteps;
-      uint32_t bstage = 0, bphase = 0, aphase = 0, abuf = 0, accphase = 0;
-      for (int64_t rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
+      uint32_t bstage = 0, bphase = 0, aphase = 0;
+      uint32_t tt = 0;                      // tiles issued by this CTA: accumulators 2*(tt&1)+h, use number tt>>1
+      for (int64_t rp = blockIdx.x; rp < row_pairs; rp += gridDim.x) {
         mbar_wait(a_full, aphase);
         aphase ^= 1;
-        for (int64_t t = 0; t < p.n_ct; ++t) {
+        for (int64_t t = 0; t < p.n_ct; ++t, ++tt) {
           mbar_wait(b_full + bstage, bphase);
-          mbar_wait(acc_empty + abuf, accphase ^ 1);
-          tc_fence_after();
           const uint32_t b_lo = ((smem_u32(sB + (size_t)bstage * p.stage_bytes) >> 4) & 0x3fff) | (1u << 16);
-          const uint32_t d_addr = tmem_base + abuf * TC_N;
+          {
+            const uint32_t abuf = 2 * (tt & 1) + h;
+            mbar_wait(acc_empty + abuf, ((tt >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_addr = tmem_base + abuf * TC_N;
 #pragma unroll
-          for (int ks = 0; ks < kMaxK; ++ks) {
-            if (ks < nk) {
-              const uint64_t ad = ((uint64_t)khi[ks] << 32) | (uint64_t)(a_lo + koff[ks]);
-              const uint64_t bd = ((uint64_t)khi[ks] << 32) | (uint64_t)(b_lo + koff[ks]);
-              umma_tf32(d_addr, ad, bd, kIdescTf32, ks > 0 ? 1u : 0u);
+            for (int ks = 0; ks < kMaxK; ++ks) {
+              if (ks < nk) {
+                const uint64_t ad = ((uint64_t)khi[ks] << 32) | (uint64_t)(a_lo + koff[ks]);
+                const uint64_t bd = ((uint64_t)khi[ks] << 32) | (uint64_t)(b_lo + koff[ks]);
+                umma_tf32(d_addr, ad, bd, kIdescTf32, ks > 0 ? 1u : 0u);
+              }
             }
+            umma_commit(acc_full + abuf);    // this row block's accumulator is ready for its epilogue group
           }
-          umma_commit(b_empty + bstage);     // B stage reusable once these MMAs have read it
-          umma_commit(acc_full + abuf);      // accumulator ready for the epilogue
+          umma_commit(b_empty + bstage);     // B stage reusable once both issuers' MMAs have read it
           if (++bstage == (uint32_t)p.n_stages) { bstage = 0; bphase ^= 1; }
-          if (++abuf == TC_ACC) { abuf = 0; accphase ^= 1; }
         }
-        umma_commit(a_empty);                // A tile reusable
+        umma_commit(a_empty);                // this issuer is done with its A tile
       }
     }
   } else {
     // ================= epilogue: warps 2..9 = two groups of four warps =================
-    // Group g drains the accumulator tiles with sequence number T = g (mod 2): two tiles are in flight, so the
-    // latency of one drain (barrier, TMEM loads, 256 FFMA/FMNMX per thread) overlaps the other's instead of
-    // stalling the MMA issuer.  Within a group, thread <-> accumulator row (TMEM lane), all 128 columns.
+    // Group h drains the accumulators of row block 2rp + h: both groups follow the same column tiles, so two
+    // accumulators per group are in flight and the latency of one drain (barrier, TMEM loads, 256 FFMA/FMNMX per
+    // thread) overlaps the MMAs of the next tile.  Within a group, thread <-> accumulator row (TMEM lane), all 128
+    // columns, and a row belongs to ONE thread for the whole pass (its candidate list is a single stream).
     // u' = sgn * (x0_i x0_j - S).  Pass 1 keeps min(u') per tile (fminf drops NaN operands, and
     // min_j max(u',1) == max(min_j u', 1), so the clamp is applied once per tile).  Pass 2 tests u' <= thr_i
     // (thr_i >= 1, so the clamped region always passes) into a 32-bit hit mask and only walks set bits.
     // Tiles that contain out-of-range columns or the row block's own diagonal take the checked path.
     const int quad = warp & 3;                       // TMEM lanes [32*quad, +32) are readable by this warp
-    const int grp = (warp - 2) >> 2;                 // which of the two tile streams
+    const int grp = (warp - 2) >> 2;                 // which row block of the pair
     const int lane_base = 32 * quad;
     const int r_in_block = lane_base + lane;         // row of the tile, also the thread's index in its group
     const float inf = __int_as_float(0x7f800000);
-    const int64_t my_blocks = (row_blocks > blockIdx.x) ? (row_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total = my_blocks * p.n_ct;
+    const int64_t my_pairs = (row_pairs > blockIdx.x) ? (row_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_pairs * p.n_ct;
     int64_t cur_rbi = -1, blk0 = 0, gi = 0;
     bool row_ok = false;
     float xs = 0.f, thr = 0.f;
     int cnt = 0;
     int32_t *my_cand = p.cand;
     float x0_next = 0.f;
-    if (grp < total) {
-      const int64_t ct0 = (grp % p.n_ct) * p.ct_step;
-      const int64_t gj0 = ct0 * TC_N + r_in_block;
+    auto flush_count = [&]() {
+      // the finish kernel reads a row's list as two halves of TC_CAPH entries (they are contiguous)
+      const int c0 = cnt < TC_CAPH ? cnt : TC_CAPH;
+      p.cand_cnt[(gi - p.row0) * 2] = c0;
+      p.cand_cnt[(gi - p.row0) * 2 + 1] = cnt - c0;        // > TC_CAPH  <=>  overflow
+    };
+    if (total > 0) {
+      const int64_t gj0 = (int64_t)r_in_block;             // first tile: ct = 0
       x0_next = gj0 < p.n ? __ldg(p.x0 + gj0) : 0.f;
     }
-    for (int64_t T = grp; T < total; T += 2) {
+    for (int64_t T = 0; T < total; ++T) {
       const int64_t rbi = T / p.n_ct, tix = T - rbi * p.n_ct, ct = tix * p.ct_step;
       if (rbi != cur_rbi) {
-        if (PASS == 2 && cur_rbi >= 0 && row_ok) p.cand_cnt[(gi - p.row0) * 2 + grp] = cnt;
+        if (PASS == 2 && cur_rbi >= 0 && row_ok) flush_count();
         cur_rbi = rbi;
-        blk0 = p.row0 + (blockIdx.x + rbi * gridDim.x) * TC_M;
+        blk0 = p.row0 + ((blockIdx.x + rbi * gridDim.x) * 2 + grp) * TC_M;
         gi = blk0 + r_in_block;
         row_ok = gi < p.row0 + p.nrows;
         const float x0i = row_ok ? __ldg(p.x0 + gi) : 0.f;
         xs = SGN_POS ? x0i : -x0i;
         if (PASS == 2) thr = row_ok ? __ldg(p.thr + (gi - p.row0)) : -1.f;
         cnt = 0;
-        my_cand = p.cand + ((gi - p.row0) * 2 + grp) * TC_CAPH;
+        my_cand = p.cand + (gi - p.row0) * TC_CAP;
       }
-      const uint32_t abuf = (uint32_t)(T & (TC_ACC - 1)), accphase = (uint32_t)((T / TC_ACC) & 1);
+      const uint32_t abuf = 2 * (uint32_t)(T & 1) + grp, accphase = (uint32_t)((T >> 1) & 1);
       const int64_t j0 = ct * TC_N;
       // time components of this tile's columns (fetched one tile of this group ahead)
       colx0[abuf * TC_N + r_in_block] = x0_next;
-      if (T + 2 < total) {
-        const int64_t ctn = ((T + 2) % p.n_ct) * p.ct_step;
+      if (T + 1 < total) {
+        const int64_t ctn = ((T + 1) % p.n_ct) * p.ct_step;
         const int64_t gjn = ctn * TC_N + r_in_block;
         x0_next = gjn < p.n ? __ldg(p.x0 + gjn) : 0.f;
       }
@@ -410,7 +430,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           for (int c = 0; c < 32; ++c) { v0[c] = 0.f; v1[c] = 0.f; }
         }
 #pragma unroll
-        for (int sub = 0; sub < ((p.debug & 1) ? 0 : 2); ++sub) {
+        for (int sub = 0; sub < ((p.debug & 9) ? 0 : 2); ++sub) {
           const int chunk = pairc * 2 + sub;
           const float (&v)[32] = sub == 0 ? v0 : v1;
           float cxc[32];                                   // 8 x LDS.128 (broadcast) instead of 32 scalar loads
@@ -447,7 +467,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               hits &= hits - 1;
               const int64_t gj = j0 + chunk * 32 + c;
               if (!checked || (gj < p.n && gj != gi)) {
-                if (cnt < TC_CAPH) my_cand[cnt] = (int32_t)gj;
+                if (cnt < TC_CAP) my_cand[cnt] = (int32_t)gj;
                 ++cnt;
               }
             }
@@ -460,8 +480,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       if (lane == 0) mbar_arrive(acc_empty + abuf);
       if (PASS == 1 && row_ok) p.tilemin[tix * p.ld_tm + (gi - p.row0)] = fmaxf(tmin, 1.0f);
     }
-    if (PASS == 2 && cur_rbi >= 0 && row_ok) p.cand_cnt[(gi - p.row0) * 2 + grp] = cnt;
-    // a group that saw no tile of a row block leaves its candidate count at the zero the host wrote
+    if (PASS == 2 && cur_rbi >= 0 && row_ok) flush_count();
   }
 
   tc_fence_before();
@@ -655,13 +674,13 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
   if (rem == 24) { L.n_slabs += 1; rem = 0; }   // 96-byte rows have no swizzle mode: take a full slab
   L.tail_row_bytes = rem * 4;
   L.stage_bytes = ((L.n_slabs * TC_SLAB_BYTES + TC_M * L.tail_row_bytes + 1023) / 1024) * 1024;
-  const int budget = 220 * 1024 - 4096;
-  L.n_stages = (budget - L.stage_bytes) / L.stage_bytes;
+  const int budget = 226 * 1024 - 4096;     // two A tiles + the B ring (+ 1 KB alignment, colx0, barriers)
+  L.n_stages = (budget - 2 * L.stage_bytes) / L.stage_bytes;
   if (L.n_stages > 2) L.n_stages = 2;      // measured: a deeper B ring does not help (the MMA issue rate and the
                                             // TMEM drain, not TMA latency, bound the tile loop); HYP_TC_STAGES overrides
   if (const char *e = getenv("HYP_TC_STAGES")) {
     const int want = atoi(e);
-    if (want >= 1 && want <= TC_MAX_STAGES && (1 + want) * L.stage_bytes <= budget) L.n_stages = want;
+    if (want >= 1 && want <= TC_MAX_STAGES && (2 + want) * L.stage_bytes <= budget) L.n_stages = want;
   }
   if (L.n_stages < 1) L.n_stages = 1;
   L.col_tiles = (n + TC_N - 1) / TC_N;
@@ -777,15 +796,15 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   p.debug = getenv("HYP_TC_DEBUG") ? atoi(getenv("HYP_TC_DEBUG")) : 0;
   p.sgn = semantics == HYP_SEM_REFERENCE ? -1.f : 1.f;
   p.x0 = x0; p.tilemin = tilemin; p.ld_tm = L.ld_tm; p.thr = thr; p.cand = cand; p.cand_cnt = cnt;
-  const size_t smem = 1024 + (size_t)(1 + L.n_stages) * L.stage_bytes + TC_ACC * TC_N * 4 +
+  const size_t smem = 1024 + (size_t)(2 + L.n_stages) * L.stage_bytes + TC_ACC * TC_N * 4 +
                       (4 + 2 * TC_ACC + 2 * TC_MAX_STAGES) * 8;
   const bool pos = p.sgn > 0.f;
   auto k1 = pos ? gram_tc_kernel<1, true> : gram_tc_kernel<1, false>;
   auto k2 = pos ? gram_tc_kernel<2, true> : gram_tc_kernel<2, false>;
   cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int64_t row_blocks = (nrows + TC_M - 1) / TC_M;
-  const int grid = (int)(row_blocks < sms ? row_blocks : sms);
+  const int64_t row_pairs = ((nrows + TC_M - 1) / TC_M + 1) / 2;
+  const int grid = (int)(row_pairs < sms ? row_pairs : sms);
 
   // Pass 1 only has to BOUND each row's k-th best from above, and the k-th smallest minimum over ANY >= k distinct
   // column tiles does that: it visits every `step`-th tile.  The bound sits near rank k*step instead of k, so pass 2
