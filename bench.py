@@ -426,9 +426,9 @@ def run_c3(a):
         shard_flops = 2.0 * nrows * V * D
         tf32_peak = pk.get("bf16_tflops", 1590.0) / 2.0               # TF32 dense = half the bf16 rate
         # hardware FLOPs of the tc engine: the collect pass visits every column tile, the bound pass every
-        # `step`-th (same rule as hyp_gram_topk: 3, fewer while that leaves under 4k sampled tiles)
+        # `step`-th (same rule as hyp_gram_topk: 2, fewer while that leaves under 4k sampled tiles)
         col_tiles = (V + 127) // 128
-        tc_step = max(1, int(os.environ.get("HYP_TC_SUB", "3")))
+        tc_step = max(1, int(os.environ.get("HYP_TC_SUB", "2")))
         while tc_step > 1 and (col_tiles + tc_step - 1) // tc_step < 4 * k:
             tc_step -= 1
         hw = 1.0 + 1.0 / tc_step
@@ -447,7 +447,7 @@ def run_c3(a):
                              "frac": (hw * shard_flops / kern_s / 1e12 if a.engine == "tc" else shard_flops / kern_s / 1e12) / tf32_peak,
                              "traffic": None, "peak_kind": kind + " bf16/2",
                              "note": "hardware FLOPs: the tc engine runs the Gram GEMM over every column tile once (collect pass) "
-                                     "and over every 3rd tile once more (bound pass); "
+                                     "and over every 2nd tile once more (bound pass); "
                                      "`value` counts the algorithmic 2*V^2*(d+1) once"},
                 "clocks": clocks}
         print(json.dumps(line))

@@ -387,8 +387,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const int64_t gj0 = (int64_t)r_in_block;             // first tile: ct = 0
       x0_next = gj0 < p.n ? __ldg(p.x0 + gj0) : 0.f;
     }
-    for (int64_t T = 0; T < total; ++T) {
-      const int64_t rbi = T / p.n_ct, tix = T - rbi * p.n_ct, ct = tix * p.ct_step;
+    // (tile counters are carried, not divided out of T: two 64-bit divisions per tile were as expensive as the math)
+    int64_t rbi = 0, tix = 0;
+    for (int64_t T = 0; T < total; ++T, ++tix) {
+      if (tix == p.n_ct) { tix = 0; ++rbi; }
+      const int64_t ct = tix * p.ct_step;
       if (rbi != cur_rbi) {
         if (PASS == 2 && cur_rbi >= 0 && row_ok) flush_count();
         cur_rbi = rbi;
@@ -406,7 +409,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       // time components of this tile's columns (fetched one tile of this group ahead)
       colx0[abuf * TC_N + r_in_block] = x0_next;
       if (T + 1 < total) {
-        const int64_t ctn = ((T + 1) % p.n_ct) * p.ct_step;
+        const int64_t ctn = (tix + 1 == p.n_ct ? 0 : tix + 1) * p.ct_step;
         const int64_t gjn = ctn * TC_N + r_in_block;
         x0_next = gjn < p.n ? __ldg(p.x0 + gjn) : 0.f;
       }
@@ -417,61 +420,70 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const float *cx = colx0 + abuf * TC_N;
       float tmin = inf;
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + abuf * TC_N;
-#pragma unroll 1
-      for (int pairc = 0; pairc < 2; ++pairc) {
-        // two 32-column chunks are requested before the first is consumed
-        float v0[32], v1[32];
-        if (!(p.debug & 1)) {
-          tmem_ld32_nowait(taddr + pairc * 64, v0);
-          tmem_ld32_nowait(taddr + pairc * 64 + 32, v1);
-          tmem_ld_wait();
-        } else {
+      // One 32-column chunk of the tile: u' for the thread's row, then the pass's consumer.
+      auto consume = [&](int chunk, const float (&v)[32]) {
+        float cxc[32];                                   // 8 x LDS.128 (broadcast) instead of 32 scalar loads
 #pragma unroll
-          for (int c = 0; c < 32; ++c) { v0[c] = 0.f; v1[c] = 0.f; }
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 t4 = reinterpret_cast<const float4 *>(cx + chunk * 32)[c4];
+          cxc[4 * c4 + 0] = t4.x; cxc[4 * c4 + 1] = t4.y; cxc[4 * c4 + 2] = t4.z; cxc[4 * c4 + 3] = t4.w;
         }
+        if (PASS == 1) {
+          if (!checked) {
+            float m4[4] = {inf, inf, inf, inf};      // four independent min chains
 #pragma unroll
-        for (int sub = 0; sub < ((p.debug & 9) ? 0 : 2); ++sub) {
-          const int chunk = pairc * 2 + sub;
-          const float (&v)[32] = sub == 0 ? v0 : v1;
-          float cxc[32];                                   // 8 x LDS.128 (broadcast) instead of 32 scalar loads
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 t4 = reinterpret_cast<const float4 *>(cx + chunk * 32)[c4];
-            cxc[4 * c4 + 0] = t4.x; cxc[4 * c4 + 1] = t4.y; cxc[4 * c4 + 2] = t4.z; cxc[4 * c4 + 3] = t4.w;
-          }
-          if (PASS == 1) {
-            if (!checked) {
-              float m4[4] = {inf, inf, inf, inf};      // four independent min chains
-#pragma unroll
-              for (int c = 0; c < 32; ++c)
-                m4[c & 3] = fminf(m4[c & 3], SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]));
-              tmin = fminf(tmin, fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])));
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const int64_t gj = j0 + chunk * 32 + c;
-                const float u = SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]);
-                if (gj < p.n && gj != gi) tmin = fminf(tmin, u);
-              }
-            }
+            for (int c = 0; c < 32; ++c)
+              m4[c & 3] = fminf(m4[c & 3], SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]));
+            tmin = fminf(tmin, fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])));
           } else {
-            uint32_t h4[4] = {0u, 0u, 0u, 0u};            // four independent OR chains
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              const float u = SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]);
-              h4[c & 3] |= (u <= thr ? 1u : 0u) << c;
-            }
-            uint32_t hits = (h4[0] | h4[1]) | (h4[2] | h4[3]);
-            while (hits) {
-              const int c = __ffs(hits) - 1;
-              hits &= hits - 1;
               const int64_t gj = j0 + chunk * 32 + c;
-              if (!checked || (gj < p.n && gj != gi)) {
-                if (cnt < TC_CAP) my_cand[cnt] = (int32_t)gj;
-                ++cnt;
-              }
+              const float u = SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]);
+              if (gj < p.n && gj != gi) tmin = fminf(tmin, u);
             }
           }
+        } else {
+          // hit mask: FSETP + SEL of an immediate bit per column, summed (disjoint bits) in a tree
+          uint32_t bit[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float u = SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]);
+            bit[c] = u <= thr ? (1u << c) : 0u;
+          }
+#pragma unroll
+          for (int w = 16; w >= 1; w >>= 1)
+#pragma unroll
+            for (int c = 0; c < w; ++c) bit[c] |= bit[c + w];
+          uint32_t hits = bit[0];
+          while (hits) {
+            const int c = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int64_t gj = j0 + chunk * 32 + c;
+            if (!checked || (gj < p.n && gj != gi)) {
+              if (cnt < TC_CAP) my_cand[cnt] = (int32_t)gj;
+              ++cnt;
+            }
+          }
+        }
+      };
+      {
+        // Three register buffers rotate over the four chunks so that only the first TMEM round trip of a tile is
+        // exposed: chunks 2 and 3 are requested while chunks 0 and 1 are consumed.  (Consumers start with loads
+        // from shared memory, which cannot move above the waits' memory clobber.)
+        float va[32], vb[32], vc[32];
+        const bool skip_math = (p.debug & 9) != 0;
+        if (!(p.debug & 1)) {
+          tmem_ld32_nowait(taddr, va);
+          tmem_ld32_nowait(taddr + 32, vb);
+          tmem_ld_wait();
+          tmem_ld32_nowait(taddr + 64, vc);
+          if (!skip_math) consume(0, va);
+          tmem_ld32_nowait(taddr + 96, va);
+          if (!skip_math) consume(1, vb);
+          tmem_ld_wait();
+          if (!skip_math) consume(2, vc);
+          if (!skip_math) consume(3, va);
         }
       }
       // release the accumulator buffer
@@ -808,9 +820,9 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
 
   // Pass 1 only has to BOUND each row's k-th best from above, and the k-th smallest minimum over ANY >= k distinct
   // column tiles does that: it visits every `step`-th tile.  The bound sits near rank k*step instead of k, so pass 2
-  // collects ~step times as many candidates for the exact re-score; step 3 is where the two costs balance at
-  // V=100k (HYP_TC_SUB overrides).  Small tables keep every tile (at least 4k sampled tiles are required).
-  int step = 3;
+  // collects ~step times as many candidates for the exact re-score; the two costs balance at step 2-3 at V=100k
+  // (7.4 / 7.5 ms; HYP_TC_SUB overrides).  Small tables keep every tile (at least 4k sampled tiles are required).
+  int step = 2;
   if (const char *e = getenv("HYP_TC_SUB")) step = atoi(e);
   if (step < 1) step = 1;
   while (step > 1 && (L.col_tiles + step - 1) / step < 4 * (int64_t)k) --step;
