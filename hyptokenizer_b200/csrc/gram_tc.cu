@@ -158,6 +158,13 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32])
 #pragma unroll
   for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
 }
+// 16-byte load from shared memory by 32-bit shared address.  (A float4 load through a generic pointer that has passed
+// through a lambda compiles to LD.E.128, a generic load: slower, and it shows up as long-scoreboard stalls.)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+  return r;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 in
@@ -417,7 +424,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       mbar_wait(acc_full + abuf, accphase);
       tc_fence_after();
       const bool checked = (j0 + TC_N > p.n) || (j0 < blk0 + TC_M && j0 + TC_N > blk0);
-      const float *cx = colx0 + abuf * TC_N;
+      const uint32_t cx_s = smem_u32(colx0 + abuf * TC_N);
       float tmin = inf;
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + abuf * TC_N;
       // One 32-column chunk of the tile: u' for the thread's row, then the pass's consumer.
@@ -425,7 +432,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         float cxc[32];                                   // 8 x LDS.128 (broadcast) instead of 32 scalar loads
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 t4 = reinterpret_cast<const float4 *>(cx + chunk * 32)[c4];
+          const float4 t4 = lds128(cx_s + (uint32_t)(chunk * 32 + 4 * c4) * 4u);
           cxc[4 * c4 + 0] = t4.x; cxc[4 * c4 + 1] = t4.y; cxc[4 * c4 + 2] = t4.z; cxc[4 * c4 + 3] = t4.w;
         }
         if (PASS == 1) {
