@@ -304,8 +304,10 @@ allpairs_topk_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int64_
   float *a0 = Bs + (size_t)d * TPAD;
   float *b0 = a0 + TM;
   float *dist = b0 + TN;                                        // [64][65]
-  unsigned long long *lists = reinterpret_cast<unsigned long long *>(dist + TM * (TN + 1) + 1);  // [64][k]
-  lists = reinterpret_cast<unsigned long long *>(((uintptr_t)lists + 7) & ~(uintptr_t)7);
+  // [64][k] keys, 8-byte aligned.  The offset is rounded in floats, not through an integer cast of the pointer: a
+  // pointer that has been through uintptr_t loses its shared address space and every access becomes a generic LD/ST.
+  const size_t lists_off = ((size_t)(2 * d) * TPAD + TM + TN + (size_t)TM * (TN + 1) + 1) & ~(size_t)1;
+  unsigned long long *lists = reinterpret_cast<unsigned long long *>(smem + lists_off);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int64_t col_tiles = (n + TN - 1) / TN;
   const int64_t row_tiles = (nrows + TM - 1) / TM;
