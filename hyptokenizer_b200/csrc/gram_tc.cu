@@ -166,6 +166,13 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return r;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld writes its destination registers asynchronously; the compiler only knows that the asm statement "wrote"
+// them, so nothing stops it from scheduling their use before the wait.  This empty asm makes the values "change" at a
+// point behind the wait (volatile asms keep their order), which pins every use after it.
+__device__ __forceinline__ void tmem_pin(float (&v)[32]) {
+  asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]));
+  asm volatile("" : "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31]));
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 in
 // [0,14), LBO >> 4 in [16,30) (unused for swizzled K-major, 1), SBO >> 4 in [32,46) = 1024 B between
@@ -185,26 +192,46 @@ constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)
                                 ((uint32_t)(TC_M >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------
-// operand preparation: XP[r][0..Kp) = spatial part zero-padded, x0[r], nrm[r], max norm
+// operand preparation.  The signed Minkowski product rides INSIDE the MMA, time-like term included:
+//   XA[r] = [ xs_0 .. xs_{d-1},  hi,  lo,  hi,  lo, 0.. ]      x0 = hi + lo, hi = x0 cut to TF32's 10 mantissa bits
+//   XB[r] = [-s xs_0 .. -s xs_{d-1}, s hi, s hi, s lo, s lo, 0.. ]                       s = sgn (+1 lorentz, -1 reference)
+// so that  XA[i] . XB[j] = s (x0_i x0_j - xs_i . xs_j) = u'  directly.  hi x hi is exact in the tensor core (10-bit
+// operands, fp32 accumulate), the three cross terms carry |lo| <= 2^-10 x0 rounded to TF32: ~2^-19 x0_i x0_j in
+// total, inside the fp32 slack of the bound.  (One TF32 slot for x0 would cost 2^-11 x0_i x0_j ~ 5e-4, far more than
+// the spread of u' near the k-th neighbour: SURVEY 7.)  d = 100 uses the four pad columns of K = 104: no extra
+// MMA, and the epilogue needs neither the column time components nor an FMA per element.
+// Also nrm[r] = |xs_r| and its maximum, for the error bound.
 // ---------------------------------------------------------------------------------------------
-__global__ void tc_pack_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int D, int Kp,
-                               float *__restrict__ XP, float *__restrict__ x0, float *__restrict__ nrm,
+__global__ void tc_pack_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int D, int Kp, float sgn,
+                               float *__restrict__ XA, float *__restrict__ XB, float *__restrict__ nrm,
                                unsigned int *__restrict__ max_nrm_bits) {
   const int lane = threadIdx.x & 31;
+  const int d = D - 1;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t r = warp; r < n; r += nwarps) {
     const float *row = E + r * ldE;
+    const float x0 = row[0];
+    const float hi = __uint_as_float(__float_as_uint(x0) & 0xffffe000u);
+    const float lo = x0 - hi;                      // exact; NaN / inf propagate into the accumulator as they should
     float ss = 0.f;
     for (int k = lane; k < Kp; k += 32) {
-      float v = (k < D - 1) ? row[1 + k] : 0.f;
-      XP[r * Kp + k] = v;
-      ss = fmaf(v, v, ss);
+      float a = 0.f, b = 0.f;
+      if (k < d) {
+        a = row[1 + k];
+        b = -sgn * a;
+        ss = fmaf(a, a, ss);
+      } else if (k < d + 4) {
+        const int t = k - d;
+        a = (t & 1) ? lo : hi;                     // hi, lo, hi, lo
+        b = sgn * (t < 2 ? hi : lo);               // hi, hi, lo, lo
+      }
+      XA[r * Kp + k] = a;
+      XB[r * Kp + k] = b;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(HYP_FULL_MASK, ss, o);
     if (lane == 0) {
-      x0[r] = row[0];
       float nr = sqrtf(ss);
       nrm[r] = nr;
       if (nr == nr) atomicMax(max_nrm_bits, __float_as_uint(nr));
@@ -225,8 +252,6 @@ struct TcParams {
                       //              bit 3: epilogue loads TMEM but skips the math
   int64_t n_ct;       // column tiles this pass visits: ct = t * ct_step, t in [0, n_ct)
   int ct_step;        // 1 = every tile; pass 1 may sample (see hyp_gram_topk)
-  float sgn;
-  const float *x0;
   // pass 1
   float *tilemin;     // [col_tiles][ld_tm]
   int64_t ld_tm;
@@ -236,19 +261,19 @@ struct TcParams {
   int32_t *cand_cnt;  // [nrows][2]: the list as two halves of <= TC_CAPH entries (second > TC_CAPH == overflow)
 };
 
-template <int PASS, bool SGN_POS>
+template <int PASS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail,
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapA_tail,
+               const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapB_tail,
                const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // layout: A tile of row block 2rp | A tile of row block 2rp+1 | B stages | colx0[TC_ACC][128] | barriers | tmem ptr
+  // layout: A tile of row block 2rp | A tile of row block 2rp+1 | B stages | barriers | tmem ptr
   // Two row blocks share every B tile: the kernel is bound by the L2 -> SM traffic of the B stream (ablation:
   // TMA + barriers alone took 44 % of a pass, 6 TB/s), and this halves it.
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *sA = base;
   uint8_t *sB = sA + 2 * (size_t)p.stage_bytes;
-  float *colx0 = reinterpret_cast<float *>(sB + (size_t)p.n_stages * p.stage_bytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(colx0 + TC_ACC * TC_N);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)p.n_stages * p.stage_bytes);
   uint64_t *a_full = bars + 0, *a_empty = bars + 1;
   uint64_t *acc_full = bars + 2, *acc_empty = bars + 2 + TC_ACC;                        // [TC_ACC] each
   uint64_t *b_full = bars + 2 + 2 * TC_ACC, *b_empty = bars + 2 + 2 * TC_ACC + TC_MAX_STAGES;   // [n_stages] each
@@ -290,8 +315,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           // (rows past the table are zero-filled by TMA; their results are never written)
           uint8_t *dstA = sA + (size_t)h * p.stage_bytes;
           const int arow = (int)(p.row0 + (2 * rp + h) * TC_M);
-          for (int s = 0; s < p.n_slabs; ++s) tma_load_2d(&tmap, a_full, dstA + s * TC_SLAB_BYTES, s * TC_KSLAB, arow);
-          if (p.tail_row_bytes) tma_load_2d(&tmap_tail, a_full, dstA + p.n_slabs * TC_SLAB_BYTES, tail_elem0, arow);
+          for (int s = 0; s < p.n_slabs; ++s) tma_load_2d(&tmapA, a_full, dstA + s * TC_SLAB_BYTES, s * TC_KSLAB, arow);
+          if (p.tail_row_bytes) tma_load_2d(&tmapA_tail, a_full, dstA + p.n_slabs * TC_SLAB_BYTES, tail_elem0, arow);
         }
         aphase ^= 1;
         for (int64_t t = 0; t < p.n_ct; ++t) {
@@ -301,9 +326,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           mbar_expect_tx(b_full + bstage, tile_tx);
           uint8_t *dst = sB + (size_t)bstage * p.stage_bytes;
           for (int s = 0; s < p.n_slabs; ++s)
-            tma_load_2d(&tmap, b_full + bstage, dst + s * TC_SLAB_BYTES, s * TC_KSLAB, (int)(ct * TC_N));
+            tma_load_2d(&tmapB, b_full + bstage, dst + s * TC_SLAB_BYTES, s * TC_KSLAB, (int)(ct * TC_N));
           if (p.tail_row_bytes)
-            tma_load_2d(&tmap_tail, b_full + bstage, dst + p.n_slabs * TC_SLAB_BYTES, tail_elem0, (int)(ct * TC_N));
+            tma_load_2d(&tmapB_tail, b_full + bstage, dst + p.n_slabs * TC_SLAB_BYTES, tail_elem0, (int)(ct * TC_N));
           if (++bstage == (uint32_t)p.n_stages) { bstage = 0; bphase ^= 1; }
         }
       }
@@ -364,36 +389,31 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   } else {
     // ================= epilogue: warps 2..9 = two groups of four warps =================
     // Group h drains the accumulators of row block 2rp + h: both groups follow the same column tiles, so two
-    // accumulators per group are in flight and the latency of one drain (barrier, TMEM loads, 256 FFMA/FMNMX per
-    // thread) overlaps the MMAs of the next tile.  Within a group, thread <-> accumulator row (TMEM lane), all 128
-    // columns, and a row belongs to ONE thread for the whole pass (its candidate list is a single stream).
-    // u' = sgn * (x0_i x0_j - S).  Pass 1 keeps min(u') per tile (fminf drops NaN operands, and
-    // min_j max(u',1) == max(min_j u', 1), so the clamp is applied once per tile).  Pass 2 tests u' <= thr_i
-    // (thr_i >= 1, so the clamped region always passes) into a 32-bit hit mask and only walks set bits.
-    // Tiles that contain out-of-range columns or the row block's own diagonal take the checked path.
+    // accumulators per group are in flight and one drain overlaps the MMAs of the next tile.  Within a group,
+    // thread <-> accumulator row (TMEM lane), all 128 columns, and a row belongs to ONE thread for the whole pass
+    // (its candidate list is a single stream).  The accumulator IS u' (see tc_pack_kernel): pass 1 keeps min(u') per
+    // tile (fminf drops NaN operands, and min_j max(u',1) == max(min_j u', 1), so the clamp is applied once per tile);
+    // pass 2 tests u' <= thr_i (thr_i >= 1, so the clamped region always passes) into a 32-bit hit mask and only
+    // walks set bits.  Tiles that contain out-of-range columns (zero rows: u' = 0) or the row block's own diagonal
+    // take the checked path.
     const int quad = warp & 3;                       // TMEM lanes [32*quad, +32) are readable by this warp
     const int grp = (warp - 2) >> 2;                 // which row block of the pair
     const int lane_base = 32 * quad;
-    const int r_in_block = lane_base + lane;         // row of the tile, also the thread's index in its group
+    const int r_in_block = lane_base + lane;         // row of the tile
     const float inf = __int_as_float(0x7f800000);
     const int64_t my_pairs = (row_pairs > blockIdx.x) ? (row_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total = my_pairs * p.n_ct;
     int64_t cur_rbi = -1, blk0 = 0, gi = 0;
     bool row_ok = false;
-    float xs = 0.f, thr = 0.f;
+    float thr = 0.f;
     int cnt = 0;
     int32_t *my_cand = p.cand;
-    float x0_next = 0.f;
     auto flush_count = [&]() {
       // the finish kernel reads a row's list as two halves of TC_CAPH entries (they are contiguous)
       const int c0 = cnt < TC_CAPH ? cnt : TC_CAPH;
       p.cand_cnt[(gi - p.row0) * 2] = c0;
       p.cand_cnt[(gi - p.row0) * 2 + 1] = cnt - c0;        // > TC_CAPH  <=>  overflow
     };
-    if (total > 0) {
-      const int64_t gj0 = (int64_t)r_in_block;             // first tile: ct = 0
-      x0_next = gj0 < p.n ? __ldg(p.x0 + gj0) : 0.f;
-    }
     // (tile counters are carried, not divided out of T: two 64-bit divisions per tile were as expensive as the math)
     int64_t rbi = 0, tix = 0;
     for (int64_t T = 0; T < total; ++T, ++tix) {
@@ -405,59 +425,37 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         blk0 = p.row0 + ((blockIdx.x + rbi * gridDim.x) * 2 + grp) * TC_M;
         gi = blk0 + r_in_block;
         row_ok = gi < p.row0 + p.nrows;
-        const float x0i = row_ok ? __ldg(p.x0 + gi) : 0.f;
-        xs = SGN_POS ? x0i : -x0i;
-        if (PASS == 2) thr = row_ok ? __ldg(p.thr + (gi - p.row0)) : -1.f;
+        if (PASS == 2) thr = row_ok ? __ldg(p.thr + (gi - p.row0)) : -inf;
         cnt = 0;
         my_cand = p.cand + (gi - p.row0) * TC_CAP;
       }
       const uint32_t abuf = 2 * (uint32_t)(T & 1) + grp, accphase = (uint32_t)((T >> 1) & 1);
       const int64_t j0 = ct * TC_N;
-      // time components of this tile's columns (fetched one tile of this group ahead)
-      colx0[abuf * TC_N + r_in_block] = x0_next;
-      if (T + 1 < total) {
-        const int64_t ctn = (tix + 1 == p.n_ct ? 0 : tix + 1) * p.ct_step;
-        const int64_t gjn = ctn * TC_N + r_in_block;
-        x0_next = gjn < p.n ? __ldg(p.x0 + gjn) : 0.f;
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       mbar_wait(acc_full + abuf, accphase);
       tc_fence_after();
       const bool checked = (j0 + TC_N > p.n) || (j0 < blk0 + TC_M && j0 + TC_N > blk0);
-      const uint32_t cx_s = smem_u32(colx0 + abuf * TC_N);
       float tmin = inf;
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + abuf * TC_N;
-      // One 32-column chunk of the tile: u' for the thread's row, then the pass's consumer.
+      // One 32-column chunk of the tile.
       auto consume = [&](int chunk, const float (&v)[32]) {
-        float cxc[32];                                   // 8 x LDS.128 (broadcast) instead of 32 scalar loads
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 t4 = lds128(cx_s + (uint32_t)(chunk * 32 + 4 * c4) * 4u);
-          cxc[4 * c4 + 0] = t4.x; cxc[4 * c4 + 1] = t4.y; cxc[4 * c4 + 2] = t4.z; cxc[4 * c4 + 3] = t4.w;
-        }
         if (PASS == 1) {
           if (!checked) {
             float m4[4] = {inf, inf, inf, inf};      // four independent min chains
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              m4[c & 3] = fminf(m4[c & 3], SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]));
+            for (int c = 0; c < 32; ++c) m4[c & 3] = fminf(m4[c & 3], v[c]);
             tmin = fminf(tmin, fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])));
           } else {
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const int64_t gj = j0 + chunk * 32 + c;
-              const float u = SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]);
-              if (gj < p.n && gj != gi) tmin = fminf(tmin, u);
+              if (gj < p.n && gj != gi) tmin = fminf(tmin, v[c]);
             }
           }
         } else {
           // hit mask: FSETP + SEL of an immediate bit per column, summed (disjoint bits) in a tree
           uint32_t bit[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float u = SGN_POS ? fmaf(xs, cxc[c], -v[c]) : fmaf(xs, cxc[c], v[c]);
-            bit[c] = u <= thr ? (1u << c) : 0u;
-          }
+          for (int c = 0; c < 32; ++c) bit[c] = v[c] <= thr ? (1u << c) : 0u;
 #pragma unroll
           for (int w = 16; w >= 1; w >>= 1)
 #pragma unroll
@@ -476,19 +474,22 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       };
       {
         // Three register buffers rotate over the four chunks so that only the first TMEM round trip of a tile is
-        // exposed: chunks 2 and 3 are requested while chunks 0 and 1 are consumed.  (Consumers start with loads
-        // from shared memory, which cannot move above the waits' memory clobber.)
+        // exposed: chunks 2 and 3 are requested while chunks 0 and 1 are consumed.
         float va[32], vb[32], vc[32];
         const bool skip_math = (p.debug & 9) != 0;
         if (!(p.debug & 1)) {
           tmem_ld32_nowait(taddr, va);
           tmem_ld32_nowait(taddr + 32, vb);
           tmem_ld_wait();
+          tmem_pin(va);
+          tmem_pin(vb);
           tmem_ld32_nowait(taddr + 64, vc);
           if (!skip_math) consume(0, va);
           tmem_ld32_nowait(taddr + 96, va);
           if (!skip_math) consume(1, vb);
           tmem_ld_wait();
+          tmem_pin(vc);
+          tmem_pin(va);
           if (!skip_math) consume(2, vc);
           if (!skip_math) consume(3, va);
         }
@@ -541,7 +542,8 @@ __global__ void kth_select_kernel(const float *__restrict__ tilemin, int64_t ld_
     }
   }
   const float tau = worst;     // +inf when fewer than k tiles hold a finite minimum
-  const float eps = 0.001953125f * 1.05f * nrm[row0 + r] * __uint_as_float(*max_nrm_bits) + 2e-6f * fmaxf(1.f, tau);
+  // spatial TF32 rounding (2^-9 |xs_i| |xs_j|, 5 % margin) + fp32 accumulation and the split time-like term
+  const float eps = 0.001953125f * 1.05f * nrm[row0 + r] * __uint_as_float(*max_nrm_bits) + 8e-6f * fmaxf(1.f, tau);
   thr[r] = tau + 2.f * eps;
 }
 
@@ -685,8 +687,9 @@ struct TcLayout {
 static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
   TcLayout L;
   const int d = D - 1;
-  L.Kp = ((d + TC_KSLAB - 1) / TC_KSLAB) * TC_KSLAB;
-  L.n_ksteps = (d + 7) / 8;
+  const int kuse = d + 4;                    // spatial columns + the four time-like slots (tc_pack_kernel)
+  L.Kp = ((kuse + TC_KSLAB - 1) / TC_KSLAB) * TC_KSLAB;
+  L.n_ksteps = (kuse + 7) / 8;
   const int k8 = L.n_ksteps * 8;
   L.n_slabs = k8 / TC_KSLAB;
   int rem = k8 % TC_KSLAB;                 // 0, 8, 16 or 24 floats
@@ -706,8 +709,8 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
   L.ld_tm = ((nrows + 31) / 32) * 32;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
-  L.off_xp = take((size_t)n * L.Kp * 4);
-  L.off_x0 = take((size_t)n * 4);
+  L.off_xp = take((size_t)n * L.Kp * 4);     // XA
+  L.off_x0 = take((size_t)n * L.Kp * 4);     // XB
   L.off_nrm = take((size_t)n * 4);
   L.off_max = take(256);
   L.off_tilemin = take((size_t)L.col_tiles * L.ld_tm * 4);
@@ -724,7 +727,7 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
 using namespace hyp;
 
 extern "C" int64_t hyp_gram_topk_workspace_bytes(int64_t n, int64_t nrows, int D) {
-  if (n < 0 || nrows < 0 || D < 2 || D - 1 > TC_MAX_SLABS * TC_KSLAB) return -1;
+  if (n < 0 || nrows < 0 || D < 2 || D - 1 + 4 > TC_MAX_SLABS * TC_KSLAB) return -1;
   return (int64_t)tc_layout(n, nrows, D).total;
 }
 
@@ -736,8 +739,8 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
               (long long)row0, (long long)nrows, D, k, 32);
     return HYP_ERR_ARG;
   }
-  if (D - 1 > TC_MAX_SLABS * TC_KSLAB) {
-    set_error("hyp_gram_topk: d=%d exceeds the %d columns one shared-memory A tile holds", D - 1,
+  if (D - 1 + 4 > TC_MAX_SLABS * TC_KSLAB) {
+    set_error("hyp_gram_topk: d=%d (+4 time-like columns) exceeds the %d columns one shared-memory tile holds", D - 1,
               TC_MAX_SLABS * TC_KSLAB);
     return HYP_ERR_UNSUPPORTED;
   }
@@ -759,7 +762,8 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   }
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t *ws = (uint8_t *)workspace;
-  float *XP = (float *)(ws + L.off_xp), *x0 = (float *)(ws + L.off_x0), *nrm = (float *)(ws + L.off_nrm);
+  float *XA = (float *)(ws + L.off_xp), *XB = (float *)(ws + L.off_x0), *nrm = (float *)(ws + L.off_nrm);
+  const float sgn = semantics == HYP_SEM_REFERENCE ? -1.f : 1.f;
   unsigned int *maxn = (unsigned int *)(ws + L.off_max);
   float *tilemin = (float *)(ws + L.off_tilemin), *thr = (float *)(ws + L.off_thr);
   int32_t *cand = (int32_t *)(ws + L.off_cand), *cnt = (int32_t *)(ws + L.off_cnt);
@@ -777,34 +781,29 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   }
   cudaMemsetAsync(maxn, 0, 4, st);
   cudaMemsetAsync(cnt, 0, (size_t)nrows * 2 * sizeof(int32_t), st);
-  tc_pack_kernel<<<sms * 4, 256, 0, st>>>(E, ldE, n, D, L.Kp, XP, x0, nrm, maxn);
+  tc_pack_kernel<<<sms * 4, 256, 0, st>>>(E, ldE, n, D, L.Kp, sgn, XA, XB, nrm, maxn);
   int rc = check_launch("hyp_gram_topk(pack)");
   if (rc) return rc;
 
   if (timing) cudaEventRecord(tev[1], st);
 
-  CUtensorMap tmap;
   const cuuint64_t gdim[2] = {(cuuint64_t)L.Kp, (cuuint64_t)n};
   const cuuint64_t gstride[1] = {(cuuint64_t)L.Kp * 4};
   const cuuint32_t box[2] = {(cuuint32_t)TC_KSLAB, (cuuint32_t)TC_M};
+  const cuuint32_t tbox[2] = {(cuuint32_t)(L.tail_row_bytes ? L.tail_row_bytes / 4 : TC_KSLAB), (cuuint32_t)TC_M};
   const cuuint32_t estride[2] = {1, 1};
-  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)XP, gdim, gstride, box, estride,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) {
-    set_error("hyp_gram_topk: cuTensorMapEncodeTiled failed (%d)", (int)cr);
-    return HYP_ERR_CUDA;
-  }
-
-  CUtensorMap tmap_tail = tmap;
-  if (L.tail_row_bytes) {
-    const cuuint32_t tbox[2] = {(cuuint32_t)(L.tail_row_bytes / 4), (cuuint32_t)TC_M};
-    cr = encode(&tmap_tail, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)XP, gdim, gstride, tbox, estride,
-                CU_TENSOR_MAP_INTERLEAVE_NONE,
-                L.tail_row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
-                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUtensorMap maps[4];                       // A, A tail, B, B tail
+  for (int m = 0; m < 4; ++m) {
+    const bool tail = (m & 1) != 0;
+    void *base = (m < 2) ? (void *)XA : (void *)XB;
+    const CUtensorMapSwizzle sw = !tail || !L.tail_row_bytes ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : L.tail_row_bytes == 32   ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                             : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult cr = encode(&maps[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, tail ? tbox : box, estride,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
-      set_error("hyp_gram_topk: cuTensorMapEncodeTiled (tail) failed (%d)", (int)cr);
+      set_error("hyp_gram_topk: cuTensorMapEncodeTiled failed (%d) for map %d", (int)cr, m);
       return HYP_ERR_CUDA;
     }
   }
@@ -813,13 +812,10 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   p.n = n; p.row0 = row0; p.nrows = nrows; p.n_slabs = L.n_slabs; p.n_ksteps = L.n_ksteps;
   p.tail_row_bytes = L.tail_row_bytes; p.stage_bytes = L.stage_bytes; p.n_stages = L.n_stages;
   p.debug = getenv("HYP_TC_DEBUG") ? atoi(getenv("HYP_TC_DEBUG")) : 0;
-  p.sgn = semantics == HYP_SEM_REFERENCE ? -1.f : 1.f;
-  p.x0 = x0; p.tilemin = tilemin; p.ld_tm = L.ld_tm; p.thr = thr; p.cand = cand; p.cand_cnt = cnt;
-  const size_t smem = 1024 + (size_t)(2 + L.n_stages) * L.stage_bytes + TC_ACC * TC_N * 4 +
-                      (4 + 2 * TC_ACC + 2 * TC_MAX_STAGES) * 8;
-  const bool pos = p.sgn > 0.f;
-  auto k1 = pos ? gram_tc_kernel<1, true> : gram_tc_kernel<1, false>;
-  auto k2 = pos ? gram_tc_kernel<2, true> : gram_tc_kernel<2, false>;
+  p.tilemin = tilemin; p.ld_tm = L.ld_tm; p.thr = thr; p.cand = cand; p.cand_cnt = cnt;
+  const size_t smem = 1024 + (size_t)(2 + L.n_stages) * L.stage_bytes + (4 + 2 * TC_ACC + 2 * TC_MAX_STAGES) * 8;
+  auto k1 = gram_tc_kernel<1>;
+  auto k2 = gram_tc_kernel<2>;
   cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t row_pairs = ((nrows + TC_M - 1) / TC_M + 1) / 2;
@@ -835,7 +831,7 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   while (step > 1 && (L.col_tiles + step - 1) / step < 4 * (int64_t)k) --step;
   p.ct_step = step;
   p.n_ct = (L.col_tiles + step - 1) / step;
-  k1<<<grid, TC_THREADS, smem, st>>>(tmap, tmap_tail, p);
+  k1<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   rc = check_launch("hyp_gram_topk(pass 1)");
   if (rc) return rc;
   if (timing) cudaEventRecord(tev[2], st);
@@ -846,13 +842,13 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   if (timing) cudaEventRecord(tev[3], st);
   p.ct_step = 1;
   p.n_ct = L.col_tiles;
-  k2<<<grid, TC_THREADS, smem, st>>>(tmap, tmap_tail, p);
+  k2<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   rc = check_launch("hyp_gram_topk(pass 2)");
   if (rc) return rc;
   int64_t fb = (nrows + 3) / 4;
   if (fb > sms * 16) fb = sms * 16;
   if (timing) cudaEventRecord(tev[4], st);
-  tc_finish_kernel<<<(int)fb, 128, 0, st>>>(E, ldE, D, row0, nrows, sqrtf(c), p.sgn, k, cand, cnt, out_idx, out_d,
+  tc_finish_kernel<<<(int)fb, 128, 0, st>>>(E, ldE, D, row0, nrows, sqrtf(c), sgn, k, cand, cnt, out_idx, out_d,
                                            row_flags);
   rc = check_launch("hyp_gram_topk(finish)");
   if (timing) {

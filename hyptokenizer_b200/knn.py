@@ -45,7 +45,7 @@ def lorentz_topk(E: torch.Tensor, k: int = 32, c: float = 1.0, semantics: Option
     d = torch.empty((nrows, k), dtype=torch.float32, device=E.device)
     L = _lib.lib()
     if engine == "auto":
-        engine = "tc" if (n >= 8192 and k <= 32 and E.shape[1] - 1 <= 128 and sem == SEM["lorentz"]) else "exact"
+        engine = "tc" if (n >= 8192 and k <= 32 and E.shape[1] - 1 <= 124 and sem == SEM["lorentz"]) else "exact"
     if engine == "exact":
         with torch.cuda.device(E.device):
             check(L.hyp_allpairs_topk(ptr(E), E.stride(0), n, row0, nrows, E.shape[1], float(c), sem, k,
@@ -55,7 +55,7 @@ def lorentz_topk(E: torch.Tensor, k: int = 32, c: float = 1.0, semantics: Option
         raise ValueError("engine must be 'exact', 'tc' or 'auto'")
     nbytes = L.hyp_gram_topk_workspace_bytes(n, nrows, E.shape[1])
     if nbytes < 0:
-        raise ValueError("tensor-core path supports d <= 128")
+        raise ValueError("tensor-core path supports d <= 124 (d + 4 operand columns fit one 128-column tile)")
     ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=E.device)
     off = (-ws.data_ptr()) % 256
     flags = torch.empty(nrows, dtype=torch.int32, device=E.device)

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("n,d,k,scale,nrows,row0", [(1024, 100, 32, 0.05, None, 0), (4500, 100, 32, 0.01, None, 0),
                                                     (4500, 50, 16, 0.3, 1000, 777), (9000, 100, 32, 0.01, 3000, 6000),
-                                                    (2100, 128, 8, 0.1, None, 0), (1500, 7, 4, 0.2, None, 0),
+                                                    (2100, 124, 8, 0.1, None, 0), (1500, 7, 4, 0.2, None, 0),
                                                     (3000, 48, 8, 0.1, None, 0), (2000, 16, 4, 0.2, 700, 1300),
                                                     (2500, 90, 8, 0.1, None, 0), (2500, 64, 8, 0.1, None, 0)])
 def test_tc_equals_exact(n, d, k, scale, nrows, row0):
@@ -57,3 +57,23 @@ def test_tc_full_size_shard_equals_exact():
     ti, td = lorentz_topk(E, k, 1.0, "lorentz", n, row0, nrows, engine="tc")
     assert torch.equal(ti, ei) and same_bits(td, ed)
     assert lorentz_topk.last_flagged == 0
+
+
+def test_tc_dimension_limit_and_large_scale():
+    """d + 4 operand columns (the time-like term rides inside the MMA as hi/lo TF32 parts) must fit 128: d = 125 is
+    refused by the tensor-core engine and `auto` takes the exact kernel.  Points far from the origin (x0 up to ~50,
+    where one TF32 slot for x0 would be off by 1) still give the exact lists."""
+    from hyptokenizer_b200.knn import lorentz_topk
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    E = synthetic_embeddings(9000, 125, scale=0.1, seed=3, device="cuda")
+    with pytest.raises(ValueError):
+        lorentz_topk(E, 8, 1.0, "lorentz", engine="tc")
+    ai, ad = lorentz_topk(E, 8, 1.0, "lorentz", engine="auto")
+    ei, ed = lorentz_topk(E, 8, 1.0, "lorentz", engine="exact")
+    assert torch.equal(ai, ei) and same_bits(ad, ed)
+    for scale in (0.5, 1.5):
+        F = synthetic_embeddings(6000, 40, scale=scale, seed=17, device="cuda")
+        assert float(F[:, 0].max()) > (3.0 if scale == 0.5 else 30.0)
+        ti, td = lorentz_topk(F, 16, 1.0, "lorentz", engine="tc")
+        xi, xd = lorentz_topk(F, 16, 1.0, "lorentz", engine="exact")
+        assert torch.equal(ti, xi) and same_bits(td, xd)
