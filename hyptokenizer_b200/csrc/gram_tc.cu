@@ -250,6 +250,7 @@ struct TcParams {
   int n_ksteps;       // ceil(d / 8) MMAs per tile
   int debug;          // HYP_TC_DEBUG bit 0: epilogue skips TMEM loads + math, bit 1: no MMAs issued, bit 2: no TMA,
                       //              bit 3: epilogue loads TMEM but skips the math
+  int rb_per_cta;     // 2: two row blocks share each B tile; 1: small shards (fewer than two row blocks per SM)
   int64_t n_ct;       // column tiles this pass visits: ct = t * ct_step, t in [0, n_ct)
   int ct_step;        // 1 = every tile; pass 1 may sample (see hyp_gram_topk)
   // pass 1
@@ -283,7 +284,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row_blocks = (p.nrows + TC_M - 1) / TC_M;
-  const int64_t row_pairs = (row_blocks + 1) / 2;
+  const int64_t row_pairs = (row_blocks + p.rb_per_cta - 1) / p.rb_per_cta;   // work items: pairs (or single blocks)
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1);
@@ -310,11 +311,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       uint32_t bstage = 0, bphase = 0, aphase = 0;
       for (int64_t rp = blockIdx.x; rp < row_pairs; rp += gridDim.x) {
         mbar_wait(a_empty, aphase ^ 1);
-        mbar_expect_tx(a_full, 2 * tile_tx);
-        for (int h = 0; h < 2; ++h) {
+        mbar_expect_tx(a_full, p.rb_per_cta * tile_tx);
+        for (int h = 0; h < p.rb_per_cta; ++h) {
           // (rows past the table are zero-filled by TMA; their results are never written)
           uint8_t *dstA = sA + (size_t)h * p.stage_bytes;
-          const int arow = (int)(p.row0 + (2 * rp + h) * TC_M);
+          const int arow = (int)(p.row0 + (p.rb_per_cta * rp + h) * TC_M);
           for (int s = 0; s < p.n_slabs; ++s) tma_load_2d(&tmapA, a_full, dstA + s * TC_SLAB_BYTES, s * TC_KSLAB, arow);
           if (p.tail_row_bytes) tma_load_2d(&tmapA_tail, a_full, dstA + p.n_slabs * TC_SLAB_BYTES, tail_elem0, arow);
         }
@@ -356,6 +357,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       }
       const int h = warp == 1 ? 0 : 1;
       const uint32_t a_lo = ((smem_u32(sA + (size_t)h * p.stage_bytes) >> 4) & 0x3fff) | (1u << 16);
+      const bool idle = h >= p.rb_per_cta;              // single-block mode: the second issuer only keeps the barriers moving
       const int nk = (p.debug & 2) ? 0 : p.n_ksteps;
       uint32_t bstage = 0, bphase = 0, aphase = 0;
       uint32_t tt = 0;                      // tiles issued by this CTA: accumulators 2*(tt&1)+h, use number tt>>1
@@ -365,7 +367,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         for (int64_t t = 0; t < p.n_ct; ++t, ++tt) {
           mbar_wait(b_full + bstage, bphase);
           const uint32_t b_lo = ((smem_u32(sB + (size_t)bstage * p.stage_bytes) >> 4) & 0x3fff) | (1u << 16);
-          {
+          if (!idle) {
             const uint32_t abuf = 2 * (tt & 1) + h;
             mbar_wait(acc_empty + abuf, ((tt >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -402,7 +404,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     const int r_in_block = lane_base + lane;         // row of the tile
     const float inf = __int_as_float(0x7f800000);
     const int64_t my_pairs = (row_pairs > blockIdx.x) ? (row_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total = my_pairs * p.n_ct;
+    const int64_t total = grp < p.rb_per_cta ? my_pairs * p.n_ct : 0;
     int64_t cur_rbi = -1, blk0 = 0, gi = 0;
     bool row_ok = false;
     float thr = 0.f;
@@ -422,7 +424,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       if (rbi != cur_rbi) {
         if (PASS == 2 && cur_rbi >= 0 && row_ok) flush_count();
         cur_rbi = rbi;
-        blk0 = p.row0 + ((blockIdx.x + rbi * gridDim.x) * 2 + grp) * TC_M;
+        blk0 = p.row0 + ((blockIdx.x + rbi * gridDim.x) * p.rb_per_cta + grp) * TC_M;
         gi = blk0 + r_in_block;
         row_ok = gi < p.row0 + p.nrows;
         if (PASS == 2) thr = row_ok ? __ldg(p.thr + (gi - p.row0)) : -inf;
@@ -818,7 +820,10 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   auto k2 = gram_tc_kernel<2>;
   cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int64_t row_pairs = ((nrows + TC_M - 1) / TC_M + 1) / 2;
+  const int64_t row_blocks = (nrows + TC_M - 1) / TC_M;
+  p.rb_per_cta = row_blocks >= 2 * (int64_t)sms ? 2 : 1;     // pairing only pays once every SM has a pair
+  if (const char *e = getenv("HYP_TC_PAIR")) p.rb_per_cta = atoi(e) == 1 ? 1 : 2;
+  const int64_t row_pairs = (row_blocks + p.rb_per_cta - 1) / p.rb_per_cta;
   const int grid = (int)(row_pairs < sms ? row_pairs : sms);
 
   // Pass 1 only has to BOUND each row's k-th best from above, and the k-th smallest minimum over ANY >= k distinct

@@ -13,9 +13,11 @@ pytestmark = pytest.mark.gpu
                                                     (2100, 124, 8, 0.1, None, 0), (1500, 7, 4, 0.2, None, 0),
                                                     (3000, 48, 8, 0.1, None, 0), (2000, 16, 4, 0.2, 700, 1300),
                                                     (2500, 90, 8, 0.1, None, 0), (2500, 64, 8, 0.1, None, 0)])
-def test_tc_equals_exact(n, d, k, scale, nrows, row0):
+@pytest.mark.parametrize("pair", ["1", "2"])
+def test_tc_equals_exact(monkeypatch, pair, n, d, k, scale, nrows, row0):
     from hyptokenizer_b200.knn import lorentz_topk
     from hyptokenizer_b200.synth import synthetic_embeddings
+    monkeypatch.setenv("HYP_TC_PAIR", pair)      # one or two row blocks per CTA (the library picks by shard size)
     E = synthetic_embeddings(n, d, scale=scale, seed=n + d, device="cuda")
     nrows = n - row0 if nrows is None else nrows
     ei, ed = lorentz_topk(E, k, 1.0, "lorentz", n, row0, nrows, engine="exact")
