@@ -434,6 +434,35 @@ __device__ __forceinline__ float resident_mdot_dynamic(const float4 *__restrict_
   return __fsub_rn(__fmul_rn(T0[slot], q0), s);
 }
 
+// Rows [row0, n) of the table in global memory against q, a warp per row (4 in flight), this warp taking every
+// `stride`-th group of 4 from `first`.  Lane 0 folds (distance bits, row) into (best_d, best_r).  Out of line: it runs
+// only for tables larger than the grid's shared memory and must not cost the resident path registers.
+__device__ __noinline__ void overflow_scan(const float *E, int64_t ldE, int64_t row0, int n, const float *q, int D,
+                                           float sqrt_c, float sgn, int64_t first, int64_t stride, int lane,
+                                           unsigned int &best_d, unsigned int &best_r) {
+  for (int64_t base = row0 + first * kRowsPerIter; base < n; base += stride * kRowsPerIter) {
+    int64_t rows[kRowsPerIter];
+    int nr = 0;
+#pragma unroll
+    for (int a = 0; a < kRowsPerIter; ++a) {
+      rows[a] = base + a;
+      if (base + a < n) nr = a + 1;
+    }
+    float mm[kRowsPerIter];
+    warp_mdot_rows<kRowsPerIter>(E, ldE, rows, nr, q, D, lane, mm);
+#pragma unroll
+    for (int a = 0; a < kRowsPerIter; ++a) {
+      if (a < nr) {
+        const float d = dist_from_mdot(mm[a], sgn, sqrt_c);            // identical on every lane
+        if (d == d && lane == 0 && __float_as_uint(d) < best_d) {      // rows ascend: strict < keeps the smallest
+          best_d = __float_as_uint(d);
+          best_r = (unsigned int)rows[a];
+        }
+      }
+    }
+  }
+}
+
 // named barrier over the first `nthreads` threads of the CTA (the speculating warp stays out of it)
 __device__ __forceinline__ void bar_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -468,7 +497,9 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
 // speculative scan writes (row n+1 of the table in shared and global memory, its len and log entry) lies beyond the
 // committed state and is rewritten by the redo; a guess is only made when merge k+1 is due under it, and a changed
 // best (smaller distance) cannot make it undue, so nothing speculative survives the launch.
-template <int NS>
+// OVER: the table may outgrow the grid's shared memory (rows >= slots * G are scored from L2).  A separate
+// instantiation: the extra code cost the all-resident kernel 12 % (registers, code layout) when it was merely present.
+template <int NS, bool OVER>
 __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(const ResidentParams rp) {
   extern __shared__ __align__(16) float smem[];
   const LoopParams &p = rp.lp;
@@ -523,7 +554,7 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   // ---- load the rows this CTA owns: a warp reads one row (coalesced), scatters it conflict-free --
   {
     const int owned0 = (n > b) ? (n - b + G - 1) / G : 0;
-    for (int sl = warp; sl < owned0; sl += kResWarps) {
+    for (int sl = warp; sl < owned0 && (!OVER || sl < S); sl += kResWarps) {   // OVER: rows beyond S slots stay in global memory
       const float *row = p.E + ((int64_t)sl * G + b) * p.ldE;
       for (int k = lane; k < D; k += 32) {
         const float v = __ldcg(row + k);
@@ -601,7 +632,15 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
       __syncwarp();
       if (lane == 0) st_relaxed_u32(&p.ws->published, nscan);
     }
-    for (int t = threadIdx.x; t < own; t += kWork) {
+    // Rows that did not fit the grid's shared memory (index >= S * G) are scored from L2, a warp per row, coalesced.
+    // They were written by CTA 0 in earlier scans: its appending warp publishes a scan's number behind a fence, and
+    // the load below (issued now, consumed after the resident rows) acquires it.
+    const int64_t over0 = (int64_t)S * G;
+    const bool has_over = OVER && (int64_t)nn > over0;
+    unsigned int pub = 0;
+    if (OVER && has_over && lane == 0) pub = ld_acquire_u32(&p.ws->published);
+    const int own_res = (OVER && own > S) ? S : own;
+    for (int t = threadIdx.x; t < own_res; t += kWork) {
       const float m = (NS > 0) ? resident_mdot_static<(NS > 0 ? NS : 8)>(T4, T0, S, t, q4, q0)
                                : resident_mdot_dynamic(T4, T0, S, t, q4, q0, N);
       if (early && t == 0) {
@@ -617,8 +656,15 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
         my_r = (unsigned int)(t * G + b);
       }
     }
+    if (OVER && has_over) {
+      if (lane == 0)
+        while (pub + 1u < nscan) pub = ld_acquire_u32(&p.ws->published);   // every earlier scan's append is visible
+      __syncwarp();
+      overflow_scan(p.E, p.ldE, over0, nn, q, D, p.sqrt_c, p.sgn, (int64_t)b * kWorkWarps + warp, (int64_t)G * kWorkWarps,
+                    lane, my_d, my_r);
+    }
     // the owner of row nn appends it (its slot is beyond `own`, so nobody reads it during this scan)
-    if (nmod == b) {
+    if (nmod == b && (!OVER || ndiv < S)) {
       for (int e = threadIdx.x; e < D; e += kWork) {
         if (e == 0) T0[ndiv] = q[0];
         else Tf[((size_t)((e - 1) >> 2) * S + ndiv) * 4 + ((e - 1) & 3)] = q[e];
@@ -884,14 +930,24 @@ extern "C" int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float
   const char *force = getenv("HYP_MERGE_LOOP");
   const bool want_l2 = force && force[0] == 'l';
   const int64_t rows_max = capacity_hint > 0 ? capacity_hint : 0;
-  if (!want_l2 && slots >= 1 && rows_max > 0 && (rows_max + sms - 1) / sms <= slots) {
+  if (const char *e = getenv("HYP_RESIDENT_SLOTS")) {       // tests: shrink the resident part to exercise the overflow path
+    const int want = atoi(e);
+    if (want >= 1 && want < slots) slots = want | 1;
+  }
+  // Rows beyond slots * sms stay in global memory and are scored from L2 by the same kernel (a warp per row); past
+  // four times the resident capacity the plain L2 loop is as good.
+  if (!want_l2 && slots >= 1 && rows_max > 0 && (rows_max + sms - 1) / sms <= (int64_t)4 * slots) {
     ResidentParams rp;
     rp.lp = p;
     rp.slots = slots;
     const size_t smem = ((size_t)12 * G4 + (size_t)4 * G4 * slots + slots + (size_t)9 * D) * sizeof(float);
-    const void *fn = Nsp == 100 ? (const void *)merge_loop_resident_kernel<100>
-                     : Nsp == 50 ? (const void *)merge_loop_resident_kernel<50>
-                                 : (const void *)merge_loop_resident_kernel<0>;
+    const bool over = (rows_max + sms - 1) / sms > slots;
+    const void *fn = over ? (Nsp == 100  ? (const void *)merge_loop_resident_kernel<100, true>
+                             : Nsp == 50 ? (const void *)merge_loop_resident_kernel<50, true>
+                                         : (const void *)merge_loop_resident_kernel<0, true>)
+                          : (Nsp == 100  ? (const void *)merge_loop_resident_kernel<100, false>
+                             : Nsp == 50 ? (const void *)merge_loop_resident_kernel<50, false>
+                                         : (const void *)merge_loop_resident_kernel<0, false>);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("hyp_merge_steps: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));

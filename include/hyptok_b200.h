@@ -184,8 +184,9 @@ int hyp_merge_state_init(hyp_merge_state *state, const hyp_best *best, int32_t n
  * (state->stop = 1) or the table is full (stop = 2, the reference's ValueError).
  * `capacity_hint` = an upper bound, known to the host, on the rows the table can reach during this
  * call (min(state->capacity, n + max_steps); the state itself lives on the device): when that many
- * rows fit in the shared memory of one persistent CTA per SM the table-resident kernel runs,
- * otherwise the L2-streaming one; both produce identical bits.
+ * rows fit in the shared memory of one persistent CTA per SM the table-resident kernel runs; up to
+ * four times that capacity the same kernel keeps the first rows resident and scores the rest from
+ * L2; beyond, the L2-streaming kernel runs.  All produce identical bits.
  * A call on a state whose `stop` is already non-zero does nothing (steps_done = 0, stop kept), so a
  * host may queue a long run as several calls (advancing `log` and `step0`) without a round trip in
  * between and read each call's log while the next one runs. */

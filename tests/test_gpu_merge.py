@@ -284,6 +284,39 @@ def test_pipelined_loop_long_run_and_no_speculative_leftovers(monkeypatch):
     assert outs[0][0] == outs[1][0] and same_bits(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("slots,n0,d_", [("5", 2000, 100), ("3", 1200, 50), ("9", 1500, 7)])
+def test_resident_loop_with_rows_beyond_shared_memory(monkeypatch, slots, n0, d_):
+    """Tables larger than the grid's shared memory: the first slots * 148 rows are resident, the rest are scored from
+    L2 by the same kernel (rows appended by CTA 0 are published to the other CTAs before they are read).  The resident
+    part is shrunk to a few slots per CTA here; logs and rows must equal the plain L2 loop bit for bit, also across
+    the boundary where appended rows stop fitting and over two launches."""
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    from hyptokenizer_b200.tokenizer.hyperbolic_merge import HyperbolicTokenizer
+    steps = 500
+    outs = []
+    for variant in ("resident", "l2"):
+        monkeypatch.setenv("HYP_MERGE_LOOP", variant)
+        monkeypatch.setenv("HYP_RESIDENT_SLOTS", slots)
+        emb = synthetic_embeddings(n0, d_, scale=0.05 if d_ > 7 else 0.2, seed=21, device="cuda")
+        tok = HyperbolicTokenizer([f"w{k}" for k in range(n0)], torch.nn.Parameter(emb),
+                                  merge_threshold=0.9 if d_ > 7 else 2.0, max_vocab_size=n0 + steps, semantics="lorentz")
+        tok.optimize_merges(steps=300)
+        tok.optimize_merges(steps=200)
+        outs.append((tok.vocab[-1], tok.current_vocab_size, tok.embeddings.detach().cpu()))
+    assert outs[0][1] == n0 + steps and outs[0][:2] == outs[1][:2] and same_bits(outs[0][2], outs[1][2])
+    # the boundary case: a table that starts inside the resident capacity and grows past it
+    monkeypatch.setenv("HYP_RESIDENT_SLOTS", "5")          # 740 rows
+    res = []
+    for variant in ("resident", "l2"):
+        monkeypatch.setenv("HYP_MERGE_LOOP", variant)
+        emb = synthetic_embeddings(600, 100, scale=0.05, seed=5, device="cuda")
+        tok = HyperbolicTokenizer([f"w{k}" for k in range(600)], torch.nn.Parameter(emb), merge_threshold=0.9,
+                                  max_vocab_size=1000, semantics="lorentz")
+        tok.optimize_merges(steps=400)
+        res.append((tok.last_trace.copy(), tok.embeddings.detach().cpu()))
+    assert np.array_equal(res[0][0], res[1][0]) and same_bits(res[0][1], res[1][1])
+
+
 def test_row_min_entry_point():
     """K4 as a standalone call: argmin over i != row of (d(E[i], E[row]), pair) and the count below threshold."""
     from hyptokenizer_b200 import _lib
