@@ -463,6 +463,17 @@ __device__ __noinline__ void overflow_scan(const float *E, int64_t ldE, int64_t 
   }
 }
 
+// The merged row of (xi, xj), out of line: for the call sites that run once per launch or once per failed guess, so
+// that only the steady-state copy (the speculating warp's) is inlined into the loop.
+template <int NS>
+__device__ __noinline__ void midpoint_cold(const float *xi, const float *xj, int len_i, int len_j, int D, float c,
+                                           int semantics, float *scr, int lane, float *qr, float *qf) {
+  warp_midpoint<NS>(xi, xj, len_i, len_j, D, c, semantics, true, scr, lane, [&](int e, float v) {
+    qr[e] = v;
+    if (e) qf[e - 1] = v;
+  });
+}
+
 // named barrier over the first `nthreads` threads of the CTA (the speculating warp stays out of it)
 __device__ __forceinline__ void bar_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -542,6 +553,10 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   long long t_mid = 0, t_scan = 0, t_bar = 0, t_mark = 0;
 #endif
 
+  auto midpoint_rare = [&](int which, float *scr) {
+    midpoint_cold<NS>(xi, xj, s_len[0], s_len[1], D, p.c, p.semantics, scr, lane, qrow + which * D,
+                      reinterpret_cast<float *>(qq4 + which * G4));
+  };
   auto midpoint_into = [&](int which, float *scr, long long *tp = nullptr) {
     float *qr = qrow + which * D;
     float *qf = reinterpret_cast<float *>(qq4 + which * G4);
@@ -718,10 +733,10 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   // ---- prologue: q_0, then scan_0 + arrival 0 next to q'_1 (hyperbolic_merge.py:317-340) -------------------------
   int code = due(0, n, best, thr, thr_f);
   if (code == 0) {
-    if (warp == 0) midpoint_into(cur, scratch);
+    if (warp == 0) midpoint_rare(cur, scratch);
     __syncthreads();
     if (spec_warp) {
-      midpoint_into(nx1, scratch + 2 * D);
+      midpoint_rare(nx1, scratch + 2 * D);
     } else {
       scan(cur, n, owned, n_mod, n_div, 0, nullptr);
       if (threadIdx.x == 0) arrive(0, n);
@@ -788,9 +803,9 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
       __syncthreads();
       if (code == 0) {
         // the guess failed: the real q_{k+1}, then scan_{k+1} next to the new q'_{k+2}
-        if (warp == 0) midpoint_into(nx1, scratch);
+        if (warp == 0) midpoint_rare(nx1, scratch);
         __syncthreads();
-        if (spec_warp) midpoint_into(nx2, scratch + 2 * D);
+        if (spec_warp) midpoint_rare(nx2, scratch + 2 * D);
         else scan(nx1, n, owned, n_mod, n_div, k + 1, nullptr);
         __syncthreads();
       }
