@@ -730,51 +730,61 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
     __threadfence();
   };
 
-  // ---- prologue: q_0, then scan_0 + arrival 0 next to q'_1 (hyperbolic_merge.py:317-340) -------------------------
+  // ---- the loop, as phases with ONE copy of the scan and of each midpoint (the kernel is sensitive to its code size).
+  // A phase = [warp 0 computes the real merged row into nx1] ; { scan of nx1 || speculating warp: the row after it
+  // into nx2 } ; CTA barrier.  Two kinds:
+  //   real phase (prologue, and after a failed guess): scan_k of the real q_k; then post its arrival and rotate.
+  //   guess phase (steady state): scan_{k+1} of q'_{k+1} while exchange_k is in flight, then read exchange_k:
+  //     unchanged -> commit merge k, post the arrival of scan_{k+1}, rotate;
+  //     changed   -> commit merge k with the new best, fetch its operands, next phase is a real one.
+  // invariant before a guess phase: merge k is due; `best`, q_k (buffer cur) are final; scan_k is done and its arrival
+  // posted; q'_{k+1} (buffer nx1) is the merged row for `best`, computed from xi, xj, s_len
   int code = due(0, n, best, thr, thr_f);
-  if (code == 0) {
-    if (warp == 0) midpoint_rare(cur, scratch);
-    __syncthreads();
-    if (spec_warp) {
-      midpoint_rare(nx1, scratch + 2 * D);
-    } else {
-      scan(cur, n, owned, n_mod, n_div, 0, nullptr);
-      if (threadIdx.x == 0) arrive(0, n);
-    }
-    __syncthreads();
-  }
+  int k = 0;                                   // next merge to commit
+  bool guess = false;                          // kind of the next phase
 #ifdef HYP_LOOP_PROF
   if (threadIdx.x == 0) t_mark = clock64();
 #endif
-
-  for (int k = 0; code == 0; ++k) {
-    // invariant: merge k is due; `best`, q_k (buffer cur) are final; scan_k is done and its arrival posted;
-    // q'_{k+1} (buffer nx1) is the merged row for `best`, computed from xi, xj, s_len
-    const bool bump = (long long)k == next_thr;            // step0 + k is a positive multiple of thr_every
+  while (code == 0) {
+    // what this phase scans: merge ks, row ns, and the owner bookkeeping that goes with row ns
+    const bool bump = guess && (long long)k == next_thr;   // step0 + k is a positive multiple of thr_every
     const double thr_n = bump ? thr * p.thr_mul : thr;
     const float thr_nf = bump ? (float)thr_n : thr_f;
-    const int own1 = owned + (n_mod == b ? 1 : 0);
     const bool wrap = n_mod + 1 == G;
-    const int nmod1 = wrap ? 0 : n_mod + 1, ndiv1 = n_div + (wrap ? 1 : 0);
-    code = due(k + 1, n + 1, best, thr_n, thr_nf);         // is merge k+1 due if `best` stays?
+    const int own1 = guess ? owned + (n_mod == b ? 1 : 0) : owned;
+    const int nmod1 = guess ? (wrap ? 0 : n_mod + 1) : n_mod, ndiv1 = guess ? n_div + (wrap ? 1 : 0) : n_div;
+    const int ks = guess ? k + 1 : k, ns = guess ? n + 1 : n;
+    int code_s = guess ? due(k + 1, n + 1, best, thr_n, thr_nf) : 0;   // is merge k+1 due if `best` stays?
 
+    if (!guess) {
+      if (warp == 0) midpoint_rare(nx1, scratch);          // the real q_k
+      __syncthreads();
+    }
     if (spec_warp) {
 #ifdef HYP_MID_PROF
-      if (code == 0) midpoint_into(nx2, scratch + 2 * D, m_prof);
+      if (code_s == 0) midpoint_into(nx2, scratch + 2 * D, m_prof);
 #else
-      if (code == 0) midpoint_into(nx2, scratch + 2 * D);
+      if (code_s == 0) midpoint_into(nx2, scratch + 2 * D);
 #endif
     } else {
-      if (code == 0) scan(nx1, n + 1, own1, nmod1, ndiv1, k + 1, &p.ws->xring[k & (kXRing - 1)]);
-      if (threadIdx.x == 0) {
+      if (code_s == 0) scan(nx1, ns, own1, nmod1, ndiv1, ks, guess ? &p.ws->xring[k & (kXRing - 1)] : nullptr);
+      if (guess && threadIdx.x == 0) {
         HYP_PHASE(t_scan);
         poll(k);
         HYP_PHASE(t_bar);
       }
     }
     __syncthreads();
-    const unsigned long long win = s_win[k & 1];
 
+    if (!guess) {
+      // scan_k is done for real: post it, q_k becomes `cur`, the row after it is the next guess
+      if (threadIdx.x == 0) arrive(k, n);
+      const int t = cur; cur = nx1; nx1 = nx2; nx2 = t;
+      guess = true;
+      continue;
+    }
+
+    const unsigned long long win = s_win[k & 1];
     bool changed = false;
     if (win != kNoKey) {
       Key r{__uint_as_float((unsigned int)(win >> 32)), (int)(win & 0xffffffffu), n};
@@ -801,21 +811,18 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
       if (threadIdx.x == 1) s_len[1] = ln;
       code = due(k + 1, n, best, thr, thr_f);
       __syncthreads();
-      if (code == 0) {
-        // the guess failed: the real q_{k+1}, then scan_{k+1} next to the new q'_{k+2}
-        if (warp == 0) midpoint_rare(nx1, scratch);
-        __syncthreads();
-        if (spec_warp) midpoint_rare(nx2, scratch + 2 * D);
-        else scan(nx1, n, owned, n_mod, n_div, k + 1, nullptr);
-        __syncthreads();
-      }
+      ++k;
+      guess = false;                           // the guess failed: the next phase recomputes q_{k+1} and scans it
+      continue;
     }
+    code = code_s;
     if (code != 0) break;
     if (threadIdx.x == 0) {
       if ((k & (kXRing / 4 - 1)) == kXRing / 4 - 1) wait_published();   // recycled slots: see scan
       arrive(k + 1, n);
     }
     const int t = cur; cur = nx1; nx1 = nx2; nx2 = t;
+    ++k;
     if (threadIdx.x == 0) HYP_PHASE(t_mid);
   }
   stop = code > 0 ? code : 0;
