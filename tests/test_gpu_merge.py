@@ -317,6 +317,27 @@ def test_resident_loop_with_rows_beyond_shared_memory(monkeypatch, slots, n0, d_
     assert np.array_equal(res[0][0], res[1][0]) and same_bits(res[0][1], res[1][1])
 
 
+def test_initial_best_through_tensor_cores_equals_exact_scan():
+    """Large tables in the corrected geometry start the loop from the tcgen05 top-1 lists; the pair must be the one the
+    exact all-pairs scan picks, also with duplicated rows (distance-0 ties, resolved by index)."""
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    from hyptokenizer_b200.tokenizer.hyperbolic_merge import HyperbolicTokenizer, _threshold_f32
+    for dup in (False, True):
+        n0 = 30500
+        emb = synthetic_embeddings(n0, 100, scale=0.05, seed=13, device="cuda")
+        if dup:
+            emb[7000] = emb[41]
+            emb[28123] = emb[41]
+            emb[300] = emb[17]
+        tok = HyperbolicTokenizer([f"w{k}" for k in range(n0)], torch.nn.Parameter(emb), merge_threshold=0.9,
+                                  max_vocab_size=n0 + 8, semantics="lorentz")
+        thr = _threshold_f32(tok.merge_threshold, n0)
+        a, b = tok._initial_best(thr), tok._global_best(thr)
+        assert (a.i, a.j) == (b.i, b.j) and a.d == b.d
+        if dup:
+            assert (a.i, a.j, a.d) == (17, 300, 0.0)
+
+
 def test_row_min_entry_point():
     """K4 as a standalone call: argmin over i != row of (d(E[i], E[row]), pair) and the count below threshold."""
     from hyptokenizer_b200 import _lib
