@@ -28,8 +28,10 @@ __device__ __forceinline__ float clamp_max(float x, float hi) { return (x > hi) 
 // acosh for u >= 1 in the form log1p(t + sqrt(t (t+2))), t = u-1: <= 2.5 ulp of torch's CPU
 // acosh and bit-equal to it ~85 % of the time. acosh(1) == 0 exactly,
 // NaN -> NaN.
+// (out of line: it is the rare branch, and the merge loop's speed depends on the size of its inlined code)
+static __device__ __noinline__ float acosh_huge(float u) { return __fadd_rn(logf(u), 0.69314718f); }
 __device__ __forceinline__ float acosh_ge1(float u) {
-  if (u > 1e18f) return __fadd_rn(logf(u), 0.69314718f);  // t*(t+2) would overflow
+  if (u > 1e18f) return acosh_huge(u);  // t*(t+2) would overflow
   float t = __fsub_rn(u, 1.0f);
   float s = __fsqrt_rn(__fmul_rn(t, __fadd_rn(t, 2.0f)));
   return log1pf(__fadd_rn(t, s));
