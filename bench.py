@@ -271,7 +271,7 @@ def run_ours(a):
                          "merge_loop_resident_kernel<100, false> (cooperative, persistent)",
         "roofline": {"bound": "hbm", "kernel": "merge_loop_resident_kernel<100, false>", "achieved": achieved, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                     "traffic": 4137216, "traffic_source": "profiles/r01_prof_merge_raw.csv: dram__bytes_read.sum + "
+                     "traffic": 4107776, "traffic_source": "profiles/r01_prof_merge_raw.csv: dram__bytes_read.sum + "
                                                            "dram__bytes_write.sum of one launch (ncu --set full)",
                      "peak_kind": pk_kind,
                      "algorithmic_bytes_per_launch": abytes, "kernel_ms": loop_ms,
