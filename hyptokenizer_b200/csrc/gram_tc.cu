@@ -515,8 +515,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 
 // tau_i = k-th smallest tile minimum of row i (thread per row, coalesced over rows), then
 // thr_i = tau_i + 2 eps_i with eps_i = 2^-9 * 1.05 * |xs_i| * max|xs| + 2e-6 * max(1, tau_i).
-// (Measured: the data-dependent insert diverges within a warp and costs ~1 ms at V=100k; splitting a row over
-// several threads made it slower.  A shared-memory transposed bisection select is the next step.)
+// (Measured: the data-dependent insert diverges within a warp; 0.35 ms at V=100k with every 2nd tile sampled.  Splitting
+// a row over several threads was slower, and so was a warp-per-row bisection over a shared-memory panel of 128 rows:
+// staging 200 KB per block with 256 threads is latency-bound.)
 __global__ void kth_select_kernel(const float *__restrict__ tilemin, int64_t ld_tm, int64_t col_tiles, int64_t nrows,
                                   int64_t row0, int k, const float *__restrict__ nrm,
                                   const unsigned int *__restrict__ max_nrm_bits, float *__restrict__ thr) {
