@@ -37,10 +37,11 @@ import tokenizer.hyperbolic_merge as RH  # noqa: E402
 import tokenizer.fast_hyperbolic_merge as RF  # noqa: E402
 import tokenizer.frequency_aware_hyperbolic_merge as RQ  # noqa: E402
 import tokenizer.hierarchical_hyperbolic_merge as RHI  # noqa: E402
+import tokenizer.compression_aware_tokenizer as RCA  # noqa: E402
 import tqdm as _tqdm  # noqa: E402
 
 # silence progress bars
-for _m in (RH, RF, RQ, RHI):
+for _m in (RH, RF, RQ, RHI, RCA):
     if hasattr(_m, "tqdm"):
         _m.tqdm = lambda it, **kw: _Quiet(it)
 
@@ -98,7 +99,7 @@ _PATCH = {"distance": _lz_distance, "batch_distance": _lz_batch_distance, "log_m
 def semantics(name: str):
     saved = []
     if name == "lorentz":
-        for mod in (RL, RH, RF, RQ, RHI):
+        for mod in (RL, RH, RF, RQ, RHI, RCA):
             for k, fn in _PATCH.items():
                 if hasattr(mod, k):
                     saved.append((mod, k, getattr(mod, k)))
@@ -444,7 +445,41 @@ def gen_trace_hier(tmpdir="/tmp"):
     dump("trace_hier.json", out)
 
 
-GENS = {"trace_hier": gen_trace_hier, "lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
+def gen_trace_compress():
+    """CompressionAwareTokenizer.optimize_merges (compression_aware_tokenizer.py:217-276), small: the first
+    `sample_size` candidates are re-scored by the greedy longest-match token count of a corpus sample."""
+    rng = random.Random(11)
+    stems = ["the", "and", "ing", "tion", "er", "re", "un", "al", "ed", "in", "light", "house", "water", "stone"]
+    sample = [" ".join(rng.choice(stems) + rng.choice(stems) for _ in range(rng.randint(2, 6))) for _ in range(14)]
+    sample.append(sample[0][:20] + " tail that shares the cache key of the first text")     # the text[:20] quirk
+    vocab = c1_vocab()
+    out = {"sample": sample, "vocab0": vocab, "d": 8, "runs": []}
+    for sem, scale, thr, ss in (("reference", 0.3, 0.1, 40), ("lorentz", 0.3, 1.2, 25), ("lorentz", 0.02, 0.05, 100)):
+        set_seeds(42)
+        emb = ref_init(len(vocab), 8, scale)
+        with semantics(sem):
+            tok = RCA.CompressionAwareTokenizer(vocab, torch.nn.Parameter(emb.clone()), corpus_sample=list(sample),
+                                                sample_size=ss, merge_threshold=thr, device=torch.device("cpu"),
+                                                max_vocab_size=256)
+            rec = record_merges(tok)
+            heads = []
+            orig = tok._find_merge_candidates
+
+            def spy():
+                c = orig()
+                heads.append([len(c), (float(c[0][2]) if c else None)])
+                return c
+
+            tok._find_merge_candidates = spy
+            tok.optimize_merges(steps=10, log_every=10 ** 9)
+        out["runs"].append({"semantics": sem, "scale": scale, "threshold0": thr, "sample_size": ss, "init": bits(emb),
+                            "merges_ij": rec, "heads": [[n, (None if s is None or s != s else s)] for n, s in heads],
+                            "final": tok_state(tok)})
+        print("compress", sem, scale, rec, heads[:3])
+    dump("trace_compress.json", out)
+
+
+GENS = {"trace_compress": gen_trace_compress, "trace_hier": gen_trace_hier, "lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
         "trace_fast": gen_trace_fast, "pair_counts": gen_pair_counts, "trace_freq": gen_trace_freq}
 
 if __name__ == "__main__":
