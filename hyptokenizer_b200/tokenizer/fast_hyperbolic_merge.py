@@ -22,6 +22,7 @@ import torch
 
 from .. import _lib
 from .._lib import SEM, HypBest, check, ptr, stream_ptr
+from ..embedding import lorentz_model as LM
 from .hyperbolic_merge import HyperbolicTokenizer, _threshold_f32
 
 logger = logging.getLogger(__name__)
@@ -131,7 +132,7 @@ class FastHyperbolicTokenizer(HyperbolicTokenizer):
         od = torch.empty(total, dtype=torch.float32, device=E.device)
         if total:
             with torch.cuda.device(E.device):
-                check(_lib.lib().hyp_allpairs_emit(ptr(E), E.stride(0), n, D, float(self.curvature),
+                check(_lib.lib().hyp_allpairs_emit(ptr(E), E.stride(0), n, D, LM._curv(self.curvature),
                                                    SEM[self.semantics], thr, ptr(oi), ptr(oj), ptr(od), total,
                                                    ptr(ws["count"]), stream_ptr()))
         # (d, i, j) lexicographic == stable sort on d of the row-major list
@@ -178,7 +179,7 @@ class FastHyperbolicTokenizer(HyperbolicTokenizer):
         out = torch.empty(k, dtype=torch.float32, device=E.device)
         with torch.cuda.device(E.device):
             check(_lib.lib().hyp_rescore_pairs(ptr(E), E.stride(0), idx[0].data_ptr(), idx[1].data_ptr(), ptr(out),
-                                               None, k, E.shape[1], float(self.curvature), SEM[self.semantics],
+                                               None, k, E.shape[1], LM._curv(self.curvature), SEM[self.semantics],
                                                stream_ptr()))
         d = out.tolist()
         return {"min": min(d), "max": max(d), "mean": np.mean(d), "std": np.std(d)}

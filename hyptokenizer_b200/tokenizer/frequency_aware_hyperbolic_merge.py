@@ -18,6 +18,7 @@ import torch
 
 from .. import _lib
 from .._lib import SEM, check, ptr, stream_ptr
+from ..embedding import lorentz_model as LM
 from ..pair_count import count_pairs, count_pairs_sharded
 from .hyperbolic_merge import HyperbolicTokenizer
 
@@ -97,7 +98,7 @@ class FrequencyAwareHyperbolicTokenizer(HyperbolicTokenizer):
         with torch.cuda.device(dev):
             check(_lib.lib().hyp_coherence_distances(ptr(E), E.stride(0), ptr(d_ii), ptr(d_jj), ptr(d_li), ptr(d_lj),
                                                      ptr(d_samples), S, ptr(out), C, E.shape[1],
-                                                     float(self.curvature), SEM[self.semantics], stream_ptr()))
+                                                     LM._curv(self.curvature), SEM[self.semantics], stream_ptr()))
         dist = out.cpu().numpy()
         samp = samples.numpy()
         keep = (samp != ii.numpy()[:, None].astype(np.int64)) & (samp != jj.numpy()[:, None].astype(np.int64))

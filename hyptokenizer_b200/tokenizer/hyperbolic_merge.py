@@ -116,7 +116,7 @@ class HyperbolicTokenizer:
         E, ws = self._table(), self._workspace()
         n, D = self.current_vocab_size, E.shape[1]
         with torch.cuda.device(E.device):
-            check(_lib.lib().hyp_allpairs_min(ptr(E), E.stride(0), n, D, float(self.curvature), SEM[self.semantics],
+            check(_lib.lib().hyp_allpairs_min(ptr(E), E.stride(0), n, D, LM._curv(self.curvature), SEM[self.semantics],
                                               thr_f32, ptr(ws["best"]), ptr(ws["allpairs"]), ws["allpairs"].numel(),
                                               stream_ptr()))
         return self._read_best()
@@ -130,7 +130,7 @@ class HyperbolicTokenizer:
         n = self.current_vocab_size
         if n >= 30000 and self.semantics == "lorentz" and E.shape[1] - 1 <= 124:   # below, the exact scan is ~1-10 ms
             from ..knn import best_pair_from_topk, lorentz_topk
-            idx, d = lorentz_topk(E, 1, float(self.curvature), "lorentz", n, engine="tc")
+            idx, d = lorentz_topk(E, 1, LM._curv(self.curvature), "lorentz", n, engine="tc")
             i, j, dv = best_pair_from_topk(idx, d)
             if dv == float("inf"):
                 return HypBest(d=float("inf"), i=-1, j=-1, count_lo=0, count_hi=0)
@@ -156,7 +156,7 @@ class HyperbolicTokenizer:
         oj = torch.empty(total, dtype=torch.int32, device=E.device)
         od = torch.empty(total, dtype=torch.float32, device=E.device)
         with torch.cuda.device(E.device):
-            check(_lib.lib().hyp_allpairs_emit(ptr(E), E.stride(0), n, D, float(self.curvature), SEM[self.semantics],
+            check(_lib.lib().hyp_allpairs_emit(ptr(E), E.stride(0), n, D, LM._curv(self.curvature), SEM[self.semantics],
                                                thr, ptr(oi), ptr(oj), ptr(od), total, ptr(ws["count"]),
                                                stream_ptr()))
         order = torch.argsort(oi.to(torch.int64) * n + oj.to(torch.int64))
@@ -177,7 +177,7 @@ class HyperbolicTokenizer:
         with torch.cuda.device(E.device):
             check(_lib.lib().hyp_midpoint(ptr(E), E.stride(0), idx[0:].data_ptr(), idx[1:].data_ptr(),
                                           idx[2:].data_ptr(), idx[3:].data_ptr(), E[n].data_ptr(), D, 1, D,
-                                          float(self.curvature), SEM[self.semantics], 1, stream_ptr()))
+                                          LM._curv(self.curvature), SEM[self.semantics], 1, stream_ptr()))
         self._append_token(token_i, token_j)
 
     merge = _merge_tokens   # north-star name for the same operation
@@ -221,7 +221,7 @@ class HyperbolicTokenizer:
         hint = min(cap, n0 + max_steps)
         with torch.cuda.device(E.device):
             for s, (off, cnt) in enumerate(segs):
-                check(_lib.lib().hyp_merge_steps(ptr(E), E.stride(0), ptr(lens), D, float(self.curvature),
+                check(_lib.lib().hyp_merge_steps(ptr(E), E.stride(0), ptr(lens), D, LM._curv(self.curvature),
                                                  SEM[self.semantics], ptr(state), log[off:].data_ptr(), cnt,
                                                  step0 + off, threshold_every, float(threshold_mul), hint,
                                                  ptr(ws["loop"]), ws["loop"].numel(), stream_ptr()))

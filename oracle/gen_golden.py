@@ -40,8 +40,15 @@ import tokenizer.hierarchical_hyperbolic_merge as RHI  # noqa: E402
 import tokenizer.compression_aware_tokenizer as RCA  # noqa: E402
 import tqdm as _tqdm  # noqa: E402
 
+# EnhancedFastHyperbolicTokenizer does not import as shipped: it asks embedding.lorentz_model for two functions that
+# do not exist.  Inject placeholders (never called on the path), then import it unmodified.
+for _name in ("poincare_to_lorentz", "lorentz_to_poincare"):
+    if not hasattr(RL, _name):
+        setattr(RL, _name, lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("shim")))
+import tokenizer.enhanced_fast_hyperbolic_merge as REN  # noqa: E402
+
 # silence progress bars
-for _m in (RH, RF, RQ, RHI, RCA):
+for _m in (RH, RF, RQ, RHI, RCA, REN):
     if hasattr(_m, "tqdm"):
         _m.tqdm = lambda it, **kw: _Quiet(it)
 
@@ -95,11 +102,28 @@ _PATCH = {"distance": _lz_distance, "batch_distance": _lz_batch_distance, "log_m
           "distance_compiled": _lz_distance, "batch_distance_compiled": _lz_batch_distance}
 
 
+def _lz_distance_grad(x, y, c=1.0):
+    """_lz_distance that keeps the graph of a tensor `c` (the shipped `torch.tensor(c)` detaches it, which is why
+    the reference's curvature step raises): the one-line fix the corrected adaptive-curvature step is pinned to."""
+    u = torch.clamp(RL.minkowski_dot(x, y), min=1.0 + 1e-8)
+    cc = c if isinstance(c, torch.Tensor) else torch.tensor(c, device=x.device, dtype=x.dtype)
+    return torch.acosh(u) / torch.sqrt(cc)
+
+
 @contextlib.contextmanager
 def semantics(name: str):
     saved = []
+    if name == "lorentz+grad":
+        with semantics("lorentz"):
+            old = REN.distance
+            REN.distance = _lz_distance_grad
+            try:
+                yield
+            finally:
+                REN.distance = old
+        return
     if name == "lorentz":
-        for mod in (RL, RH, RF, RQ, RHI, RCA):
+        for mod in (RL, RH, RF, RQ, RHI, RCA, REN):
             for k, fn in _PATCH.items():
                 if hasattr(mod, k):
                     saved.append((mod, k, getattr(mod, k)))
@@ -479,7 +503,97 @@ def gen_trace_compress():
     dump("trace_compress.json", out)
 
 
-GENS = {"trace_compress": gen_trace_compress, "trace_hier": gen_trace_hier, "lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
+def gen_trace_enhanced(tmpdir="/tmp"):
+    """EnhancedFastHyperbolicTokenizer.optimize_merges (enhanced_fast_hyperbolic_merge.py:1015-1209) under the import
+    shim above, constructed directly.  Runs: all four features in the shipped arithmetic (below the first curvature
+    step, which raises as shipped -- its error text is recorded from a second short run); feature subsets in the
+    corrected geometry; and the corrected curvature step (`lorentz+grad`: `distance` keeps the graph of `c`)."""
+    assert not REN.NLTK_AVAILABLE
+    lines = hier_corpus_lines()
+    path = os.path.join(tmpdir, "hyp_golden_corpus4.txt")
+    with open(path, "w", encoding="utf-8") as f:
+        f.write("\n".join(lines) + "\n")
+    vocab = c1_vocab()
+    sample = lines[:5] + [lines[0][:20] + " shares the cache key of the first text"] + lines[5:17]
+    out = {"lines": lines, "sample": sample, "vocab0": vocab, "d": 16, "runs": []}
+    flags_all = dict(use_frequency_aware=True, use_hierarchical=True, use_adaptive_curvature=True,
+                     use_compression_aware=True)
+    runs = [
+        dict(sem="reference", scale=0.3, thr=0.5, steps=45, log_every=20, phases={2: 15, 3: 30}, flags=flags_all, kw={}),
+        dict(sem="lorentz", scale=0.02, thr=0.5, steps=60, log_every=25, phases={2: 20, 3: 40},
+             flags=dict(flags_all, use_adaptive_curvature=False), kw={}),
+        dict(sem="lorentz", scale=0.3, thr=1.3, steps=30, log_every=10, phases=None,
+             flags=dict(use_frequency_aware=True, use_hierarchical=False, use_adaptive_curvature=False,
+                        use_compression_aware=True), kw={}),
+        dict(sem="lorentz", scale=0.3, thr=1.3, steps=24, log_every=1000, phases=None,
+             flags=dict(use_frequency_aware=False, use_hierarchical=False, use_adaptive_curvature=False,
+                        use_compression_aware=True), kw=dict(adaptive_threshold=False)),
+        dict(sem="lorentz+grad", scale=0.05, thr=0.5, steps=50, log_every=1000, phases={2: 20, 3: 35},
+             flags=dict(use_frequency_aware=False, use_hierarchical=True, use_adaptive_curvature=True,
+                        use_compression_aware=False), kw={}, ctor=dict(optimize_curvature_freq=8, curvature_lr=0.05)),
+    ]
+    for r in runs:
+        set_seeds(42)
+        emb = ref_init(len(vocab), 16, r["scale"])
+        with semantics(r["sem"]):
+            tok = REN.EnhancedFastHyperbolicTokenizer(
+                vocab, torch.nn.Parameter(emb.clone()), merge_threshold=r["thr"], device=torch.device("cpu"),
+                max_vocab_size=160, use_approximate_search=False, corpus_path=path, corpus_sample=list(sample),
+                **r["flags"], **r.get("ctor", {}))
+            rec = record_merges(tok)
+            heads, curv = [], []
+            orig = tok._find_merge_candidates_fast
+
+            def spy():
+                c = orig()
+                b = c[0] if c else None
+                nn = lambda v: None if v != v else float(v)
+                heads.append([len(c), tok.merge_threshold, tok.current_phase] +
+                             ([nn(b.combined_score), b.distance, float(b.frequency_score), nn(b.semantic_score),
+                               b.compression_score, b.morphology_score] if b is not None else []))
+                return c
+
+            tok._find_merge_candidates_fast = spy
+            if r["flags"]["use_adaptive_curvature"]:
+                oc = tok._optimize_curvature
+
+                def spy_c(e):
+                    oc(e)
+                    curv.append(float(tok.curvature.item()))
+
+                tok._optimize_curvature = spy_c
+            torch.manual_seed(123)
+            random.seed(5)
+            kw = dict(r["kw"])
+            if r["phases"] is not None:
+                kw["phase_transition_steps"] = r["phases"]
+            tok.optimize_merges(steps=r["steps"], log_every=r["log_every"], **kw)
+        stats = {str(k): v for k, v in getattr(tok, "training_stats", {}).items()}
+        out["runs"].append({"semantics": r["sem"], "scale": r["scale"], "threshold0": r["thr"], "steps": r["steps"],
+                            "log_every": r["log_every"], "phases": r["phases"], "flags": r["flags"],
+                            "ctor": r.get("ctor", {}), "kw": r["kw"], "init": bits(emb), "merges_ij": rec,
+                            "heads": heads, "curvatures": curv, "stats": stats,
+                            "final_threshold": tok.merge_threshold, "final": tok_state(tok)})
+        print("enhanced", r["sem"], r["flags"], "merges", len(rec), rec[:8], "heads", len(heads), "curv", curv)
+    # the shipped curvature step: what it raises, and after how many merges
+    set_seeds(42)
+    emb = ref_init(len(vocab), 16, 0.3)
+    tok = REN.EnhancedFastHyperbolicTokenizer(vocab, torch.nn.Parameter(emb.clone()), device=torch.device("cpu"),
+                                              max_vocab_size=160, use_approximate_search=False,
+                                              use_frequency_aware=False, use_compression_aware=False,
+                                              optimize_curvature_freq=7)
+    rec = record_merges(tok)
+    try:
+        tok.optimize_merges(steps=20, log_every=1000)
+        err = None
+    except RuntimeError as e:
+        err = str(e)
+    out["shipped_curvature_step"] = {"init": bits(emb), "freq": 7, "merges_ij": rec, "error": err}
+    print("shipped curvature step:", len(rec), "merges, then", err)
+    dump("trace_enhanced.json", out)
+
+
+GENS = {"trace_enhanced": gen_trace_enhanced, "trace_compress": gen_trace_compress, "trace_hier": gen_trace_hier, "lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
         "trace_fast": gen_trace_fast, "pair_counts": gen_pair_counts, "trace_freq": gen_trace_freq}
 
 if __name__ == "__main__":

@@ -1,0 +1,127 @@
+"""Shared driver for the EnhancedFastHyperbolicTokenizer trace tests: runs one golden run of
+tests/golden/trace_enhanced.json (oracle/gen_golden.py gen_trace_enhanced, the unmodified reference under the import
+shim of SURVEY.md 8c) through a tokenizer class and compares.  Bar: identical merges, candidate counts, thresholds,
+phases, string-derived scores and vocabulary; distance-derived numbers within 1e-5 relative."""
+import math
+import random
+
+import numpy as np
+import torch
+
+from helpers import from_bits
+
+REL = 1e-5
+
+
+def close(got, want, rel=REL):
+    if want is None:
+        return got is None or got != got
+    if got is None:
+        return False
+    if isinstance(want, float) and math.isnan(want):
+        return got != got
+    return abs(got - want) <= rel * max(abs(want), 1e-30) or abs(got - want) <= 1e-7
+
+
+def run_golden(cls, gd, r, corpus_path, device=None):
+    vocab, d = gd["vocab0"], gd["d"]
+    emb = from_bits(r["init"], len(vocab), d + 1)
+    sem = "lorentz" if r["semantics"].startswith("lorentz") else "reference"
+    kw = {} if device is None else {"device": device}
+    tok = cls(vocab, torch.nn.Parameter(emb), merge_threshold=r["threshold0"], max_vocab_size=160,
+              use_approximate_search=False, corpus_path=corpus_path, corpus_sample=list(gd["sample"]),
+              semantics=sem, **r["flags"], **r["ctor"], **kw)
+    merges, heads, curv = [], [], []
+    merge, find = tok._merge_tokens, tok._find_merge_candidates_fast
+
+    def spy_merge(i, j):
+        merges.append([int(i), int(j)])
+        return merge(i, j)
+
+    def spy_find():
+        c = find()
+        b = c[0] if c else None
+        nn = lambda v: None if v != v else float(v)
+        heads.append([len(c), tok.merge_threshold, tok.current_phase] +
+                     ([nn(b.combined_score), b.distance, float(b.frequency_score), nn(b.semantic_score),
+                       b.compression_score, b.morphology_score] if b is not None else []))
+        return c
+
+    tok._merge_tokens, tok._find_merge_candidates_fast = spy_merge, spy_find
+    if r["flags"]["use_adaptive_curvature"]:
+        oc = tok._optimize_curvature
+
+        def spy_c(*a):
+            oc(*a)
+            curv.append(float(tok.curvature.item()))
+
+        tok._optimize_curvature = spy_c
+    torch.manual_seed(123)
+    random.seed(5)
+    kw = dict(r["kw"])
+    if r["phases"] is not None:
+        kw["phase_transition_steps"] = {int(k): v for k, v in r["phases"].items()}
+    tok.optimize_merges(steps=r["steps"], log_every=r["log_every"], **kw)
+    return tok, merges, heads, curv
+
+
+def check_run(tok, merges, heads, curv, gd, r):
+    d = gd["d"]
+    assert merges == r["merges_ij"]
+    assert len(heads) == len(r["heads"])
+    for step, (got, want) in enumerate(zip(heads, r["heads"])):
+        assert len(got) == len(want), step
+        assert got[0] == want[0] and got[2] == want[2], (step, got, want)            # candidates, phase
+        assert close(got[1], want[1], 1e-12), (step, got, want)                         # threshold (host floats)
+        if len(want) > 3:
+            for k in (3, 4, 6):                                                         # combined, distance, coherence
+                assert close(got[k], want[k]), (step, k, got, want)
+            for k in (5, 7, 8):                                                         # frequency, compression, morphology
+                assert close(got[k], want[k], 1e-12), (step, k, got, want)
+    assert len(curv) == len(r["curvatures"])
+    for got, want in zip(curv, r["curvatures"]):
+        assert abs(got - want) <= 1e-4 * want, (curv, r["curvatures"])
+    stats = getattr(tok, "training_stats", {})
+    assert sorted(str(k) for k in stats) == sorted(r["stats"])
+    for k, want in r["stats"].items():
+        got = stats[int(k)]
+        assert got["vocab_size"] == want["vocab_size"] and got["phase"] == want["phase"]
+        for name in ("min_dist", "max_dist", "mean_dist"):
+            assert close(float(got[name]), want[name]), (k, name, got, want)
+    assert close(tok.merge_threshold, r["final_threshold"], 1e-12)
+    fin = r["final"]
+    assert tok.current_vocab_size == fin["n"] and tok.vocab == fin["vocab"]
+    assert [list(m) for m in tok.merge_history] == fin["merges"]
+    want = from_bits(fin["embeddings"], fin["n"], d + 1).numpy()
+    got = tok.embeddings[: fin["n"]].detach().cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want).any(axis=1)
+    scale = np.abs(want[ok]).max(axis=1, keepdims=True)
+    tol = REL if not curv else 1e-4
+    assert np.all(np.abs(got[ok].astype(np.float64) - want[ok]) <= tol * scale)
+
+
+def check_save_load(cls, tok, gd, out):
+    """reference :1211-1427: file set, the full-table embeddings.pt, and a load() that gives a working object."""
+    import json
+    import os
+    tok.save(out)
+    files = set(os.listdir(out))
+    assert {"vocab.json", "embeddings.pt", "merges.json", "enhanced_config.json", "curvature.pt", "merge_pairs.pt",
+            "hierarchical_data.json", "training_stats.json"} <= files
+    saved = torch.load(f"{out}/embeddings.pt")
+    assert tuple(saved.shape) == (160, gd["d"] + 1)                   # the full table, as the reference saves it
+    cfg = json.load(open(f"{out}/enhanced_config.json"))
+    assert cfg["current_phase"] == 3 and cfg["current_vocab_size"] == tok.current_vocab_size
+    assert abs(cfg["curvature"] - float(tok.curvature.item())) < 1e-7
+    back = cls.load(out)
+    assert back.vocab == tok.vocab and back.current_vocab_size == tok.current_vocab_size
+    assert [tuple(m) for m in back.merge_history] == [tuple(m) for m in tok.merge_history]
+    assert back.current_phase == 3 and back.use_adaptive_curvature and not back.use_frequency_aware
+    assert abs(float(back.curvature.item()) - float(tok.curvature.item())) < 1e-7
+    assert [tuple(p) for p in back.merge_pairs] == [tuple(p) for p in tok.merge_pairs]
+    n = tok.current_vocab_size
+    assert torch.allclose(back.embeddings[:n].detach().cpu(), tok.embeddings[:n].detach().cpu(), rtol=1e-6, atol=0)
+    assert back.common_morphemes == tok.common_morphemes and back.common_words == tok.common_words
+    assert back.training_stats == tok.training_stats
+    assert back.tokenize("water stone") == tok.tokenize("water stone")
