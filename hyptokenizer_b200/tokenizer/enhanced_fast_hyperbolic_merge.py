@@ -19,10 +19,8 @@ arithmetic) leaves the order exactly as the reference's `list.sor
 Adaptive curvature.  As shipped, the curvature step cannot run: `distance` detaches `c` (`torch.tensor(c)`,
 reference lorentz_model.py:137), so `loss.backward()` raises at the first step that is a multiple of
 `optimize_curvature_freq` (probed).  `semantics="reference"` keeps that behaviour, error included.  In
-`semantics="lorentz"` the step is the corrected one: every distance of the two losses is
-`acosh(u) / sqrt(c)` with `acosh(u)` from ONE device re-score of all sampled pairs (K3, c = 1) and `c` a host scalar
-that autograd differentiates in closed form; the draws (`torch.randperm`, `torch.randint`) are consumed in the
-reference's order, the update is the reference's Adam step and clamp to [0.1, 10], then the table is re-projected (K1).
+`semantics="lorentz"` the step is the corrected one of `adaptive_curvature_tokenizer.CurvatureStepMixin` (SURVEY.md
+8f-4), shared with `AdaptiveCurvatureTokenizer`.
 """
 from __future__ import annotations
 
@@ -35,10 +33,9 @@ from typing import Any, Dict, List, Optional, Set, Tuple, Union
 import numpy as np
 import torch
 
-from .. import _lib
-from .._lib import SEM, check, ptr, stream_ptr
 from ..embedding import lorentz_model as LM
 from ..pair_count import count_pairs
+from .adaptive_curvature_tokenizer import CurvatureStepMixin
 from .fast_hyperbolic_merge import AdaptiveMergeCache, FastHyperbolicTokenizer, MergeCandidate
 from .frequency_aware_hyperbolic_merge import FrequencyAwareHyperbolicTokenizer as _FreqAware
 from .hierarchical_hyperbolic_merge import NLTK_AVAILABLE, HierarchicalHyperbolicTokenizer as _Hier
@@ -93,7 +90,7 @@ class _LengthIndex:
         return count
 
 
-class EnhancedFastHyperbolicTokenizer(FastHyperbolicTokenizer):
+class EnhancedFastHyperbolicTokenizer(CurvatureStepMixin, FastHyperbolicTokenizer):
     """reference enhanced_fast_hyperbolic_merge.py:66-1427."""
 
     def __init__(self, vocab: List[str], embeddings: torch.nn.Parameter,
@@ -232,98 +229,15 @@ class EnhancedFastHyperbolicTokenizer(FastHyperbolicTokenizer):
         return out
 
     # ---- adaptive curvature (reference :637-811) ---------------------------------------------------------------------
-    def _pair_acosh(self, ii: List[int], jj: List[int]) -> torch.Tensor:
-        """acosh(clamped product) of the given row pairs: one K3 launch with c = 1, back as a host fp32 tensor."""
-        E = self._table()
-        k = len(ii)
-        idx = torch.tensor([ii, jj], dtype=torch.int32).to(E.device)
-        out = torch.empty(k, dtype=torch.float32, device=E.device)
-        with torch.cuda.device(E.device):
-            check(_lib.lib().hyp_rescore_pairs(ptr(E), E.stride(0), idx[0].data_ptr(), idx[1].data_ptr(), ptr(out),
-                                               None, k, E.shape[1], 1.0, SEM[self.semantics], stream_ptr()))
-        return out.cpu()
-
-    def _draw_curvature_samples(self, n: int):
-        """The draws of reference :651-688 and :719-733, in their order: per tracked merge pair a `torch.randperm(n)`
-        head of 10 with i, j removed, then up to 500 `torch.randint` pairs (i != j kept)."""
-        hier = []
-        for i, j in self.merge_pairs[-min(len(self.merge_pairs), 100):]:
-            if i >= n or j >= n:
-                continue
-            sample = torch.randperm(n)[:min(10, n - 2)]
-            sample = sample[(sample != i) & (sample != j)].tolist()
-            if sample:
-                hier.append((i, j, sample))
-        dist_pairs = []
-        for _ in range(min(500, n * (n - 1) // 2)):
-            a, b = torch.randint(0, n, (2,)).tolist()
-            if a != b:
-                dist_pairs.append((a, b))
-        return hier, dist_pairs
-
-    def _curvature_loss(self, c: torch.Tensor, hier, hier_acosh: torch.Tensor, dist_acosh: torch.Tensor):
-        """hierarchy_weight * (:637-702) + distortion_weight * (:704-751) as a function of the scalar `c`; every
-        distance is acosh(u) / sqrt(c).  `hier_acosh` holds, per tracked pair, [pair, i-vs-samples..., j-vs-samples...]."""
-        root = torch.sqrt(c)
-        h_loss = torch.zeros((), dtype=torch.float32)
-        off = 0
-        for _, _, sample in hier:
-            m = len(sample)
-            pair = hier_acosh[off] / root
-            oi = hier_acosh[off + 1: off + 1 + m] / root
-            oj = hier_acosh[off + 1 + m: off + 1 + 2 * m] / root
-            off += 1 + 2 * m
-            h_loss = h_loss + torch.relu(pair - oi + 0.1).mean() + torch.relu(pair - oj + 0.1).mean()
-        num_pairs = min(len(self.merge_pairs), 100)
-        if num_pairs > 0:
-            h_loss = h_loss / (2 * num_pairs)
-        if len(dist_acosh):
-            d = dist_acosh / root
-            d_loss = torch.exp(-10 * d.mean()) + 0.1 * d.var()
-        else:
-            d_loss = torch.zeros((), dtype=torch.float32)
-        return self.hierarchy_weight * h_loss + self.distortion_weight * d_loss, h_loss, d_loss
-
     def _optimize_curvature(self, embeddings: Optional[torch.Tensor] = None) -> None:
         """reference :753-782.  `embeddings` is accepted for signature compatibility; the table is read in place."""
-        if not self.use_adaptive_curvature:
-            return
-        if self.semantics == "reference":
-            # the shipped step: the two losses are built from distances whose `c` is detached, so backward() has nothing
-            # to differentiate (probed on the reference: this is the error it raises at this point)
-            raise RuntimeError("element 0 of tensors does not require grad and does not have a grad_fn")
-        # the reference hands the step `self.embeddings.detach()`, the WHOLE table: its samples range over all
-        # max_vocab_size rows (unused rows are the origin after the constructor's projection)
-        n = self._table().shape[0]
-        hier, dist_pairs = self._draw_curvature_samples(n)
-        ii: List[int] = []
-        jj: List[int] = []
-        for i, j, sample in hier:
-            ii += [i] + [i] * len(sample) + [j] * len(sample)
-            jj += [j] + sample + sample
-        nh = len(ii)
-        ii += [a for a, _ in dist_pairs]
-        jj += [b for _, b in dist_pairs]
-        acosh = self._pair_acosh(ii, jj) if ii else torch.empty(0)
-        c_host = self.curvature.detach().cpu().clone().requires_grad_(True)
-        loss, h_loss, d_loss = self._curvature_loss(c_host, hier, acosh[:nh], acosh[nh:])
-        self.curvature_optimizer.zero_grad()
-        if loss.requires_grad:
-            loss.backward()
-            self.curvature.grad = c_host.grad.to(self.curvature.device)
-            self.curvature_optimizer.step()
-        with torch.no_grad():
-            self.curvature.clamp_(min=0.1, max=10.0)
-        self.last_curvature_loss = tuple(float(t.detach()) for t in (loss, h_loss, d_loss))
-        logger.info("Optimized curvature: %.4f, Loss: %.4f (H: %.4f, D: %.4f)", self.curvature.item(),
-                    *self.last_curvature_loss)
+        if self.use_adaptive_curvature:
+            self._curvature_step()
 
     def _project_embeddings(self) -> None:
         """reference :784-792 and :243: the whole `[max_vocab_size, D]` table (unused rows become the origin)."""
-        if not self.use_adaptive_curvature:
-            return
-        with torch.no_grad():
-            self.embeddings.data = LM.project_to_hyperboloid(self._table(), LM._curv(self.curvature))
+        if self.use_adaptive_curvature:
+            self._project_table()
 
     def _merge_tokens(self, i: int, j: int) -> None:
         """reference :794-809."""

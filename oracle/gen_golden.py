@@ -46,9 +46,10 @@ for _name in ("poincare_to_lorentz", "lorentz_to_poincare"):
     if not hasattr(RL, _name):
         setattr(RL, _name, lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("shim")))
 import tokenizer.enhanced_fast_hyperbolic_merge as REN  # noqa: E402
+import tokenizer.adaptive_curvature_tokenizer as RAC  # noqa: E402
 
 # silence progress bars
-for _m in (RH, RF, RQ, RHI, RCA, REN):
+for _m in (RH, RF, RQ, RHI, RCA, REN, RAC):
     if hasattr(_m, "tqdm"):
         _m.tqdm = lambda it, **kw: _Quiet(it)
 
@@ -115,15 +116,15 @@ def semantics(name: str):
     saved = []
     if name == "lorentz+grad":
         with semantics("lorentz"):
-            old = REN.distance
-            REN.distance = _lz_distance_grad
+            old = REN.distance, RAC.distance
+            REN.distance = RAC.distance = _lz_distance_grad
             try:
                 yield
             finally:
-                REN.distance = old
+                REN.distance, RAC.distance = old
         return
     if name == "lorentz":
-        for mod in (RL, RH, RF, RQ, RHI, RCA, REN):
+        for mod in (RL, RH, RF, RQ, RHI, RCA, REN, RAC):
             for k, fn in _PATCH.items():
                 if hasattr(mod, k):
                     saved.append((mod, k, getattr(mod, k)))
@@ -593,7 +594,48 @@ def gen_trace_enhanced(tmpdir="/tmp"):
     dump("trace_enhanced.json", out)
 
 
-GENS = {"trace_enhanced": gen_trace_enhanced, "trace_compress": gen_trace_compress, "trace_hier": gen_trace_hier, "lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
+def gen_trace_adaptive():
+    """AdaptiveCurvatureTokenizer.optimize_merges (adaptive_curvature_tokenizer.py:267-330) under the same import shim:
+    the shipped arithmetic below its first curvature step, the error that step raises, and the corrected step
+    (`lorentz+grad`).  The loop takes candidates[0] of the UNSORTED row-major list."""
+    vocab = c1_vocab()
+    out = {"vocab0": vocab, "d": 16, "runs": []}
+    for sem, scale, thr, steps, freq, lr in (("reference", 0.3, 0.1, 12, 100, 0.01), ("reference", 0.3, 0.1, 12, 5, 0.01),
+                                             ("lorentz+grad", 0.05, 0.3, 30, 6, 0.05), ("lorentz+grad", 0.3, 1.4, 25, 4, 0.2)):
+        set_seeds(42)
+        emb = ref_init(len(vocab), 16, scale)
+        with semantics(sem):
+            tok = RAC.AdaptiveCurvatureTokenizer(vocab, torch.nn.Parameter(emb.clone()), merge_threshold=thr,
+                                                 device=torch.device("cpu"), max_vocab_size=120, curvature_lr=lr,
+                                                 optimize_freq=freq)
+            rec = record_merges(tok)
+            curv, ncand = [], []
+            oc, of = tok._optimize_curvature, tok._find_merge_candidates
+
+            def spy_c(e):
+                oc(e)
+                curv.append(float(tok.curvature.item()))
+
+            def spy_f():
+                c = of()
+                ncand.append([len(c)] + ([c[0][0], c[0][1], fbits(c[0][2])] if c else []))
+                return c
+
+            tok._optimize_curvature, tok._find_merge_candidates = spy_c, spy_f
+            torch.manual_seed(321)
+            try:
+                tok.optimize_merges(steps=steps, log_every=10 ** 9)
+                err = None
+            except RuntimeError as e:
+                err = str(e)
+        out["runs"].append({"semantics": sem, "scale": scale, "threshold0": thr, "steps": steps, "optimize_freq": freq,
+                            "curvature_lr": lr, "init": bits(emb), "merges_ij": rec, "candidates": ncand,
+                            "curvatures": curv, "error": err, "final": tok_state(tok)})
+        print("adaptive", sem, "merges", len(rec), rec[:8], "curv", curv, "err", err)
+    dump("trace_adaptive.json", out)
+
+
+GENS = {"trace_adaptive": gen_trace_adaptive, "trace_enhanced": gen_trace_enhanced, "trace_compress": gen_trace_compress, "trace_hier": gen_trace_hier, "lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
         "trace_fast": gen_trace_fast, "pair_counts": gen_pair_counts, "trace_freq": gen_trace_freq}
 
 if __name__ == "__main__":

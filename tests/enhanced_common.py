@@ -125,3 +125,71 @@ def check_save_load(cls, tok, gd, out):
     assert back.common_morphemes == tok.common_morphemes and back.common_words == tok.common_words
     assert back.training_stats == tok.training_stats
     assert back.tokenize("water stone") == tok.tokenize("water stone")
+
+
+def run_adaptive(cls, gd, r, device=None):
+    """One run of tests/golden/trace_adaptive.json (gen_trace_adaptive) through an AdaptiveCurvatureTokenizer class."""
+    from helpers import fbits
+    vocab, d = gd["vocab0"], gd["d"]
+    emb = from_bits(r["init"], len(vocab), d + 1)
+    sem = "lorentz" if r["semantics"].startswith("lorentz") else "reference"
+    tok = cls(vocab, torch.nn.Parameter(emb), merge_threshold=r["threshold0"], max_vocab_size=120,
+              curvature_lr=r["curvature_lr"], optimize_freq=r["optimize_freq"], semantics=sem)
+    merges, curv, ncand = [], [], []
+    merge, oc, of = tok._merge_tokens, tok._optimize_curvature, tok._find_merge_candidates
+
+    def spy_merge(i, j):
+        merges.append([int(i), int(j)])
+        return merge(i, j)
+
+    def spy_c(*a):
+        oc(*a)
+        curv.append(float(tok.curvature.item()))
+
+    def spy_f():
+        c = of()
+        ncand.append([len(c)] + ([c[0][0], c[0][1], c[0][2]] if c else []))
+        return c
+
+    tok._merge_tokens, tok._optimize_curvature, tok._find_merge_candidates = spy_merge, spy_c, spy_f
+    torch.manual_seed(321)
+    err = None
+    try:
+        tok.optimize_merges(steps=r["steps"], log_every=10 ** 9)
+    except RuntimeError as e:
+        err = str(e)
+    assert err == r["error"]
+    assert merges == r["merges_ij"]
+    assert len(curv) == len(r["curvatures"])
+    for got, want in zip(curv, r["curvatures"]):
+        assert abs(got - want) <= 1e-4 * want, (curv, r["curvatures"])
+    assert len(ncand) == len(r["candidates"])
+    exact = not curv
+    for step, (got, want) in enumerate(zip(ncand, r["candidates"])):
+        assert got[:3] == want[:3], (step, got, want)                    # count and the first row-major candidate
+        if len(want) > 3:
+            wd = float(from_bits([want[3]])[0])
+            assert close(got[3], wd, REL if exact else 1e-4), (step, got, wd)
+    fin = r["final"]
+    assert tok.current_vocab_size == fin["n"] and tok.vocab == fin["vocab"]
+    want = from_bits(fin["embeddings"], fin["n"], d + 1).numpy()
+    got = tok.embeddings[: fin["n"]].detach().cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want).any(axis=1)
+    scale = np.abs(want[ok]).max(axis=1, keepdims=True)
+    assert np.all(np.abs(got[ok].astype(np.float64) - want[ok]) <= (REL if exact else 1e-4) * scale)
+    return tok
+
+
+def check_adaptive_save_load(cls, tok, out):
+    import os
+    tok.save(out)
+    assert {"vocab.json", "embeddings.pt", "curvature.pt", "merges.json", "merge_pairs.pt", "config.json"} <= set(os.listdir(out))
+    assert tuple(torch.load(f"{out}/embeddings.pt").shape) == (120, tok.embeddings.shape[1])
+    back = cls.load(out)
+    n = tok.current_vocab_size
+    assert back.vocab == tok.vocab and back.current_vocab_size == n
+    assert abs(float(back.curvature.item()) - float(tok.curvature.item())) < 1e-7
+    assert [tuple(p) for p in back.merge_pairs] == [tuple(p) for p in tok.merge_pairs]
+    assert torch.allclose(back.embeddings[:n].detach().cpu(), tok.embeddings[:n].detach().cpu(), rtol=1e-6, atol=0)
+    assert back.optimize_freq == tok.optimize_freq

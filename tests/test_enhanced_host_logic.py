@@ -12,6 +12,7 @@ from oracle import lorentz as OL
 from hyptokenizer_b200.embedding import lorentz_model as LM
 from oracle import merge as OM
 
+from hyptokenizer_b200.tokenizer import adaptive_curvature_tokenizer as PA
 from hyptokenizer_b200.tokenizer import enhanced_fast_hyperbolic_merge as PE
 from hyptokenizer_b200.tokenizer import hyperbolic_merge as PH
 
@@ -45,9 +46,34 @@ def _host_merge(self, i, j):
     self._append_token(ti, tj)
 
 
-class HostEnhanced(PE.EnhancedFastHyperbolicTokenizer):
+def _host_find(self):
+    """HyperbolicTokenizer._find_merge_candidates: row-major (i, j, d) under the threshold."""
+    n = self.current_vocab_size
+    E = self.embeddings.data[:n]
+    dist = OL.batch_distance(E, E, LM._curv(self.curvature), self.semantics)
+    thr = torch.tensor(PH._threshold_f32(self.merge_threshold, n), dtype=torch.float32)
+    keep = (dist < thr) & torch.triu(torch.ones(n, n, dtype=torch.bool), diagonal=1)
+    ii, jj = keep.nonzero(as_tuple=True)
+    return list(zip(ii.tolist(), jj.tolist(), dist[ii, jj].tolist()))
+
+
+class _HostCurvature:
     def _table(self):
         return self.embeddings.data
+
+    def _project_table(self):
+        self.embeddings.data = OL.project_to_hyperboloid(self._table(), LM._curv(self.curvature))
+
+    def _pair_acosh(self, ii, jj):
+        E = self._table()
+        return OL.distance(E[torch.tensor(ii)], E[torch.tensor(jj)], 1.0, self.semantics)
+
+
+class HostAdaptive(_HostCurvature, PA.AdaptiveCurvatureTokenizer):
+    pass
+
+
+class HostEnhanced(_HostCurvature, PE.EnhancedFastHyperbolicTokenizer):
 
     def _candidate_arrays(self):
         n = self.current_vocab_size
@@ -90,17 +116,14 @@ class HostEnhanced(PE.EnhancedFastHyperbolicTokenizer):
 
     def _project_embeddings(self):
         if self.use_adaptive_curvature:
-            self.embeddings.data = OL.project_to_hyperboloid(self._table(), LM._curv(self.curvature))
-
-    def _pair_acosh(self, ii, jj):
-        E = self._table()
-        return OL.distance(E[torch.tensor(ii)], E[torch.tensor(jj)], 1.0, self.semantics)
+            self._project_table()
 
 
 @pytest.fixture()
 def host(monkeypatch, golden, tmp_path):
     monkeypatch.setattr(PH.HyperbolicTokenizer, "__init__", _host_init)
     monkeypatch.setattr(PH.HyperbolicTokenizer, "_merge_tokens", _host_merge)
+    monkeypatch.setattr(PH.HyperbolicTokenizer, "_find_merge_candidates", _host_find)
     monkeypatch.setattr(PE, "count_pairs",
                         lambda data, device=None: OM.count_pairs_py(data.decode("utf-8").splitlines(True)))
     gd = golden("trace_enhanced.json")
@@ -159,3 +182,11 @@ def test_length_index_matches_the_reference_scan():
                 i += 1
             count += 1
         assert PE._LengthIndex(vocab).count(text, extra) == count
+
+
+@pytest.mark.parametrize("run", [0, 1, 2, 3])
+def test_adaptive_curvature_host_policy_against_reference_trace(host, golden, run, tmp_path):
+    gd = golden("trace_adaptive.json")
+    tok = EC.run_adaptive(HostAdaptive, gd, gd["runs"][run])
+    if run == 3:
+        EC.check_adaptive_save_load(HostAdaptive, tok, str(tmp_path / "saved"))

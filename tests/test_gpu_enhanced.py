@@ -75,3 +75,16 @@ def test_save_load_round_trip(corpus, tmp_path):
     gd, path = corpus
     tok, *_ = EC.run_golden(_cls(), gd, gd["runs"][4], path)
     EC.check_save_load(_cls(), tok, gd, str(tmp_path / "saved"))
+
+
+@pytest.mark.parametrize("run", [0, 1, 2, 3])
+def test_adaptive_curvature_trace(golden, run, tmp_path):
+    """AdaptiveCurvatureTokenizer (reference tokenizer/adaptive_curvature_tokenizer.py) against
+    tests/golden/trace_adaptive.json: shipped arithmetic below and at its first curvature step (which raises, as the
+    reference does), and the corrected step."""
+    from hyptokenizer_b200.tokenizer.adaptive_curvature_tokenizer import AdaptiveCurvatureTokenizer
+    gd = golden("trace_adaptive.json")
+    tok = EC.run_adaptive(AdaptiveCurvatureTokenizer, gd, gd["runs"][run])
+    assert tok.embeddings.is_cuda
+    if run == 3:
+        EC.check_adaptive_save_load(AdaptiveCurvatureTokenizer, tok, str(tmp_path / "saved"))
