@@ -68,21 +68,27 @@ def test_module_alias_drop_in():
     import hyptokenizer_b200.tokenizer as T
     for name in ("lorentz_model",):
         importlib.import_module(f"hyptokenizer_b200.embedding.{name}")
-    for name in ("hyperbolic_merge", "fast_hyperbolic_merge", "frequency_aware_hyperbolic_merge"):
+    mods = ("hyperbolic_merge", "fast_hyperbolic_merge", "frequency_aware_hyperbolic_merge",
+            "hierarchical_hyperbolic_merge", "compression_aware_tokenizer", "adaptive_curvature_tokenizer",
+            "enhanced_fast_hyperbolic_merge")
+    for name in mods:
         importlib.import_module(f"hyptokenizer_b200.tokenizer.{name}")
     saved = {k: sys.modules.get(k) for k in ("embedding", "embedding.lorentz_model", "tokenizer",
                                              "tokenizer.hyperbolic_merge", "tokenizer.fast_hyperbolic_merge",
-                                             "tokenizer.frequency_aware_hyperbolic_merge")}
+                                             *(f"tokenizer.{m}" for m in mods))}
     try:
         sys.modules["embedding"] = E
         sys.modules["embedding.lorentz_model"] = E.lorentz_model
         sys.modules["tokenizer"] = T
-        for m in ("hyperbolic_merge", "fast_hyperbolic_merge", "frequency_aware_hyperbolic_merge"):
+        for m in mods:
             sys.modules[f"tokenizer.{m}"] = getattr(T, m)
         from embedding.lorentz_model import (batch_distance, distance, exp_map, log_map, minkowski_dot,  # noqa: F401
                                              minkowski_norm, parallel_transport, project_to_hyperboloid)
         from tokenizer.fast_hyperbolic_merge import AdaptiveMergeCache, FastHyperbolicTokenizer, MergeCandidate  # noqa: F401
         from tokenizer.frequency_aware_hyperbolic_merge import FrequencyAwareHyperbolicTokenizer  # noqa: F401
+        from tokenizer.enhanced_fast_hyperbolic_merge import (EnhancedFastHyperbolicTokenizer,  # noqa: F401
+                                                              EnhancedMergeCandidate)
+        from tokenizer.adaptive_curvature_tokenizer import AdaptiveCurvatureTokenizer  # noqa: F401
         from tokenizer.hyperbolic_merge import HyperbolicTokenizer  # noqa: F401
         import inspect
         sig = inspect.signature(HyperbolicTokenizer.__init__)
