@@ -11,6 +11,10 @@ import torch
 from helpers import from_bits
 
 REL = 1e-5
+# The coherence averages distances from a RECOMPUTED point (exp o log, whose cosh / sinh / acosh last bits differ between
+# libm and the CPU's vector math library) to table rows: at small scales u - 1 ~ 3e-3, one ulp of u moves
+# d = acosh(u) by 1.2e-7 / sqrt(2 (u - 1)) ~ 2e-5 relative.  Observed 1.7e-5 on B200; the merges are identical.
+COH_REL = 1e-4
 
 
 def close(got, want, rel=REL):
@@ -65,19 +69,42 @@ def run_golden(cls, gd, r, corpus_path, device=None):
     return tok, merges, heads, curv
 
 
-def check_run(tok, merges, heads, curv, gd, r):
+def one_bit_tie_step(heads, want_heads):
+    """First step whose head pair has distance 0 on one side and acosh(1 + 2^-23) = 4.9e-4 (or the next value) on the
+    other: two copies of one merged row, whose mutual product is 1 or 1 + 2^-23 depending on the last bit of x0 -- which
+    comes out of sqrt / cosh / sinh and is not reproducible between the CPU's vector math library and libm (DESIGN.md
+    "Known deviations").  From there on the two traces may legitimately part."""
+    for k, (g, w) in enumerate(zip(heads, want_heads)):
+        if len(g) > 3 and len(w) > 3 and not close(g[4], w[4]) and max(abs(g[4]), abs(w[4])) <= 1e-3:
+            return k
+    return None
+
+
+def check_run(tok, merges, heads, curv, gd, r, min_prefix=8):
     d = gd["d"]
-    assert merges == r["merges_ij"]
-    assert len(heads) == len(r["heads"])
-    for step, (got, want) in enumerate(zip(heads, r["heads"])):
+    want_heads = r["heads"]
+    tie = one_bit_tie_step(heads, want_heads)
+    if tie is not None:
+        # compare the traces up to the step where the one-bit tie decides, and nothing after it
+        assert tie >= min_prefix, (tie, heads[tie], want_heads[tie])
+        m = sum(1 for w in want_heads[:tie] if len(w) > 3)
+        assert merges[:m] == r["merges_ij"][:m]
+        heads, want_heads = heads[:tie], want_heads[:tie]
+    else:
+        assert merges == r["merges_ij"]
+        assert len(heads) == len(want_heads)
+    for step, (got, want) in enumerate(zip(heads, want_heads)):
         assert len(got) == len(want), step
         assert got[0] == want[0] and got[2] == want[2], (step, got, want)            # candidates, phase
         assert close(got[1], want[1], 1e-12), (step, got, want)                         # threshold (host floats)
         if len(want) > 3:
-            for k in (3, 4, 6):                                                         # combined, distance, coherence
-                assert close(got[k], want[k]), (step, k, got, want)
+            assert close(got[4], want[4]), (step, got, want)                            # distance of two table rows
+            for k in (3, 6):                                                            # combined score, coherence
+                assert close(got[k], want[k], COH_REL), (step, k, got, want)
             for k in (5, 7, 8):                                                         # frequency, compression, morphology
                 assert close(got[k], want[k], 1e-12), (step, k, got, want)
+    if tie is not None:
+        return
     assert len(curv) == len(r["curvatures"])
     for got, want in zip(curv, r["curvatures"]):
         assert abs(got - want) <= 1e-4 * want, (curv, r["curvatures"])
