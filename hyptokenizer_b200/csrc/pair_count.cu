@@ -229,20 +229,25 @@ pair_count_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long lon
 // v2 removes both:
 //  * classification is SIMD-in-register over the thread's 24-byte neighbourhood: two 24-bit masks (space, line break)
 //    from carry-free byte arithmetic, and the count / resolve-slowly decisions of all 16 pairs as mask algebra;
-//  * each CTA ranks the ASCII bytes of its first window by frequency.  Pairs of the 32 most frequent symbols are
+//  * each CTA ranks the ASCII bytes of its first window by frequency.  Pairs of the 31 most frequent symbols are
 //    counted in LANE-PRIVATE one-byte counters (word-interleaved: lane t owns bank t, so a warp's 32 updates are 32
 //    plain LDS.U8 / STS.U8 with no conflicts and no atomics; a counter that wraps carries 256 into the global table),
 //    pairs within the 64 most frequent go to a CTA histogram with ATOMS, anything rarer straight to the global table.
 //    Counts stay exact for any input; the alphabet only decides how fast.
+//  * the hot loop is branch-free: a byte outside the private alphabet has private rank 31, whose row and column of
+//    the table are junk bins, and a pair that is not counted is sent to junk bin (31, 31); the byte offset of a bin
+//    is one add of two table entries, A[first byte] + B[second byte].  The only dependent chain is
+//    LDS.U8 -> +1 -> STS.U8 per pair, and a thread runs TWO 16-byte groups side by side (equal offsets forward the
+//    value in registers) so that two chains are in flight;
 //  * the stream is staged through two shared-memory windows with cp.async, the next chunk in flight while this one
-//    is counted (one CTA of 6 warps per SM: the private counters take 6 x 32 KB).
-constexpr int kV2Threads = 192;
+//    is counted (one CTA of 12 warps per SM: the private counters take 12 x 16 KB).
+constexpr int kV2Threads = 384;
 constexpr int kV2Warps = kV2Threads / 32;
-constexpr int kV2Iters = 2;
-constexpr int kV2Chunk = kV2Threads * 16 * kV2Iters;      // 6144 bytes of text per CTA iteration
+constexpr int kV2Chunk = kV2Threads * 16;                 // 6144 bytes of text per CTA iteration, one group per thread
 constexpr int kV2Win = kHalo + kV2Chunk + kHalo;          // 6272
-constexpr int kPrivPerWarp = 32 * 32 * 32;                // 1024 bins x 32 lanes x 1 byte
-constexpr size_t kV2Smem = (size_t)kV2Warps * kPrivPerWarp + 64 * 64 * 4 + 2 * kV2Win + 256 + 256 + 64;
+constexpr int kPrivPerWarp = 32 * 32 * 16;                // 1024 bins x 16 lane pairs x 1 byte
+constexpr uint32_t kJunkOff = 7u * 2048u + 31u * 64u + 3u;    // bin (31, 31)
+constexpr size_t kV2Smem = (size_t)kV2Warps * kPrivPerWarp + 64 * 64 * 4 + 512 + 512 + 256 + 256 + 64;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -263,27 +268,83 @@ __device__ __forceinline__ void classify4(uint32_t w, uint32_t &sp, uint32_t &nl
 // bits 7, 15, 23, 31 -> bits 0..3
 __device__ __forceinline__ uint32_t gather4(uint32_t m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xfu; }
 
+// byte offset of private bin (ra, rb) inside a lane pair's column: word row (ra & 7) * 32 + rb (16 words per row),
+// byte ra >> 3 of the word
+__device__ __forceinline__ uint32_t priv_off_a(uint32_t ra) { return (ra & 7u) * 2048u + (ra >> 3); }
+__device__ __forceinline__ uint32_t priv_off_b(uint32_t rb) { return rb * 64u; }
+
 struct V2Ctx {
-  uint8_t *priv_lane;            // this lane's byte column of its warp's private counters
   uint32_t *hist64;
   const uint8_t *sym;            // byte -> frequency rank 0..63, 0xff = none
   unsigned long long *ascii_counts;
-  // cold path: pairs resolved by the general scans, pairs outside the private alphabet
+  // cold path: pairs resolved by the general scans, pairs outside the private alphabet.  It never touches the private
+  // counters (a column is shared by two lanes and only the converged hot loop keeps them apart).
   __device__ __forceinline__ void add(uint32_t a, uint32_t b) const {
-    const uint32_t ra = sym[a], rb = sym[b], r = ra | rb;
-    if (ra < 31u && rb < 31u) {               // rank 31 is the junk row / column of the private table (see the hot loop)
-      const uint32_t idx = ra * 32u + rb;
-      uint8_t *p = priv_lane + (idx >> 2) * 128u + (idx & 3u);
-      const uint32_t v = (uint32_t)*p + 1u;
-      *p = (uint8_t)v;
-      if ((v & 0xffu) == 0u) atomicAdd(ascii_counts + a * 128u + b, 256ULL);
-    } else if (r < 64u) {
-      atomicAdd(&hist64[ra * 64u + rb], 1u);
-    } else {
-      atomicAdd(ascii_counts + a * 128u + b, 1ULL);
-    }
+    const uint32_t ra = sym[a], rb = sym[b];
+    if ((ra | rb) < 64u) atomicAdd(&hist64[ra * 64u + rb], 1u);
+    else atomicAdd(ascii_counts + a * 128u + b, 1ULL);
   }
 };
+
+// One 16-byte group of a thread, classified: which pairs are counted outright, which need the general scans, which
+// of the counted ones lie outside the private alphabet, and the two table entries of each of its 17 bytes.
+struct V2Group {
+  int64_t base;
+  uint32_t counted, slow, other;
+  bool general;                  // a non-ASCII byte or an end of the text in the neighbourhood: per-position path
+  uint32_t A[16], B[17];         // B[0] is unused
+};
+
+// the 24-byte neighbourhood of the group at `base` (a multiple of 16): bytes base-4 .. base+19 as six words, straight
+// from global memory (a warp reads 512 contiguous bytes; the context words hit the lines its neighbours fetch).
+// Anything that is not there -- before the text, or within 20 bytes of its end -- reads as 0x80 and sends the group
+// down the per-position path.
+__device__ __forceinline__ void v2_load(uint32_t (&W)[6], const uint8_t *__restrict__ text, int64_t n, int64_t base) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) W[k] = 0x80808080u;
+  if (base + 20 <= n) {
+    const uint4 mid = __ldg(reinterpret_cast<const uint4 *>(text + base));
+    W[1] = mid.x; W[2] = mid.y; W[3] = mid.z; W[4] = mid.w;
+    W[5] = __ldg(reinterpret_cast<const uint32_t *>(text + base + 16));
+    if (base >= 4) W[0] = __ldg(reinterpret_cast<const uint32_t *>(text + base - 4));
+  }
+}
+
+__device__ __forceinline__ void v2_prepare(V2Group &g, int64_t base, int64_t n, const uint32_t (&W)[6],
+                                           const uint16_t *tabA, const uint16_t *tabB, const uint8_t *tabF) {
+  g.base = base;
+  g.counted = g.slow = g.other = 0;
+  g.general = false;
+  if (base >= n) return;
+  if (((W[0] | W[1] | W[2] | W[3] | W[4] | W[5]) & 0x80808080u) != 0) {
+    g.general = true;
+    return;
+  }
+  uint32_t S = 0, N = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    uint32_t sp, nl;
+    classify4(W[k], sp, nl);
+    S |= gather4(sp) << (4 * k);
+    N |= gather4(nl) << (4 * k);
+  }
+  // bit q = position + 4; pair i = (byte i, byte i+1) sits at bit i + 4
+  const uint32_t valid = ~N & ~(N >> 1) & 0x000ffff0u;
+  const uint32_t left_unres = S & (S << 1) & ~(N << 1), right_unres = (S >> 1) & (S >> 2) & ~(N >> 2);
+  g.counted = (valid & (~S | ~(S << 1)) & (~(S >> 1) | ~(S >> 2))) >> 4;
+  g.slow = (valid & (left_unres | right_unres)) >> 4;
+  auto byte_at = [&](int j) -> uint32_t { return (W[(j + 4) >> 2] >> (8 * ((j + 4) & 3))) & 0xffu; };
+  uint32_t nb = 0;                           // bit 16 - j: byte j is outside the private alphabet
+#pragma unroll
+  for (int j = 0; j < 17; ++j) {
+    const uint32_t c = byte_at(j);
+    if (j < 16) g.A[j] = tabA[c];
+    if (j > 0) g.B[j] = tabB[c];
+    nb = nb * 2u + tabF[c];
+  }
+  nb = __brev(nb) >> 15;                     // bit j
+  g.other = g.counted & (nb | (nb >> 1));
+}
 
 __global__ void __launch_bounds__(kV2Threads, 1)
 pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long long *__restrict__ ascii_counts,
@@ -291,37 +352,21 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t *priv = smem_raw;                                                    // [warps][256 word rows][32 lanes][4]
   uint32_t *hist64 = reinterpret_cast<uint32_t *>(smem_raw + kV2Warps * kPrivPerWarp);   // [64*64]
-  uint8_t *win_base = reinterpret_cast<uint8_t *>(hist64 + 64 * 64);            // two windows
-  uint8_t *sym = win_base + 2 * kV2Win;                                         // byte -> frequency rank, 0xff = none
-  uint8_t *psym = sym + 256;                                                    // byte -> min(rank, 31)
-  uint8_t *inv = psym + 256;                                                    // rank -> byte
+  uint16_t *tabA = reinterpret_cast<uint16_t *>(hist64 + 64 * 64);              // byte -> priv_off_a(private rank)
+  uint16_t *tabB = tabA + 256;                                                  // byte -> priv_off_b(private rank)
+  uint8_t *tabF = reinterpret_cast<uint8_t *>(tabB + 256);                      // byte -> 1 if outside the private alphabet
+  uint8_t *sym = tabF + 256;                                                    // byte -> frequency rank, 0xff = none
+  uint8_t *inv = sym + 256;                                                     // rank -> byte
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_chunks = (n + kV2Chunk - 1) / kV2Chunk;
 
-  auto window = [&](int64_t ch, int64_t &c0, int64_t &c1, int64_t &w0, int64_t &w1) {
-    c0 = ch * kV2Chunk;
-    c1 = (c0 + kV2Chunk < n) ? c0 + kV2Chunk : n;
-    w0 = (c0 - kHalo > 0) ? c0 - kHalo : 0;
-    w1 = (c1 + kHalo < n) ? c1 + kHalo : n;
-  };
-  auto load_window = [&](uint8_t *win, int64_t ch) {
-    int64_t c0, c1, w0, w1;
-    window(ch, c0, c1, w0, w1);
-    const int nvec = (int)((w1 - w0) >> 4);
-    for (int v = tid; v < nvec; v += kV2Threads) cp_async16(win + 16 * v, text + w0 + 16 * (int64_t)v);
-    for (int b = (nvec << 4) + tid; b < (int)(w1 - w0); b += kV2Threads) win[b] = __ldg(text + w0 + b);
-  };
-
   int64_t ch = blockIdx.x;
   if (ch >= n_chunks) return;
-  load_window(win_base, ch);
-  cp_async_wait_all();
   for (int k = tid; k < 256; k += kV2Threads) hist64[k] = 0;
   __syncthreads();
-  {  // frequency ranks of the ASCII bytes of this CTA's first window
-    int64_t c0, c1, w0, w1;
-    window(ch, c0, c1, w0, w1);
-    for (int b = tid; b < (int)(w1 - w0); b += kV2Threads) atomicAdd(&hist64[win_base[b]], 1u);
+  {  // frequency ranks of the ASCII bytes of this CTA's first chunk
+    const int64_t c0 = ch * kV2Chunk, c1 = (c0 + kV2Chunk < n) ? c0 + kV2Chunk : n;
+    for (int64_t b = c0 + tid; b < c1; b += kV2Threads) atomicAdd(&hist64[__ldg(text + b)], 1u);
     __syncthreads();
     uint32_t rank = 0xffu;
     if (tid < 128 && tid != 0x0a && tid != 0x0d) {
@@ -335,10 +380,15 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
     }
     __syncthreads();
     if (tid < 128) {
+      const uint32_t pr = rank < 31u ? rank : 31u;
       sym[tid] = (uint8_t)rank;
       sym[128 + tid] = 0xff;
-      psym[tid] = (uint8_t)(rank < 31u ? rank : 31u);
-      psym[128 + tid] = 31;
+      tabA[tid] = (uint16_t)priv_off_a(pr);
+      tabB[tid] = (uint16_t)priv_off_b(pr);
+      tabF[tid] = pr == 31u;
+      tabA[128 + tid] = (uint16_t)priv_off_a(31u);
+      tabB[128 + tid] = (uint16_t)priv_off_b(31u);
+      tabF[128 + tid] = 1;
       if (rank != 0xffu) inv[rank] = (uint8_t)tid;
     }
     uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
@@ -346,113 +396,97 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
     for (int k = tid; k < nz; k += kV2Threads) z[k] = make_uint4(0, 0, 0, 0);
     __syncthreads();
   }
-  const V2Ctx ctx{priv + warp * kPrivPerWarp + lane * 4, hist64, sym, ascii_counts};
+  uint8_t *const priv_col = priv + warp * kPrivPerWarp + (lane >> 1) * 4;   // shared by lanes 2t and 2t + 1
+  const bool odd = lane & 1;
+  const V2Ctx ctx{hist64, sym, ascii_counts};
+  const Text T{text, n, nullptr, 0, 0};        // the cold paths read the text from global memory (L1)
 
-  int buf = 0;
-  for (; ch < n_chunks; ch += gridDim.x) {
-    const uint8_t *win = win_base + buf * kV2Win;
-    if (ch + gridDim.x < n_chunks) load_window(win_base + (buf ^ 1) * kV2Win, ch + gridDim.x);
-    int64_t c0, c1, w0, w1;
-    window(ch, c0, c1, w0, w1);
-    Text T{text, n, win, w0, w1};
-#pragma unroll 1
-    for (int it = 0; it < kV2Iters; ++it) {
-      const int64_t base = c0 + 16 * (int64_t)(tid + it * kV2Threads);
-      if (base >= c1) break;
-      uint32_t W[6];
-      {
-        const uint4 mid = *reinterpret_cast<const uint4 *>(win + (base - w0));
-        W[1] = mid.x; W[2] = mid.y; W[3] = mid.z; W[4] = mid.w;
-        W[0] = (base - 4 >= w0) ? *reinterpret_cast<const uint32_t *>(win + (base - 4 - w0)) : 0x80808080u;
-        W[5] = (base + 20 <= w1) ? *reinterpret_cast<const uint32_t *>(win + (base + 16 - w0)) : 0x80808080u;
+  // No barrier in the main loop: every warp streams its own 512 bytes per step, the next step's words in flight
+  // while this step is counted.
+  const int64_t step = (int64_t)gridDim.x * kV2Chunk;
+  int64_t base = ch * kV2Chunk + 16 * (int64_t)tid;
+  uint32_t Wn[6];
+  v2_load(Wn, text, n, base);
+  for (; ch < n_chunks; ch += gridDim.x, base += step) {
+    uint32_t W[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) W[k] = Wn[k];
+    if (ch + gridDim.x < n_chunks) v2_load(Wn, text, n, base + step);
+
+    V2Group g;
+    v2_prepare(g, base, n, W, tabA, tabB, tabF);
+
+    // Hot loop, executed by the whole warp (groups with nothing to count walk the junk bin): one LDS.U8 -> +1 -> STS.U8
+    // per pair, in two phases because a column of counters belongs to a PAIR of lanes -- even lanes update while odd
+    // lanes walk the junk bin, then the other way round.
+    uint32_t wrap = 0;                         // bit 15 - i: the counter of pair i passed 255
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t o = ((g.counted >> i) & 1u) ? g.A[i] + g.B[i + 1] : kJunkOff;
+      uint8_t *pe = priv_col + (odd ? kJunkOff : o), *po = priv_col + (odd ? o : kJunkOff);
+      const uint32_t ve = (uint32_t)*pe + 1u;
+      *pe = (uint8_t)ve;
+      __syncwarp();
+      const uint32_t vo = (uint32_t)*po + 1u;
+      *po = (uint8_t)vo;
+      __syncwarp();
+      wrap = wrap * 2u + ((odd ? vo : ve) >> 8);
+    }
+
+    // Cold paths.
+    {
+      uint32_t wrapped = (__brev(wrap) >> 16) & g.counted & ~g.other;
+      while (wrapped) {                          // a private counter passed 255: carry into the global table
+        const int i = __ffs(wrapped) - 1;
+        wrapped &= wrapped - 1;
+        atomicAdd(ascii_counts + T.at(base + i) * 128u + T.at(base + i + 1), 256ULL);
       }
-      // groups at either end of the text, or with a non-ASCII byte in their 24-byte neighbourhood, go slow
-      if (((W[0] | W[1] | W[2] | W[3] | W[4] | W[5]) & 0x80808080u) == 0) {
-        uint32_t S = 0, N = 0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          uint32_t sp, nl;
-          classify4(W[k], sp, nl);
-          S |= gather4(sp) << (4 * k);
-          N |= gather4(nl) << (4 * k);
-        }
-        // bit q = position + 4; pair i = (byte i, byte i+1) sits at bit i + 4
-        const uint32_t valid = ~N & ~(N >> 1) & 0x000ffff0u;
-        const uint32_t left_unres = S & (S << 1) & ~(N << 1), right_unres = (S >> 1) & (S >> 2) & ~(N >> 2);
-        const uint32_t fast = valid & (~S | ~(S << 1)) & (~(S >> 1) | ~(S >> 2));
-        uint32_t slow = (valid & (left_unres | right_unres)) >> 4;
-        auto byte_at = [&](int j) -> uint32_t { return (W[(j + 4) >> 2] >> (8 * ((j + 4) & 3))) & 0xffu; };
-        // Hot loop, branch-free: pr = private rank 0..30, or 31 for every byte outside the private alphabet, so that
-        // pr_a * 32 + pr_b lands in a junk bin (row or column 31) by itself; pairs that are not counted are sent to
-        // junk bin 1023.  One dependent LDS.U8 -> +1 -> STS.U8 per pair; everything else is independent of that chain.
-        uint32_t pr[17];
-#pragma unroll
-        for (int j = 0; j < 17; ++j) pr[j] = psym[byte_at(j)];
-        uint32_t nb = 0;                           // bit j: byte j is outside the private alphabet
-#pragma unroll
-        for (int j = 0; j < 17; ++j) nb |= ((pr[j] + 1u) >> 5) << j;
-        const uint32_t counted = fast >> 4;
-        uint32_t other = counted & (nb | (nb >> 1));
-        uint32_t wrapped = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint32_t idx = ((counted >> i) & 1u) ? pr[i] * 32u + pr[i + 1] : 1023u;
-          uint8_t *p = ctx.priv_lane + (idx >> 2) * 128u + (idx & 3u);
-          const uint32_t v = (uint32_t)*p + 1u;
-          *p = (uint8_t)v;
-          wrapped |= (v >> 8) << i;
-        }
-        wrapped &= counted & ~other;
-        while (wrapped) {                          // a private counter passed 255: carry into the global table
-          const int i = __ffs(wrapped) - 1;
-          wrapped &= wrapped - 1;
-          atomicAdd(ascii_counts + (uint32_t)win[base + i - w0] * 128u + win[base + i + 1 - w0], 256ULL);
-        }
-        while (other) {                            // counted pairs outside the private alphabet
-          const int i = __ffs(other) - 1;
-          other &= other - 1;
-          ctx.add(win[base + i - w0], win[base + i + 1 - w0]);
-        }
-        while (slow) {
-          // a run of spaces next to the pair: resolve with the general scans
-          const int i = __ffs(slow) - 1;
-          slow &= slow - 1;
-          const int64_t pp = base + i;
-          const uint32_t a = win[pp - w0], bch = win[pp + 1 - w0];
-          auto sp = [&](uint32_t c) -> bool { return (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x20); };
-          bool left = !sp(a), right = !sp(bch);
-          if (!left) {
-            int64_t q = pp - 1;
-            while (q >= 0) {
-              const uint32_t cq = T.at(q);
-              if (cq >= 0x80) {
-                int l2;
-                const int64_t qs = T.is_start(q) ? q : T.prev_start(q);
-                const uint32_t cp = T.decode(qs, l2);
-                if (!is_space(cp)) { left = true; break; }
-                q = qs - 1;
-                continue;
-              }
-              if (is_nl(cq)) break;
-              if (!sp(cq)) { left = true; break; }
-              --q;
-            }
-          }
-          if (left && !right) {
-            int64_t q = pp + 2;
-            while (q < n) {
+      uint32_t other = g.other;
+      while (other) {                            // counted pairs outside the private alphabet
+        const int i = __ffs(other) - 1;
+        other &= other - 1;
+        ctx.add(T.at(base + i), T.at(base + i + 1));
+      }
+      uint32_t slow = g.slow;
+      while (slow) {
+        // a run of spaces next to the pair: resolve with the general scans
+        const int i = __ffs(slow) - 1;
+        slow &= slow - 1;
+        const int64_t pp = base + i;
+        const uint32_t a = T.at(pp), bch = T.at(pp + 1);
+        auto sp = [&](uint32_t c) -> bool { return (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x20); };
+        bool left = !sp(a), right = !sp(bch);
+        if (!left) {
+          int64_t q = pp - 1;
+          while (q >= 0) {
+            const uint32_t cq = T.at(q);
+            if (cq >= 0x80) {
               int l2;
-              const uint32_t cq = T.decode(q, l2);
-              if (is_nl(cq)) break;
-              if (!is_space(cq)) { right = true; break; }
-              q += l2;
+              const int64_t qs = T.is_start(q) ? q : T.prev_start(q);
+              const uint32_t cp = T.decode(qs, l2);
+              if (!is_space(cp)) { left = true; break; }
+              q = qs - 1;
+              continue;
             }
+            if (is_nl(cq)) break;
+            if (!sp(cq)) { left = true; break; }
+            --q;
           }
-          if (left && right) ctx.add(a, bch);
         }
-        continue;
+        if (left && !right) {
+          int64_t q = pp + 2;
+          while (q < n) {
+            int l2;
+            const uint32_t cq = T.decode(q, l2);
+            if (is_nl(cq)) break;
+            if (!is_space(cq)) { right = true; break; }
+            q += l2;
+          }
+        }
+        if (left && right) ctx.add(a, bch);
       }
-      const int64_t p_end = (base + 16 < c1) ? base + 16 : c1;
+      if (g.general) {
+      const int64_t p_end = (base + 16 < n) ? base + 16 : n;
       for (int64_t p = base; p < p_end; ++p) {
         if (!T.is_start(p)) continue;
         int la, lb;
@@ -489,23 +523,22 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
         if (a < 128 && b < 128) ctx.add(a, b);
         else hash_add(hkeys, hvals, cap_mask, ((unsigned long long)a << 32) | b, overflow);
       }
+      }
     }
-    cp_async_wait_all();
-    __syncthreads();
-    buf ^= 1;
   }
+  __syncthreads();
 
-  // flush: private counters (sum over the warp's 32 lanes per bin), then the CTA histogram
+  // flush: private counters (sum over the warp's 16 columns per bin), then the CTA histogram
   const uint32_t *rows = reinterpret_cast<const uint32_t *>(priv + warp * kPrivPerWarp);
   for (int g = 0; g < 256; ++g) {
-    const uint32_t w = rows[g * 32 + lane];
+    const uint32_t w = lane < 16 ? rows[g * 16 + lane] : 0u;
     const uint32_t s0 = __reduce_add_sync(HYP_FULL_MASK, w & 0xffu), s1 = __reduce_add_sync(HYP_FULL_MASK, (w >> 8) & 0xffu);
     const uint32_t s2 = __reduce_add_sync(HYP_FULL_MASK, (w >> 16) & 0xffu), s3 = __reduce_add_sync(HYP_FULL_MASK, w >> 24);
     if (lane < 4) {
       const uint32_t s = lane == 0 ? s0 : lane == 1 ? s1 : lane == 2 ? s2 : s3;
-      const uint32_t idx = g * 4 + lane;
-      if (s && (idx >> 5) != 31u && (idx & 31u) != 31u)
-        atomicAdd(ascii_counts + (uint32_t)inv[idx >> 5] * 128u + inv[idx & 31u], (unsigned long long)s);
+      const uint32_t ra = (uint32_t)(g >> 5) + 8u * lane, rb = g & 31;      // row (ra & 7) * 32 + rb, byte ra >> 3
+      if (s && ra != 31u && rb != 31u)
+        atomicAdd(ascii_counts + (uint32_t)inv[ra] * 128u + inv[rb], (unsigned long long)s);
     }
   }
   for (int k = tid; k < 64 * 64; k += kV2Threads) {
