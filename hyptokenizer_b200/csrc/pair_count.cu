@@ -315,6 +315,8 @@ __device__ __forceinline__ void v2_prepare(V2Group &g, int64_t base, int64_t n, 
   g.base = base;
   g.counted = g.slow = g.other = 0;
   g.general = false;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) g.A[j] = g.B[j + 1] = 0;
   if (base >= n) return;
   if (((W[0] | W[1] | W[2] | W[3] | W[4] | W[5]) & 0x80808080u) != 0) {
     g.general = true;
@@ -419,23 +421,28 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
     // Hot loop, executed by the whole warp (groups with nothing to count walk the junk bin): one LDS.U8 -> +1 -> STS.U8
     // per pair, in two phases because a column of counters belongs to a PAIR of lanes -- even lanes update while odd
     // lanes walk the junk bin, then the other way round.
-    uint32_t wrap = 0;                         // bit 15 - i: the counter of pair i passed 255
+    // (A lane that has nothing to add in a phase issues nothing: the RMW is predicated, not redirected.)
+    const uint32_t mine_e = odd ? 0u : g.counted, mine_o = odd ? g.counted : 0u;
+    uint32_t wacc[4] = {0, 0, 0, 0};           // byte 3 - (i & 3) of wacc[i >> 2]: 1 if the counter of pair i passed 255
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const uint32_t o = ((g.counted >> i) & 1u) ? g.A[i] + g.B[i + 1] : kJunkOff;
-      uint8_t *pe = priv_col + (odd ? kJunkOff : o), *po = priv_col + (odd ? o : kJunkOff);
-      const uint32_t ve = (uint32_t)*pe + 1u;
-      *pe = (uint8_t)ve;
+      uint8_t *p = priv_col + (g.A[i] + g.B[i + 1]);
+      uint32_t v = 0;
+      if ((mine_e >> i) & 1u) { v = (uint32_t)*p + 1u; *p = (uint8_t)v; }
       __syncwarp();
-      const uint32_t vo = (uint32_t)*po + 1u;
-      *po = (uint8_t)vo;
+      if ((mine_o >> i) & 1u) { v = (uint32_t)*p + 1u; *p = (uint8_t)v; }
       __syncwarp();
-      wrap = wrap * 2u + ((odd ? vo : ve) >> 8);
+      wacc[i >> 2] = __byte_perm(wacc[i >> 2], v, 0x2105);
+    }
+    uint32_t wrap = 0;                         // bit i: the counter of pair i passed 255
+    if (wacc[0] | wacc[1] | wacc[2] | wacc[3]) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wrap |= ((wacc[i >> 2] >> (8 * (3 - (i & 3)))) & 1u) << i;
     }
 
     // Cold paths.
     {
-      uint32_t wrapped = (__brev(wrap) >> 16) & g.counted & ~g.other;
+      uint32_t wrapped = wrap & ~g.other;
       while (wrapped) {                          // a private counter passed 255: carry into the global table
         const int i = __ffs(wrapped) - 1;
         wrapped &= wrapped - 1;
