@@ -247,7 +247,7 @@ constexpr int kV2Chunk = kV2Threads * 16;                 // 6144 bytes of text 
 constexpr int kV2Win = kHalo + kV2Chunk + kHalo;          // 6272
 constexpr int kPrivPerWarp = 32 * 32 * 16;                // 1024 bins x 16 lane pairs x 1 byte
 constexpr uint32_t kJunkOff = 7u * 2048u + 31u * 64u + 3u;    // bin (31, 31)
-constexpr size_t kV2Smem = (size_t)kV2Warps * kPrivPerWarp + 64 * 64 * 4 + 512 + 512 + 256 + 256 + 64;
+constexpr size_t kV2Smem = (size_t)kV2Warps * kPrivPerWarp + 64 * 64 * 4 + 512 + 512 + 1024 + 256 + 64;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -311,7 +311,7 @@ __device__ __forceinline__ void v2_load(uint32_t (&W)[6], const uint8_t *__restr
 }
 
 __device__ __forceinline__ void v2_prepare(V2Group &g, int64_t base, int64_t n, const uint32_t (&W)[6],
-                                           const uint16_t *tabA, const uint16_t *tabB, const uint8_t *tabF) {
+                                           const uint16_t *tabA, const uint16_t *tabB, const uint32_t *tabC) {
   g.base = base;
   g.counted = g.slow = g.other = 0;
   g.general = false;
@@ -322,30 +322,27 @@ __device__ __forceinline__ void v2_prepare(V2Group &g, int64_t base, int64_t n, 
     g.general = true;
     return;
   }
-  uint32_t S = 0, N = 0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    uint32_t sp, nl;
-    classify4(W[k], sp, nl);
-    S |= gather4(sp) << (4 * k);
-    N |= gather4(nl) << (4 * k);
-  }
-  // bit q = position + 4; pair i = (byte i, byte i+1) sits at bit i + 4
-  const uint32_t valid = ~N & ~(N >> 1) & 0x000ffff0u;
-  const uint32_t left_unres = S & (S << 1) & ~(N << 1), right_unres = (S >> 1) & (S >> 2) & ~(N >> 2);
-  g.counted = (valid & (~S | ~(S << 1)) & (~(S >> 1) | ~(S >> 2))) >> 4;
-  g.slow = (valid & (left_unres | right_unres)) >> 4;
+  // Classification by table: tabC[byte] = space | line break << 10 | outside the private alphabet << 20, and
+  // acc = 2 acc + tabC[byte] over positions 8 .. -1 (and 17 .. 9) leaves three 10-bit planes, position -1 (9) at bit 0.
   auto byte_at = [&](int j) -> uint32_t { return (W[(j + 4) >> 2] >> (8 * ((j + 4) & 3))) & 0xffu; };
-  uint32_t nb = 0;                           // bit 16 - j: byte j is outside the private alphabet
+  uint32_t lo = 0, hi = 0;
 #pragma unroll
-  for (int j = 0; j < 17; ++j) {
+  for (int j = 17; j >= -1; --j) {
     const uint32_t c = byte_at(j);
-    if (j < 16) g.A[j] = tabA[c];
-    if (j > 0) g.B[j] = tabB[c];
-    nb = nb * 2u + tabF[c];
+    if (j >= 0 && j < 16) g.A[j] = tabA[c];
+    if (j >= 1 && j < 17) g.B[j] = tabB[c];
+    if (j >= 9) hi = hi * 2u + tabC[c];
+    else lo = lo * 2u + tabC[c];
   }
-  nb = __brev(nb) >> 15;                     // bit j
-  g.other = g.counted & (nb | (nb >> 1));
+  // bit k of a plane = position k - 1; pair i = (byte i, byte i + 1): prev at bit i, a at i + 1, b at i + 2, next at i + 3
+  const uint32_t S = (lo & 0x3ffu) | ((hi & 0x1ffu) << 10);
+  const uint32_t N = ((lo >> 10) & 0x3ffu) | (((hi >> 10) & 0x1ffu) << 10);
+  const uint32_t P = ((lo >> 20) & 0x3ffu) | (((hi >> 20) & 0x1ffu) << 10);
+  const uint32_t valid = ~((N >> 1) | (N >> 2)) & 0xffffu;
+  const uint32_t left_unres = (S >> 1) & S & ~N, right_unres = (S >> 2) & (S >> 3) & ~(N >> 3);
+  g.counted = valid & (~(S >> 1) | ~S) & (~(S >> 2) | ~(S >> 3));
+  g.slow = valid & (left_unres | right_unres);
+  g.other = g.counted & ((P >> 1) | (P >> 2));
 }
 
 __global__ void __launch_bounds__(kV2Threads, 1)
@@ -356,8 +353,8 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
   uint32_t *hist64 = reinterpret_cast<uint32_t *>(smem_raw + kV2Warps * kPrivPerWarp);   // [64*64]
   uint16_t *tabA = reinterpret_cast<uint16_t *>(hist64 + 64 * 64);              // byte -> priv_off_a(private rank)
   uint16_t *tabB = tabA + 256;                                                  // byte -> priv_off_b(private rank)
-  uint8_t *tabF = reinterpret_cast<uint8_t *>(tabB + 256);                      // byte -> 1 if outside the private alphabet
-  uint8_t *sym = tabF + 256;                                                    // byte -> frequency rank, 0xff = none
+  uint32_t *tabC = reinterpret_cast<uint32_t *>(tabB + 256);                    // byte -> class bits, see v2_prepare
+  uint8_t *sym = reinterpret_cast<uint8_t *>(tabC + 256);                                                    // byte -> frequency rank, 0xff = none
   uint8_t *inv = sym + 256;                                                     // rank -> byte
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t n_chunks = (n + kV2Chunk - 1) / kV2Chunk;
@@ -387,10 +384,12 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
       sym[128 + tid] = 0xff;
       tabA[tid] = (uint16_t)priv_off_a(pr);
       tabB[tid] = (uint16_t)priv_off_b(pr);
-      tabF[tid] = pr == 31u;
+      const uint32_t t = tid;
+      const uint32_t is_sp = (t >= 0x09 && t <= 0x0d) || (t >= 0x1c && t <= 0x20), is_br = t == 0x0a || t == 0x0d;
+      tabC[tid] = is_sp | (is_br << 10) | ((pr == 31u ? 1u : 0u) << 20);
       tabA[128 + tid] = (uint16_t)priv_off_a(31u);
       tabB[128 + tid] = (uint16_t)priv_off_b(31u);
-      tabF[128 + tid] = 1;
+      tabC[128 + tid] = 1u << 20;
       if (rank != 0xffu) inv[rank] = (uint8_t)tid;
     }
     uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
@@ -416,7 +415,7 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
     if (ch + gridDim.x < n_chunks) v2_load(Wn, text, n, base + step);
 
     V2Group g;
-    v2_prepare(g, base, n, W, tabA, tabB, tabF);
+    v2_prepare(g, base, n, W, tabA, tabB, tabC);
 
     // Hot loop, executed by the whole warp (groups with nothing to count walk the junk bin): one LDS.U8 -> +1 -> STS.U8
     // per pair, in two phases because a column of counters belongs to a PAIR of lanes -- even lanes update while odd
@@ -427,12 +426,12 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       uint8_t *p = priv_col + (g.A[i] + g.B[i + 1]);
-      uint32_t v = 0;
-      if ((mine_e >> i) & 1u) { v = (uint32_t)*p + 1u; *p = (uint8_t)v; }
+      uint32_t l = 0;                          // the counter before this lane's +1
+      if ((mine_e >> i) & 1u) { l = *p; *p = (uint8_t)(l + 1u); }
       __syncwarp();
-      if ((mine_o >> i) & 1u) { v = (uint32_t)*p + 1u; *p = (uint8_t)v; }
+      if ((mine_o >> i) & 1u) { l = *p; *p = (uint8_t)(l + 1u); }
       __syncwarp();
-      wacc[i >> 2] = __byte_perm(wacc[i >> 2], v, 0x2105);
+      wacc[i >> 2] = __byte_perm(wacc[i >> 2], l + 1u, 0x2105);
     }
     uint32_t wrap = 0;                         // bit i: the counter of pair i passed 255
     if (wacc[0] | wacc[1] | wacc[2] | wacc[3]) {
