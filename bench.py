@@ -528,7 +528,7 @@ def run_c4(a):
             "config": {"workload": "c4 (pair-count part): 1 GiB ASCII stream per GPU, lines of 20 random words; input "
                                    "larger than L2" + ("; histograms summed with one all_reduce per step" if world > 1 else ""),
                        "distinct_pairs": len(counts), "total_pairs": int(sum(counts.values()))},
-            "gpu_launches": a.steps, "roofline": {"bound": "hbm", "kernel": "pair_count_kernel", "achieved": kgbs,
+            "gpu_launches": a.steps, "roofline": {"bound": "hbm", "kernel": "pair_count_v2_kernel" if os.environ.get("HYP_PAIR_COUNT", "v2") != "v1" else "pair_count_kernel", "achieved": kgbs,
                                                   "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": kgbs / pk["hbm_gbs"],
                                                   "traffic": None, "peak_kind": kind},
             "clocks": clocks,

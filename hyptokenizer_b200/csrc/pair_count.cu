@@ -8,9 +8,10 @@
 // removed.  A pair (a, b) at consecutive positions of one line is therefore counted iff some
 // non-space character sits at or before `a` in that line and some non-space sits at or after `b`.
 //
-// HBM-bound integer/byte work: the stream is read once in 16-byte vectors into shared memory,
-// ASCII pairs go to a CTA-private 128x128 shared-memory histogram (flushed once), everything else
-// to a global open-addressing table keyed by (cp_a << 32 | cp_b).
+// HBM-bound integer/byte work, two kernels with identical results.  v1 (kept, HYP_PAIR_COUNT=v1): the stream is read
+// once in 16-byte vectors into shared memory, ASCII pairs go to a CTA-private 128x128 shared-memory histogram with
+// atomics (flushed once).  v2 (default, further down): private non-atomic counters for the frequent symbols.  In both,
+// pairs with a non-ASCII code point go to a global open-addressing table keyed by (cp_a << 32 | cp_b).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -225,48 +226,33 @@ pair_count_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long lon
 // v2: lane-private counters.
 //
 // v1 above retires one shared-memory atomic per input byte, and ATOMS runs at ~1 lane per clock per SM on this part:
-// 148 SMs x 1.97 GHz = the 312 GB/s it measures, with 80 thread instructions per byte of per-position branching on top.
-// v2 removes both:
-//  * classification is SIMD-in-register over the thread's 24-byte neighbourhood: two 24-bit masks (space, line break)
-//    from carry-free byte arithmetic, and the count / resolve-slowly decisions of all 16 pairs as mask algebra;
-//  * each CTA ranks the ASCII bytes of its first window by frequency.  Pairs of the 31 most frequent symbols are
-//    counted in LANE-PRIVATE one-byte counters (word-interleaved: lane t owns bank t, so a warp's 32 updates are 32
-//    plain LDS.U8 / STS.U8 with no conflicts and no atomics; a counter that wraps carries 256 into the global table),
-//    pairs within the 64 most frequent go to a CTA histogram with ATOMS, anything rarer straight to the global table.
-//    Counts stay exact for any input; the alphabet only decides how fast.
-//  * the hot loop is branch-free: a byte outside the private alphabet has private rank 31, whose row and column of
-//    the table are junk bins, and a pair that is not counted is sent to junk bin (31, 31); the byte offset of a bin
-//    is one add of two table entries, A[first byte] + B[second byte].  The only dependent chain is
-//    LDS.U8 -> +1 -> STS.U8 per pair, and a thread runs TWO 16-byte groups side by side (equal offsets forward the
-//    value in registers) so that two chains are in flight;
-//  * the stream is staged through two shared-memory windows with cp.async, the next chunk in flight while this one
-//    is counted (one CTA of 12 warps per SM: the private counters take 12 x 16 KB).
+// 148 SMs x 1.97 GHz = the ~310 GB/s it measures, with 80 thread instructions per byte of per-position branching on top.
+// v2 removes both (487 GB/s on the same stream):
+//  * each CTA ranks the ASCII bytes of its first chunk by frequency.  Pairs of the 31 most frequent symbols are
+//    counted in PRIVATE one-byte counters, one column of 1024 bins per PAIR of lanes, word-interleaved so that column
+//    c of a warp lives in bank c: an update is a plain LDS.U8 / +1 / STS.U8, no atomics and no bank conflicts, in two
+//    predicated phases (even lanes, then odd lanes) because two lanes share a column.  A counter that wraps carries
+//    256 into the global table.  Pairs within the 64 most frequent symbols go to a CTA histogram with ATOMS, anything
+//    rarer straight to the global table.  Counts stay exact for any input; the alphabet only decides how fast.
+//  * the hot loop has no data-dependent branch: a byte outside the private alphabet has private rank 31, whose row
+//    and column of the table are junk bins; the byte offset of a bin is one add of two table entries,
+//    A[first byte] + B[second byte]; pairs that are not counted are predicated off;
+//  * classification is by table as well: C[byte] carries "space", "line break" and "outside the private alphabet" in
+//    three 10-bit planes, and acc = 2 acc + C[byte] over the thread's 19-byte neighbourhood yields the three position
+//    masks with one IMAD per byte; the count / resolve-slowly decisions of all 16 pairs are mask algebra;
+//  * no barrier in the main loop: a thread reads its 16 bytes (+ 4 of context on either side) straight from global
+//    memory, a warp 512 contiguous bytes, the next step's words in flight while this step is counted.  One CTA of 12
+//    warps per SM (the private counters take 12 x 16 KB of its shared memory).
+// What was measured on the way (B200, 256 MiB of the config-4 stream): lane-private columns with 6 warps 240 GB/s
+// (latency-bound, every pair a chain of dependent branches) -> branch-free 398 -> two groups per thread side by side
+// 383 (no gain: not the chain) -> lane-pair columns + 12 warps, still staged through shared-memory windows 361 (one
+// barrier per 512 bytes per warp) -> barrier-free 438 -> predicated phases 454 -> table classification 487.  ncu at
+// that point: ~435 warp instructions per 512 bytes, issue slots ~55 % busy, stalls on the LDS -> +1 dependency.
 constexpr int kV2Threads = 384;
 constexpr int kV2Warps = kV2Threads / 32;
 constexpr int kV2Chunk = kV2Threads * 16;                 // 6144 bytes of text per CTA iteration, one group per thread
-constexpr int kV2Win = kHalo + kV2Chunk + kHalo;          // 6272
 constexpr int kPrivPerWarp = 32 * 32 * 16;                // 1024 bins x 16 lane pairs x 1 byte
-constexpr uint32_t kJunkOff = 7u * 2048u + 31u * 64u + 3u;    // bin (31, 31)
 constexpr size_t kV2Smem = (size_t)kV2Warps * kPrivPerWarp + 64 * 64 * 4 + 512 + 512 + 1024 + 256 + 64;
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-}
-
-// four bytes (all < 0x80) -> bit 7 of each byte set where the byte is an ASCII space (9..13, 28..32) / a line break
-__device__ __forceinline__ void classify4(uint32_t w, uint32_t &sp, uint32_t &nl) {
-  const uint32_t ge9 = w + 0x77777777u, ge14 = w + 0x72727272u, ge28 = w + 0x64646464u, ge33 = w + 0x5f5f5f5fu;
-  sp = ((ge9 & ~ge14) | (ge28 & ~ge33)) & 0x80808080u;
-  const uint32_t ne10 = (w ^ 0x0a0a0a0au) + 0x7f7f7f7fu, ne13 = (w ^ 0x0d0d0d0du) + 0x7f7f7f7fu;
-  nl = ~(ne10 & ne13) & 0x80808080u;
-}
-// bits 7, 15, 23, 31 -> bits 0..3
-__device__ __forceinline__ uint32_t gather4(uint32_t m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xfu; }
 
 // byte offset of private bin (ra, rb) inside a lane pair's column: word row (ra & 7) * 32 + rb (16 words per row),
 // byte ra >> 3 of the word
@@ -417,10 +403,9 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
     V2Group g;
     v2_prepare(g, base, n, W, tabA, tabB, tabC);
 
-    // Hot loop, executed by the whole warp (groups with nothing to count walk the junk bin): one LDS.U8 -> +1 -> STS.U8
-    // per pair, in two phases because a column of counters belongs to a PAIR of lanes -- even lanes update while odd
-    // lanes walk the junk bin, then the other way round.
-    // (A lane that has nothing to add in a phase issues nothing: the RMW is predicated, not redirected.)
+    // Hot loop, executed by the whole (converged) warp: one LDS.U8 -> +1 -> STS.U8 per pair, in two phases because a
+    // column of counters belongs to a PAIR of lanes -- even lanes update, then odd lanes.  A lane that has nothing to
+    // add in a phase issues nothing: the RMW is predicated.  __syncwarp orders the phases for the compiler too.
     const uint32_t mine_e = odd ? 0u : g.counted, mine_o = odd ? g.counted : 0u;
     uint32_t wacc[4] = {0, 0, 0, 0};           // byte 3 - (i & 3) of wacc[i >> 2]: 1 if the counter of pair i passed 255
 #pragma unroll
@@ -580,7 +565,7 @@ extern "C" int hyp_pair_count(const uint8_t *text, int64_t n_bytes, unsigned lon
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   static const int variant = [] {
     const char *e = getenv("HYP_PAIR_COUNT");
-    return (e && e[0] == 'v' && e[1] == '2') ? 2 : 1;
+    return (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;     // HYP_PAIR_COUNT=v1 selects the atomics-only kernel
   }();
   if (variant == 2) {
     static bool attr2 = false;

@@ -47,15 +47,53 @@ def test_edge_cases(case):
     assert count_pairs(text.encode("utf-8")) == count_pairs_py(_lines(text))
 
 
-def test_chunk_boundaries():
-    """Lines and whitespace runs straddling the 16 KiB CTA chunk boundary."""
+@pytest.mark.parametrize("chunk", [16384, 6144])
+def test_chunk_boundaries(chunk):
+    """Lines and whitespace runs straddling the CTA chunk boundaries (16 KiB in the v1 kernel, 6 KiB in v2)."""
     from hyptokenizer_b200.pair_count import count_pairs
     from oracle.merge import count_pairs_py
     parts = []
     for k in range(40):
-        parts.append("x" * (16384 - 3 + (k % 7)) + " " * (k % 5) + "\n" + " " * (k % 3) + "yz")
+        parts.append("x" * (chunk - 3 + (k % 7)) + " " * (k % 5) + "\n" + " " * (k % 3) + "yz")
     text = "".join(parts)
     assert count_pairs(text.encode("utf-8")) == count_pairs_py(_lines(text))
+
+
+def test_wide_alphabet_and_counter_wraps():
+    """More distinct symbols than the private table of the v2 kernel holds (31) and than its CTA histogram holds (64),
+    with enough repetitions for the one-byte private counters to wrap many times; exact against the C oracle."""
+    import numpy as np
+    from hyptokenizer_b200.pair_count import count_pairs
+    from oracle.pair_count import count_pairs_c
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(bytes(range(33, 127)) + b" \t", np.uint8)               # 96 symbols
+    w = 1.0 / (np.arange(len(alphabet)) + 1.0)
+    data = rng.choice(alphabet, size=6 << 20, p=w / w.sum())
+    data[rng.integers(0, data.size, data.size // 60)] = 10
+    got = count_pairs(data)
+    want = count_pairs_c(data)
+    assert got == want
+
+
+def test_v1_kernel_matches_too():
+    """The atomics-only kernel stays selectable (HYP_PAIR_COUNT=v1, read once per process) and exact."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from test_gpu_paircount import EDGE, _lines\n"
+        "from hyptokenizer_b200.pair_count import count_pairs\n"
+        "from hyptokenizer_b200.synth import synthetic_corpus\n"
+        "from oracle.merge import count_pairs_py\n"
+        "for k, t in EDGE.items():\n"
+        "    assert count_pairs(t.encode('utf-8')) == count_pairs_py(_lines(t)), k\n"
+        "d = synthetic_corpus(8 << 20, seed=3)\n"
+        "ls = d.tobytes().decode('ascii').split('\\n')\n"
+        "assert sum(count_pairs(d).values()) == sum(max(len(l.strip()) - 1, 0) for l in ls)\n"
+        "print('v1 ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HYP_PAIR_COUNT="v1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "v1 ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_large_ascii_vs_oracle():
