@@ -530,7 +530,10 @@ def run_c4(a):
                        "distinct_pairs": len(counts), "total_pairs": int(sum(counts.values()))},
             "gpu_launches": a.steps, "roofline": {"bound": "hbm", "kernel": "pair_count_v2_kernel" if os.environ.get("HYP_PAIR_COUNT", "v2") != "v1" else "pair_count_kernel", "achieved": kgbs,
                                                   "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": kgbs / pk["hbm_gbs"],
-                                                  "traffic": None, "peak_kind": kind},
+                                                  "traffic": 1078586856 if os.environ.get("HYP_PAIR_COUNT", "v2") != "v1" else None,
+                                                  "traffic_source": "profiles/r01_prof_pair_v2_raw.csv: dram__bytes_read.sum + "
+                                                                    "dram__bytes_write.sum of one launch over 1 GiB (ncu --set full)",
+                                                  "peak_kind": kind},
             "clocks": clocks,
             "e2e": {"value": nbytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": int(asc.numel() * 8 + 2 * cap * 8)}}

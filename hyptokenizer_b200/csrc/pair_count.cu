@@ -227,36 +227,44 @@ pair_count_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long lon
 //
 // v1 above retires one shared-memory atomic per input byte, and ATOMS runs at ~1 lane per clock per SM on this part:
 // 148 SMs x 1.97 GHz = the ~310 GB/s it measures, with 80 thread instructions per byte of per-position branching on top.
-// v2 removes both (487 GB/s on the same stream):
-//  * each CTA ranks the ASCII bytes of its first chunk by frequency.  Pairs of the 31 most frequent symbols are
-//    counted in PRIVATE one-byte counters, one column of 1024 bins per PAIR of lanes, word-interleaved so that column
+// v2 removes both (680 GB/s on the same stream):
+//  * each CTA ranks the ASCII bytes of its first chunk by frequency.  Pairs of the 27 most frequent symbols are
+//    counted in PRIVATE one-byte counters, one column of 28 x 28 bins per PAIR of lanes, word-interleaved so that column
 //    c of a warp lives in bank c: an update is a plain LDS.U8 / +1 / STS.U8, no atomics and no bank conflicts, in two
 //    predicated phases (even lanes, then odd lanes) because two lanes share a column.  A counter that wraps carries
 //    256 into the global table.  Pairs within the 64 most frequent symbols go to a CTA histogram with ATOMS, anything
 //    rarer straight to the global table.  Counts stay exact for any input; the alphabet only decides how fast.
-//  * the hot loop has no data-dependent branch: a byte outside the private alphabet has private rank 31, whose row
+//  * the hot loop has no data-dependent branch: a byte outside the private alphabet has the last private rank, whose row
 //    and column of the table are junk bins; the byte offset of a bin is one add of two table entries,
 //    A[first byte] + B[second byte]; pairs that are not counted are predicated off;
 //  * classification is by table as well: C[byte] carries "space", "line break" and "outside the private alphabet" in
 //    three 10-bit planes, and acc = 2 acc + C[byte] over the thread's 19-byte neighbourhood yields the three position
 //    masks with one IMAD per byte; the count / resolve-slowly decisions of all 16 pairs are mask algebra;
 //  * no barrier in the main loop: a thread reads its 16 bytes (+ 4 of context on either side) straight from global
-//    memory, a warp 512 contiguous bytes, the next step's words in flight while this step is counted.  One CTA of 12
-//    warps per SM (the private counters take 12 x 16 KB of its shared memory).
+//    memory, a warp 512 contiguous bytes, the next step's words in flight while this step is counted.  One CTA of 16
+//    warps per SM (the private counters take 16 x 12.25 KB of its shared memory).
 // What was measured on the way (B200, 256 MiB of the config-4 stream): lane-private columns with 6 warps 240 GB/s
 // (latency-bound, every pair a chain of dependent branches) -> branch-free 398 -> two groups per thread side by side
 // 383 (no gain: not the chain) -> lane-pair columns + 12 warps, still staged through shared-memory windows 361 (one
-// barrier per 512 bytes per warp) -> barrier-free 438 -> predicated phases 454 -> table classification 487.  ncu at
-// that point: ~435 warp instructions per 512 bytes, issue slots ~55 % busy, stalls on the LDS -> +1 dependency.
-constexpr int kV2Threads = 384;
+// barrier per 512 bytes per warp) -> barrier-free 438 -> predicated phases 454 -> table classification 487 (569 on
+// 1 GiB) -> a 28 x 28 table, which fits 16 warps instead of 12: 680 on 1 GiB.  ncu before that last step: 533 warp
+// instructions per 512 bytes, issue slots 53 % busy, shared-memory pipe 54 %, a third of the stalls on LDS -> +1.
+#ifndef HYP_PC_SYMS
+#define HYP_PC_SYMS 28      // 27 private symbols, 16 warps per SM: 680 GB/s; 32 (31 symbols, 12 warps): 569 GB/s
+#endif
+constexpr int kPrivSyms = HYP_PC_SYMS;                     // private table dimension: kPrivSyms - 1 symbols + the junk rank
+constexpr int kPrivDiv = (kPrivSyms + 3) / 4;             // ranks sharing a byte lane of the word: ra / kPrivDiv
+constexpr int kPrivRows = kPrivDiv * kPrivSyms;           // word rows per column
+constexpr uint32_t kJunkRank = kPrivSyms - 1;
+constexpr int kV2Threads = HYP_PC_SYMS <= 28 ? 512 : 384;
 constexpr int kV2Warps = kV2Threads / 32;
 constexpr int kV2Chunk = kV2Threads * 16;                 // 6144 bytes of text per CTA iteration, one group per thread
-constexpr int kPrivPerWarp = 32 * 32 * 16;                // 1024 bins x 16 lane pairs x 1 byte
+constexpr int kPrivPerWarp = kPrivRows * 64;              // rows x 16 lane pairs x 4 bytes
 constexpr size_t kV2Smem = (size_t)kV2Warps * kPrivPerWarp + 64 * 64 * 4 + 512 + 512 + 1024 + 256 + 64;
 
-// byte offset of private bin (ra, rb) inside a lane pair's column: word row (ra & 7) * 32 + rb (16 words per row),
-// byte ra >> 3 of the word
-__device__ __forceinline__ uint32_t priv_off_a(uint32_t ra) { return (ra & 7u) * 2048u + (ra >> 3); }
+// byte offset of private bin (ra, rb) inside a lane pair's column: word row (ra % kPrivDiv) * kPrivSyms + rb (16 words
+// per row), byte ra / kPrivDiv of the word
+__device__ __forceinline__ uint32_t priv_off_a(uint32_t ra) { return (ra % kPrivDiv) * (kPrivSyms * 64u) + ra / kPrivDiv; }
 __device__ __forceinline__ uint32_t priv_off_b(uint32_t rb) { return rb * 64u; }
 
 struct V2Ctx {
@@ -365,16 +373,16 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
     }
     __syncthreads();
     if (tid < 128) {
-      const uint32_t pr = rank < 31u ? rank : 31u;
+      const uint32_t pr = rank < kJunkRank ? rank : kJunkRank;
       sym[tid] = (uint8_t)rank;
       sym[128 + tid] = 0xff;
       tabA[tid] = (uint16_t)priv_off_a(pr);
       tabB[tid] = (uint16_t)priv_off_b(pr);
       const uint32_t t = tid;
       const uint32_t is_sp = (t >= 0x09 && t <= 0x0d) || (t >= 0x1c && t <= 0x20), is_br = t == 0x0a || t == 0x0d;
-      tabC[tid] = is_sp | (is_br << 10) | ((pr == 31u ? 1u : 0u) << 20);
-      tabA[128 + tid] = (uint16_t)priv_off_a(31u);
-      tabB[128 + tid] = (uint16_t)priv_off_b(31u);
+      tabC[tid] = is_sp | (is_br << 10) | ((pr == kJunkRank ? 1u : 0u) << 20);
+      tabA[128 + tid] = (uint16_t)priv_off_a(kJunkRank);
+      tabB[128 + tid] = (uint16_t)priv_off_b(kJunkRank);
       tabC[128 + tid] = 1u << 20;
       if (rank != 0xffu) inv[rank] = (uint8_t)tid;
     }
@@ -521,14 +529,14 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
 
   // flush: private counters (sum over the warp's 16 columns per bin), then the CTA histogram
   const uint32_t *rows = reinterpret_cast<const uint32_t *>(priv + warp * kPrivPerWarp);
-  for (int g = 0; g < 256; ++g) {
+  for (int g = 0; g < kPrivRows; ++g) {
     const uint32_t w = lane < 16 ? rows[g * 16 + lane] : 0u;
     const uint32_t s0 = __reduce_add_sync(HYP_FULL_MASK, w & 0xffu), s1 = __reduce_add_sync(HYP_FULL_MASK, (w >> 8) & 0xffu);
     const uint32_t s2 = __reduce_add_sync(HYP_FULL_MASK, (w >> 16) & 0xffu), s3 = __reduce_add_sync(HYP_FULL_MASK, w >> 24);
     if (lane < 4) {
       const uint32_t s = lane == 0 ? s0 : lane == 1 ? s1 : lane == 2 ? s2 : s3;
-      const uint32_t ra = (uint32_t)(g >> 5) + 8u * lane, rb = g & 31;      // row (ra & 7) * 32 + rb, byte ra >> 3
-      if (s && ra != 31u && rb != 31u)
+      const uint32_t ra = (uint32_t)(g / kPrivSyms) + kPrivDiv * lane, rb = g % kPrivSyms;   // inverse of priv_off_a/b
+      if (s && ra < kJunkRank && rb != kJunkRank)
         atomicAdd(ascii_counts + (uint32_t)inv[ra] * 128u + inv[rb], (unsigned long long)s);
     }
   }
