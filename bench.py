@@ -450,6 +450,24 @@ def run_c3(a):
                                      "and over every 2nd tile once more (bound pass); "
                                      "`value` counts the algorithmic 2*V^2*(d+1) once"},
                 "clocks": clocks}
+        # recall (north star): the timed engine against exact brute force, and the reference's own candidate generator --
+        # exact L2 kNN over Klein coordinates, which its FAISS-HNSW index approximates -- against the exact Lorentz lists
+        rs = min(1024, nrows)
+        g = torch.Generator().manual_seed(0)
+        rows = (row0 + torch.randperm(nrows, generator=g)[:rs]).sort().values.to(dev)
+        got = idx[(rows - row0)].to(torch.int64)
+        ex_i = torch.empty((rs, k), dtype=torch.int32, device=dev)
+        ex_d = torch.empty((rs, k), dtype=torch.float32, device=dev)
+        hits = 0
+        for j, r in enumerate(rows.tolist()):                         # the exact CUDA-core engine, row by row
+            check(L.hyp_allpairs_topk(ptr(E), D, V, r, 1, D, 1.0, sem, k, ex_i[j].data_ptr(), ex_d[j].data_ptr(), sp))
+        torch.cuda.synchronize()
+        line["recall"] = {"rows": rs, "k": k,
+                          "timed_engine_vs_exact_bruteforce": knn.recall_at_k(got, ex_i),
+                          "reference_klein_l2_knn_vs_exact_lorentz": knn.recall_at_k(knn.klein_l2_topk(E, k, rows), ex_i),
+                          "note": "FAISS is not installable in this image: the second figure is for EXACT L2 kNN over Klein "
+                                  "coordinates xs/(x0+1e-8), the list a perfect HNSW search of the reference's index returns "
+                                  "(fast_hyperbolic_merge.py:195-240, :286-304); Klein-L2 order is not Lorentz-distance order"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -121,3 +121,28 @@ def lorentz_topk_sharded(E: torch.Tensor, k: int = 32, c: float = 1.0, semantics
     row0, nrows, _ = shard_rows(n, dist.get_world_size(group), dist.get_rank(group))
     li, ld = lorentz_topk(E, k, c, semantics, n, row0, nrows, engine=engine)
     return gather_topk(li, ld, n, group)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# recall against what the reference's FAISS indexes rank by (evaluation only, never on a hot path)
+# ---------------------------------------------------------------------------------------------------------
+def klein_l2_topk(E: torch.Tensor, k: int, rows: torch.Tensor, n: Optional[int] = None) -> torch.Tensor:
+    """The k nearest rows of each of `rows` by squared L2 distance between Klein coordinates `xs / (x0 + 1e-8)`, self
+    excluded, ties on index: EXACTLY what the reference's `IndexFlatL2` returns and what its HNSW index approximates
+    (fast_hyperbolic_merge.py:195-240 builds the index over these coordinates, :286-304 queries it).  FAISS itself is
+    not installable here, so this is the stand-in for "the reference FAISS path" in recall figures: a perfect HNSW
+    search returns this list.  Plain torch ops (a reporting helper, works on any device); returns int64 [len(rows), k]."""
+    n = E.shape[0] if n is None else n
+    K = (E[:n, 1:] / (E[:n, 0:1] + 1e-8)).to(torch.float64)
+    q = K[rows]
+    d2 = (q * q).sum(1, keepdim=True) - 2.0 * (q @ K.T) + (K * K).sum(1)[None, :]
+    d2[torch.arange(len(rows), device=E.device), rows] = float("inf")
+    # ascending by (distance, index): stable sort of the index-ordered columns
+    return torch.sort(d2, dim=1, stable=True).indices[:, :k]
+
+
+def recall_at_k(found: torch.Tensor, truth: torch.Tensor) -> float:
+    """Mean over rows of |found[r] ∩ truth[r]| / k for two [rows, k] index lists."""
+    f = found.to(torch.int64).unsqueeze(2)
+    t = truth.to(torch.int64).unsqueeze(1)
+    return float((f == t).any(dim=2).to(torch.float64).mean().item())

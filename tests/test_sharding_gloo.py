@@ -144,3 +144,25 @@ def test_shard_byte_ranges_are_line_aligned_and_cover():
     assert shard_byte_range(empty, 0, 2) == (0, 0) and shard_byte_range(empty, 1, 2) == (0, 0)
     one_line = np.frombuffer(b"abcdef", dtype=np.uint8)
     assert [shard_byte_range(one_line, r, 2) for r in range(2)] == [(0, 6), (6, 6)]
+
+
+def test_klein_l2_topk_and_recall_helpers():
+    """The recall helpers of knn.py (pure torch, evaluation only): Klein-L2 kNN against a float64 numpy brute force."""
+    import numpy as np
+    import torch
+    from hyptokenizer_b200.knn import klein_l2_topk, recall_at_k
+    from oracle.lorentz import initialize_embeddings
+    torch.manual_seed(3)
+    E = initialize_embeddings(300, 12, 1.0, 0.3)
+    rows = torch.tensor([0, 7, 150, 299])
+    got = klein_l2_topk(E, 5, rows).numpy()
+    K = (E[:, 1:] / (E[:, 0:1] + 1e-8)).double().numpy()
+    for g, r in zip(got, rows.tolist()):
+        d2 = ((K - K[r]) ** 2).sum(1)
+        d2[r] = np.inf
+        want = np.argsort(d2, kind="stable")[:5]
+        assert set(g.tolist()) == set(want.tolist())
+    a = torch.tensor([[1, 2, 3, 4], [5, 6, 7, 8]])
+    b = torch.tensor([[4, 3, 9, 1], [0, 0, 0, 0]])
+    assert recall_at_k(a, b) == (3 / 4 + 0) / 2
+    assert recall_at_k(a, a) == 1.0
