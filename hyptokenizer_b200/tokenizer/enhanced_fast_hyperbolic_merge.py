@@ -33,12 +33,11 @@ from typing import Any, Dict, List, Optional, Set, Tuple, Union
 import numpy as np
 import torch
 
-from ..embedding import lorentz_model as LM
 from ..pair_count import count_pairs
 from .adaptive_curvature_tokenizer import CurvatureStepMixin
 from .fast_hyperbolic_merge import AdaptiveMergeCache, FastHyperbolicTokenizer, MergeCandidate
 from .frequency_aware_hyperbolic_merge import FrequencyAwareHyperbolicTokenizer as _FreqAware
-from .hierarchical_hyperbolic_merge import NLTK_AVAILABLE, HierarchicalHyperbolicTokenizer as _Hier
+from .hierarchical_hyperbolic_merge import NLTK_AVAILABLE, HierarchicalHyperbolicTokenizer as _Hier  # noqa: F401
 
 logger = logging.getLogger(__name__)
 

@@ -156,7 +156,6 @@ def check_save_load(cls, tok, gd, out):
 
 def run_adaptive(cls, gd, r, device=None):
     """One run of tests/golden/trace_adaptive.json (gen_trace_adaptive) through an AdaptiveCurvatureTokenizer class."""
-    from helpers import fbits
     vocab, d = gd["vocab0"], gd["d"]
     emb = from_bits(r["init"], len(vocab), d + 1)
     sem = "lorentz" if r["semantics"].startswith("lorentz") else "reference"

@@ -2,10 +2,6 @@
 the device kernels, against golden traces of the unmodified reference under the import shim of SURVEY.md 8c
 (tests/golden/trace_enhanced.json, oracle/gen_golden.py gen_trace_enhanced).  The host policy alone is covered on the
 CPU by tests/test_enhanced_host_logic.py; this file is the same comparison with K2 / K1 / K3 / K6 / K7 underneath."""
-import json
-import os
-
-import numpy as np
 import pytest
 import torch
 
