@@ -353,7 +353,10 @@ class HyperbolicTokenizer:
         os.makedirs(path, exist_ok=True)
         with open(f"{path}/vocab.json", "w") as f:
             json.dump(self.vocab, f)
-        active = self.embeddings[: self.current_vocab_size].detach().cpu()
+        # The reference saves `embeddings[:n].detach().cpu()`, on its CPU device a VIEW of the whole table: torch.save
+        # writes the full storage and the file loads as [n, D].  Same here (table to the host first, then the view), so
+        # that the file is the reference's byte for byte when the rows are (tests/golden/persistence.json).
+        active = self.embeddings.detach().cpu()[: self.current_vocab_size]
         torch.save(active, f"{path}/embeddings.pt")
         with open(f"{path}/merges.json", "w") as f:
             json.dump(self.merge_history, f)

@@ -635,7 +635,33 @@ def gen_trace_adaptive():
     dump("trace_adaptive.json", out)
 
 
-GENS = {"trace_adaptive": gen_trace_adaptive, "trace_enhanced": gen_trace_enhanced, "trace_compress": gen_trace_compress, "trace_hier": gen_trace_hier, "lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
+def gen_persistence(tmpdir="/tmp"):
+    """HyperbolicTokenizer.save (hyperbolic_merge.py:473-504) after five merges: sha256 and size of every file it writes.
+    `embeddings.pt` is `torch.save` of a VIEW of the full `[max_vocab_size, D]` table, so the file carries the whole
+    storage; torch.save is deterministic, so a byte-identical file is a meaningful target."""
+    import hashlib
+    import shutil
+    vocab = c1_vocab()
+    set_seeds(42)
+    emb = ref_init(len(vocab), 8, 0.3)
+    out = {"vocab0": vocab, "d": 8, "max_vocab_size": 64, "threshold": 1.2, "init": bits(emb), "torch": torch.__version__}
+    with semantics("lorentz"):
+        tok = RH.HyperbolicTokenizer(vocab, torch.nn.Parameter(emb.clone()), merge_threshold=1.2, device=torch.device("cpu"),
+                                     max_vocab_size=64)
+        out["merges"] = run_base_loop(tok, 5)
+        path = os.path.join(tmpdir, "hyp_golden_saved")
+        shutil.rmtree(path, ignore_errors=True)
+        tok.save(path)
+    out["files"] = {}
+    for fn in sorted(os.listdir(path)):
+        data = open(os.path.join(path, fn), "rb").read()
+        out["files"][fn] = {"size": len(data), "sha256": hashlib.sha256(data).hexdigest()}
+    out["final"] = tok_state(tok)
+    print("persistence", out["files"])
+    dump("persistence.json", out)
+
+
+GENS = {"persistence": gen_persistence, "trace_adaptive": gen_trace_adaptive, "trace_enhanced": gen_trace_enhanced, "trace_compress": gen_trace_compress, "trace_hier": gen_trace_hier, "lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
         "trace_fast": gen_trace_fast, "pair_counts": gen_pair_counts, "trace_freq": gen_trace_freq}
 
 if __name__ == "__main__":
