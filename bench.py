@@ -554,7 +554,8 @@ def run_c4(a):
                                                   "peak_kind": kind},
             "clocks": clocks,
             "e2e": {"value": nbytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes,
-                    "d2h_bytes_per_step": int(asc.numel() * 8 + 2 * cap * 8)}}
+                    # what pairs_to_dict reads back: the dense table and the USED entries of the open-addressing table
+                    "d2h_bytes_per_step": int(asc.numel() * 8 + 16 * int((keys != -1).sum().item()))}}
     if not a.no_cpu_baseline:
         from oracle.pair_count import count_pairs_c
         sample = host[: 256 << 20].numpy()
