@@ -230,7 +230,7 @@ pair_count_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long lon
 // v2 removes both (680 GB/s on the same stream):
 //  * each CTA ranks the ASCII bytes of its first chunk by frequency.  Pairs of the 27 most frequent symbols are
 //    counted in PRIVATE one-byte counters, one column of 28 x 28 bins per PAIR of lanes, word-interleaved so that column
-//    c of a warp lives in bank c: an update is a plain LDS.U8 / +1 / STS.U8, no atomics and no bank conflicts, in two
+//    c of a warp lives in bank c (+16 in odd rows): an update is a plain LDS.U8 / +1 / STS.U8, no atomics and no bank conflicts, in two
 //    predicated phases (even lanes, then odd lanes) because two lanes share a column.  A counter that wraps carries
 //    256 into the global table.  Pairs within the 64 most frequent symbols go to a CTA histogram with ATOMS, anything
 //    rarer straight to the global table.  Counts stay exact for any input; the alphabet only decides how fast.
@@ -258,7 +258,7 @@ constexpr int kPrivRows = kPrivDiv * kPrivSyms;           // word rows per colum
 constexpr uint32_t kJunkRank = kPrivSyms - 1;
 constexpr int kV2Threads = HYP_PC_SYMS <= 28 ? 512 : 384;
 constexpr int kV2Warps = kV2Threads / 32;
-constexpr int kV2Chunk = kV2Threads * 16;                 // 6144 bytes of text per CTA iteration, one group per thread
+constexpr int kV2Chunk = kV2Threads * 16;                 // bytes of text per CTA step (8 KiB), one 16-byte group per thread
 constexpr int kPrivPerWarp = kPrivRows * 64;              // rows x 16 lane pairs x 4 bytes
 constexpr size_t kV2Smem = (size_t)kV2Warps * kPrivPerWarp + 64 * 64 * 4 + 512 + 512 + 1024 + 256 + 64;
 

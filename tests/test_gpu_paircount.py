@@ -47,9 +47,10 @@ def test_edge_cases(case):
     assert count_pairs(text.encode("utf-8")) == count_pairs_py(_lines(text))
 
 
-@pytest.mark.parametrize("chunk", [16384, 6144])
+@pytest.mark.parametrize("chunk", [16384, 8192, 6144])
 def test_chunk_boundaries(chunk):
-    """Lines and whitespace runs straddling the CTA chunk boundaries (16 KiB in the v1 kernel, 6 KiB in v2)."""
+    """Lines and whitespace runs straddling the CTA chunk boundaries (16 KiB in the v1 kernel, 8 KiB -- 6 KiB with the
+    32-symbol table -- in v2)."""
     from hyptokenizer_b200.pair_count import count_pairs
     from oracle.merge import count_pairs_py
     parts = []
