@@ -69,24 +69,29 @@ class _LengthIndex:
         self.by_len = by_len
         self.lengths = sorted(by_len, reverse=True)
 
-    def count(self, text: str, extra: str) -> int:
-        """Number of tokens of `text` under vocabulary + [extra]."""
+    def tokenize(self, text: str, extra: str = "") -> List[str]:
+        """Greedy longest-match tokens of `text` under vocabulary + [extra]."""
         by_len = self.by_len
         lengths = self.lengths
         le = len(extra)
         if le and le not in by_len:
             lengths = sorted(set(lengths) | {le}, reverse=True)
-        count, i, n = 0, 0, len(text)
+        tokens: List[str] = []
+        i, n = 0, len(text)
         while i < n:
             for length in lengths:
                 piece = text[i:i + length]
                 if len(piece) == length and ((length == le and piece == extra) or piece in by_len.get(length, ())):
-                    i += length
                     break
             else:
-                i += 1                  # no vocabulary entry starts here: the character itself
-            count += 1
-        return count
+                piece = text[i]         # no vocabulary entry starts here: the character itself
+            tokens.append(piece)
+            i += len(piece)
+        return tokens
+
+    def count(self, text: str, extra: str) -> int:
+        """Number of tokens of `text` under vocabulary + [extra]."""
+        return len(self.tokenize(text, extra))
 
 
 class EnhancedFastHyperbolicTokenizer(CurvatureStepMixin, FastHyperbolicTokenizer):
@@ -246,12 +251,10 @@ class EnhancedFastHyperbolicTokenizer(CurvatureStepMixin, FastHyperbolicTokenize
 
     # ---- compression-aware pieces (reference :813-899) -----------------------------------------------------------------
     def _tokenize_with_vocab(self, text: str, vocab: List[str]) -> List[str]:
+        """reference :813-847."""
         if not self.use_compression_aware:
             return self.tokenize(text)
-        from .compression_aware_tokenizer import CompressionAwareTokenizer
-        return CompressionAwareTokenizer._tokenize_with_vocab(self, text, vocab)
-
-    _length_index = staticmethod(lambda vocab: sorted(_LengthIndex(vocab).by_len.items(), reverse=True))
+        return _LengthIndex(vocab).tokenize(text)
 
     def _compute_compression_score(self, i: int, j: int, index: Optional[_LengthIndex] = None) -> float:
         """reference :849-899, including the `merge_{i}_{j}_{text[:20]}` cache key and the 10-text cap."""

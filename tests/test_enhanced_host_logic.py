@@ -172,16 +172,19 @@ def test_length_index_matches_the_reference_scan():
         extra = "".join(rng.choice(alphabet) for _ in range(rng.randint(1, 5)))
         text = "".join(rng.choice(alphabet + "z") for _ in range(rng.randint(0, 30)))
         ref_vocab = sorted(vocab + [extra], key=len, reverse=True)
-        count, i = 0, 0
+        tokens, i = [], 0
         while i < len(text):
             for t in ref_vocab:
                 if text[i:].startswith(t):
+                    tokens.append(t)
                     i += len(t)
                     break
             else:
+                tokens.append(text[i])
                 i += 1
-            count += 1
-        assert PE._LengthIndex(vocab).count(text, extra) == count
+        assert PE._LengthIndex(vocab).count(text, extra) == len(tokens)
+        assert PE._LengthIndex(vocab).tokenize(text, extra) == tokens
+        assert PE._LengthIndex(vocab + [extra]).tokenize(text) == tokens
 
 
 @pytest.mark.parametrize("run", [0, 1, 2, 3])
