@@ -416,6 +416,7 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
     // add in a phase issues nothing: the RMW is predicated.  __syncwarp orders the phases for the compiler too.
     const uint32_t mine_e = odd ? 0u : g.counted, mine_o = odd ? g.counted : 0u;
     uint32_t wacc[4] = {0, 0, 0, 0};           // byte 3 - (i & 3) of wacc[i >> 2]: 1 if the counter of pair i passed 255
+#ifndef HYP_PC_ONEPHASE
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       uint8_t *p = priv_col + (g.A[i] + g.B[i + 1]);
@@ -426,6 +427,25 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
       __syncwarp();
       wacc[i >> 2] = __byte_perm(wacc[i >> 2], l + 1u, 0x2105);
     }
+#else
+    // EXPERIMENT for round 2 (not measured, not the default; A/B with tools/ab_pair.sh and EXTRA=-DHYP_PC_ONEPHASE):
+    // one phase per update.  The two lanes of a column exchange their target offsets; when both are active on the
+    // SAME bin the even lane adds 2 and the odd lane nothing, otherwise both update (different bytes) at once.
+    (void)mine_e; (void)mine_o;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t act = (g.counted >> i) & 1u;
+      const uint32_t o = g.A[i] + g.B[i + 1];
+      const uint32_t key = act ? o : (0x10000u | (uint32_t)lane);      // an idle lane matches nobody
+      const bool coll = __shfl_xor_sync(HYP_FULL_MASK, key, 1) == key;
+      const uint32_t inc = coll ? 2u : 1u;
+      uint8_t *p = priv_col + o;
+      uint32_t l = 0;
+      if (act && !(coll && odd)) { l = *p; *p = (uint8_t)(l + inc); }
+      __syncwarp();
+      wacc[i >> 2] = __byte_perm(wacc[i >> 2], l + inc, 0x2105);       // byte 1 of l + inc: the counter passed 255
+    }
+#endif
     uint32_t wrap = 0;                         // bit i: the counter of pair i passed 255
     if (wacc[0] | wacc[1] | wacc[2] | wacc[3]) {
 #pragma unroll
