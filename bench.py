@@ -1,23 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- merges/sec of the HypTokenizer merge loop on B200 (BASELINE.json configs[1]).
+"""bench.py -- the HypTokenizer merge-loop hot path on B200 (BASELINE.json: "merges/sec at V=50k,d=100; all-pairs
+Lorentz dist TFLOP/s + % roofline").
 
-Workload ("c2"): FastHyperbolicTokenizer, embedding_dim=100, V0=10 000 synthetic tokens grown to
-target_vocab_size=50 000 (40 000 merges), SURVEY.md 8d.  One "step" = one whole job: initial
-all-pairs argmin over V0 rows + 40 000 device-resident merges.
+The default run measures, on N GPUs, every driver-visible figure of the path in ONE JSON line:
 
-  value   merges/s with the table already in HBM, C-ABI calls only, CUDA events on the launch stream
-  e2e     the same job through the public class (host embeddings in pinned memory -> H2D,
-          optimize_merges, D2H of the merge log and of embeddings[:n], host string rebuild)
-  roofline  the merge-loop kernel against measured HBM bandwidth: algorithmic bytes
-          sum_n 4*n*(d+1) over the merges of one launch / its CUDA-event duration
-  cpu_baseline  the oracle port (reference algorithm, torch CPU eager) on a bounded sample
+  c2 (headline; BASELINE configs[1])   FastHyperbolicTokenizer, d=100, V0=10 000 -> target_vocab_size=50 000: one
+      "step" = one whole job (initial all-pairs argmin + 40 000 device-resident merges).
+        value     merges/s, table resident in HBM, C-ABI calls only, CUDA events on the launch stream
+        e2e       the same job through the public class: pinned host embeddings -> H2D, optimize_merges, D2H of
+                  the merge log and of embeddings[:n], host string rebuild
+        roofline  merge_loop_resident_kernel: algorithmic bytes sum_n 4 n (d+1) / its event-timed duration against
+                  measured HBM copy bandwidth (+ smem_frac: the same bytes against the shared-memory bandwidth,
+                  the bound that actually applies -- the table lives in shared memory)
+      N > 1: the loop is sequential and fits one GPU ("replicas only"): N independent jobs.
+  c3 (BASELINE configs[2])   all-pairs Lorentz distance + top-32 over V=100 000, d=100: tcgen05 TF32 Gram filter +
+      fp32 re-score, rows SHARDED over the N ranks, the per-shard lists all-gathered INSIDE the timed region (the
+      finishing kernels store into every rank's buffer over NVLink, hyp_ctx; NCCL all-gather timed beside it).
+      config.c3_* / secondary.c3: ms, algorithmic TFLOP/s (2 V^2 (d+1) once), fraction of the TF32 peak measured
+      here with torch.matmul 8192^3, recall against exact brute force and against Klein-L2 kNN.
+  c4 (BASELINE configs[3], counting part)   pair counting over a 1 GiB stream per rank: GB/s and HBM fraction.
 
-`--impl reference` times the reference's own algorithm (oracle port: the reference is pure Python
-and cannot travel to the GPU box) on the host cores.
-
-N > 1 (torchrun): the merge loop is inherently sequential and its table fits one GPU's L2, so the
-path does not shard ("replicas only"): every rank runs an independent job on its own
-seed; value = total merges of all ranks / max-over-ranks time.
+`--workload c2|c3|c4|tok|c2-sharded|c5` runs one of them alone with its own line.
+`--impl reference` runs the UNMODIFIED reference (staged into baseline/_ref by tools/stage_reference.py) on the
+host cores: FastHyperbolicTokenizer.optimize_merges at the largest size it can run (V0=2 000, d=100), one cache
+cycle (101 merges) per step, measured, not scaled; the n=V0=10 000 figure is a cost model and labelled as such.
 """
 from __future__ import annotations
 
@@ -39,6 +45,8 @@ import torch  # noqa: E402
 V0, D_EMB, TARGET = 10000, 100, 50000
 SCALE = 0.01            # the reference's init scale (scripts/train_hyperbolic_tokenizer.py:92)
 THRESHOLD = 0.1
+C3_V, C3_K = 100000, 32
+REF_V0, REF_CYCLE = 2000, 101     # reference arm: the largest size the reference runs; one pop-100 cache cycle
 
 
 def parse():
@@ -51,12 +59,18 @@ def parse():
     ap.add_argument("--v0", type=int, default=V0)
     ap.add_argument("--target", type=int, default=TARGET)
     ap.add_argument("--dim", type=int, default=D_EMB)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "tok", "c2-sharded"],
-                    help="c2: merge loop (headline, merges/s); c3: all-pairs Lorentz distance + top-k=32 over V=100k, "
-                         "row-sharded over the ranks with an all-gather (TFLOP/s)")
+    ap.add_argument("--workload", default="all", choices=["all", "c2", "c3", "c4", "c5", "tok", "c2-sharded"],
+                    help="all (default): c2 headline + c3 + c4 in one line; c2: merge loop (merges/s); c3: all-pairs "
+                         "Lorentz distance + top-k=32 over V=100k, row-sharded, all-gather inside the timed region "
+                         "(TFLOP/s); c4: pair counting; c5: enhanced tokenizer loop at size; tok: batched tokenize")
     ap.add_argument("--engine", default="tc", choices=["tc", "exact"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--ref-v0", type=int, default=REF_V0, help="vocabulary size the reference arm runs")
+    ap.add_argument("--c4-bytes", type=int, default=1 << 30)
+    ap.add_argument("--c5-steps", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tf32-peak", action="store_true")
     return ap.parse_args()
 
 
@@ -65,7 +79,7 @@ def peaks():
     if os.path.exists(path):
         with open(path) as f:
             return json.load(f), "measured"
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
 class ClockSampler:
@@ -116,32 +130,91 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+class Env:
+    """One process per GPU (torchrun) or a single process: rank / world / device + NCCL for the plumbing."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        from hyptokenizer_b200 import _lib
+        self.L = _lib.lib()
+        _lib.check_device(self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce(self, x: float, op: str) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
 def algorithmic_bytes(v0: int, merges: int, d: int) -> float:
     """each merge reads the n current rows once: 4*n*(d+1) bytes (+ one row written)."""
     n_sum = merges * v0 + merges * (merges - 1) // 2
     return 4.0 * (d + 1) * (n_sum + merges)
 
 
+def measure_tf32_peak(dev) -> dict:
+    """Dense TF32 throughput measured the way MEASURED_PEAKS.json measures bf16: torch.matmul
+    8192^3 with TF32 allowed, best of 10 (burst) and back to back for 2 s (sustained), CUDA events."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn((n, n), device=dev)
+        b = torch.randn((n, n), device=dev)
+        c = torch.empty((n, n), device=dev)
+        flops = 2.0 * n ** 3
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = float("inf")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(10):
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(2000.0 / best))
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        sus = e0.elapsed_time(e1) / reps
+        del a, b, c
+        return {"tf32_tflops": flops / (best * 1e-3) / 1e12, "tf32_tflops_sustained": flops / (sus * 1e-3) / 1e12,
+                "how": "torch.matmul fp32 8192^3 with allow_tf32 (2*N^3): best of 10 (burst), back to back for ~2 s (sustained)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 # ------------------------------------------------------------------------------------------------
-# our arm
+# c2: the merge loop (headline)
 # ------------------------------------------------------------------------------------------------
-def run_ours(a):
-    import torch.distributed as dist
-    from hyptokenizer_b200 import _lib
-    from hyptokenizer_b200._lib import SEM, check, ptr
+def bench_c2(a, env: Env) -> dict:
+    from hyptokenizer_b200._lib import SEM, HypMergeState, check, ptr
     from hyptokenizer_b200.synth import synthetic_embeddings, synthetic_vocab
     from hyptokenizer_b200.tokenizer.fast_hyperbolic_merge import FastHyperbolicTokenizer
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    L = _lib.lib()
-    _lib.check_device(dev)
-
+    L, dev, rank, world = env.L, env.dev, env.rank, env.world
     v0, d, target = a.v0, a.dim, a.target
     merges = target - v0
     D = d + 1
@@ -159,7 +232,6 @@ def run_ours(a):
     best = torch.empty(32, dtype=torch.uint8, device=dev)
     state = torch.empty(40, dtype=torch.uint8, device=dev)
     log = torch.empty((merges, 4), dtype=torch.int32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -170,7 +242,7 @@ def run_ours(a):
         E[:v0].copy_(init)
         E[v0:].zero_()
         lens.copy_(lens_init)
-        flush.fill_(1)                                   # L2 flush between timed iterations
+        env.flush.fill_(1)                               # L2 flush between timed iterations
         ev[0].record(stream)
         check(L.hyp_allpairs_min(ptr(E), D, v0, D, 1.0, sem, thr32, ptr(best), ptr(ws_ap), ws_ap.numel(), sp))
         check(L.hyp_merge_state_init(ptr(state), ptr(best), v0, target, THRESHOLD, sp))
@@ -185,20 +257,14 @@ def run_ours(a):
 
     for _ in range(a.warmup):
         one_step(False)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
+    env.barrier()
+    sampler = ClockSampler(env.local) if rank == 0 else None
     t_total, t_loop = [], []
     for _ in range(a.steps):
         tt, tl = one_step(True)
         t_total.append(tt)
         t_loop.append(tl)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
+    env.barrier()
     clocks = sampler.stop() if sampler else None
     prof = ws_lp[32:96].cpu().numpy().view(np.int64)
     mprof = ws_lp[96:160].cpu().numpy().view(np.int64)
@@ -209,16 +275,12 @@ def run_ours(a):
             n_ = max(int(prof[base + 3]), 1)
             print(f"[phases {name}] cycles/merge: midpoint={prof[base] / n_:.0f} scan={prof[base + 1] / n_:.0f} "
                   f"barrier={prof[base + 2] / n_:.0f}", file=sys.stderr)
-    from hyptokenizer_b200._lib import HypMergeState
     st = HypMergeState.from_buffer_copy(state.cpu().numpy().tobytes())
     done = st.steps_done
     ms_total = float(sum(t_total))
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    done_all = torch.tensor([done * a.steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(done_all, op=dist.ReduceOp.SUM)
-    value = float(done_all.item()) / (float(tmax.item()) * 1e-3)
+    tmax = env.reduce(ms_total, "max")
+    done_all = env.reduce(done * a.steps, "sum")
+    value = done_all / (tmax * 1e-3)
 
     # ---- end to end through the public class, host buffers, copies inside the timed region ----------
     e2e = None
@@ -226,10 +288,9 @@ def run_ours(a):
         vocab = synthetic_vocab(v0)
         out = torch.empty((target, D), dtype=torch.float32).pin_memory()    # landing buffer of the result table
         e2e_t = []
+        n_e2e = n_rows = 0
         for it in range(2):
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
+            env.barrier()
             t0 = time.perf_counter()
             tok = FastHyperbolicTokenizer(vocab, torch.nn.Parameter(host_emb), merge_threshold=THRESHOLD,
                                           max_vocab_size=target, device=dev, semantics=a.semantics)
@@ -239,23 +300,17 @@ def run_ours(a):
             torch.cuda.synchronize()
             e2e_t.append(time.perf_counter() - t0)
             n_e2e = len(tok.last_trace)
-        te = torch.tensor([min(e2e_t)], dtype=torch.float64, device=dev)
-        ne = torch.tensor([float(n_e2e)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ne, op=dist.ReduceOp.SUM)
-        e2e = {"value": float(ne.item()) / float(te.item()), "unit": "merges/s",
+        te = env.reduce(min(e2e_t), "max")
+        ne = env.reduce(float(n_e2e), "sum")
+        e2e = {"value": ne / te, "unit": "merges/s",
                "h2d_bytes_per_step": int(host_emb.numel() * 4 + target * 4 + 40),
                "d2h_bytes_per_step": int(n_e2e * 16 + n_rows * D * 4 + 40 * ((n_e2e + 8191) // 8192))}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
     pk, pk_kind = peaks()
     loop_ms = float(np.mean(t_loop))
     abytes = algorithmic_bytes(v0, done, d)
     achieved = abytes / (loop_ms * 1e-3) / 1e9
+    smem_peak = 148 * 128 * float(pk.get("sm_max_mhz", 1965.0)) * 1e6 / 1e9     # GB/s: 128 B/clk/SM
     line = {
         "metric": "merges/sec at V=50k,d=100", "value": value, "unit": "merges/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True,
@@ -269,27 +324,263 @@ def run_ours(a):
         "gpu_launches": 3 * a.steps,
         "launches_note": "per step: allpairs_tile_kernel<min>, merge_state_init_kernel, "
                          "merge_loop_resident_kernel<100, false> (cooperative, persistent)",
-        "roofline": {"bound": "hbm", "kernel": "merge_loop_resident_kernel<100, false>", "achieved": achieved, "peak": pk["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+        "roofline": {"bound": "hbm", "kernel": "merge_loop_resident_kernel<100, false>", "achieved": achieved,
+                     "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                     "smem_frac": achieved / smem_peak, "smem_peak_gbs": smem_peak,
                      "traffic": 4107776, "traffic_source": "profiles/r01_prof_merge_raw.csv: dram__bytes_read.sum + "
                                                            "dram__bytes_write.sum of one launch (ncu --set full)",
                      "peak_kind": pk_kind,
                      "algorithmic_bytes_per_launch": abytes, "kernel_ms": loop_ms,
                      "note": "the table (<= 20.2 MB) lives in the shared memory of the persistent grid, so DRAM traffic is far "
-                             "below the algorithmic bytes; frac is the algorithmic rate against HBM copy bandwidth"},
+                             "below the algorithmic bytes: frac is the algorithmic rate against HBM copy bandwidth (an "
+                             "equivalence), smem_frac the same rate against 148 SMs x 128 B/clk, the bound that applies"},
         "clocks": clocks,
     }
     if e2e:
         line["e2e"] = e2e
-    if not a.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline(a)
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port of the reference algorithm on the host cores
+# c3: all-pairs Lorentz distance + top-k over V=100k, row-sharded, lists all-gathered inside the timed region
+# ------------------------------------------------------------------------------------------------
+def bench_c3(a, env: Env, tf32: dict | None) -> dict:
+    import ctypes as C
+    from hyptokenizer_b200 import knn
+    from hyptokenizer_b200._lib import SEM, check, ptr
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    L, dev, rank, world, dist = env.L, env.dev, env.rank, env.world, env.dist
+    V, d, k = C3_V, a.dim, C3_K
+    D = d + 1
+    sem = SEM[a.semantics]
+    E = synthetic_embeddings(V, d, scale=SCALE, seed=42).to(dev)       # every rank holds all columns
+    row0, nrows, per = knn.shard_rows(V, world, rank)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx = None
+    if a.engine == "tc" and a.exchange in ("auto", "p2p"):
+        ctx = knn.topk_context(V, k, dev)                              # None: peers cannot map each other's memory
+        if ctx is None and a.exchange == "p2p":
+            raise RuntimeError("--exchange p2p: hyp_ctx could not be connected")
+    # local-only / NCCL variants: the shard's lists as interleaved records in a single-rank context's buffer
+    idx = torch.empty((per, k), dtype=torch.int32, device=dev)
+    dd = torch.empty((per, k), dtype=torch.float32, device=dev)
+    flags = torch.zeros(max(per, 1), dtype=torch.int32, device=dev)
+    nbytes = L.hyp_gram_topk_workspace_bytes(V, max(nrows, 1), D)
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    wsp = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+    rec_local = torch.empty((per, k), dtype=torch.int64, device=dev)
+    rec_all = torch.empty((world * per, k), dtype=torch.int64, device=dev)
+    result = {}
+
+    def local_lists():
+        if a.engine == "tc":
+            check(L.hyp_gram_topk(ptr(E), D, V, row0, nrows, D, 1.0, sem, k, ptr(idx), ptr(dd), ptr(flags), wsp, nbytes, sp))
+        else:
+            check(L.hyp_allpairs_topk(ptr(E), D, V, row0, nrows, D, 1.0, sem, k, ptr(idx), ptr(dd), sp))
+
+    def step_fused():
+        if ctx is not None:
+            result["rec"] = ctx.gram_topk(E, 1.0, a.semantics)
+        else:
+            step_nccl()
+
+    def step_local():
+        local_lists()
+
+    def step_nccl():
+        local_lists()
+        rec_local.copy_(knn.join_records(idx, dd))
+        if world > 1:
+            dist.all_gather_into_tensor(rec_all, rec_local)
+            result["rec"] = rec_all
+        else:
+            result["rec"] = rec_local
+
+    def timed(fn, with_clocks=False):
+        for _ in range(a.warmup):
+            fn()
+        env.barrier()
+        sampler = ClockSampler(env.local) if (rank == 0 and with_clocks) else None
+        ts = []
+        for _ in range(a.steps):
+            env.flush.fill_(1)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        env.barrier()
+        clocks = sampler.stop() if sampler else None
+        return env.reduce(sum(ts), "max") / a.steps, clocks
+
+    ms_fused, clocks = timed(step_fused, with_clocks=True)
+    rec = result["rec"]
+    gi, gd = knn.split_records(rec[:V])
+    gi, gd = gi.contiguous(), gd.contiguous()
+    ms_local, _ = timed(step_local)
+    ms_nccl = None
+    if world > 1 and ctx is not None:
+        ms_nccl, _ = timed(step_nccl)
+    flagged = int(flags[:nrows].sum().item())
+    status = ctx.status() if ctx is not None else 0
+
+    # correctness and recall on rank 0 (north star): the gathered lists against exact brute force on two 512-row blocks
+    # (one of the first shard, one of the last), and the reference's own candidate generator -- exact L2 kNN over Klein
+    # coordinates, which its FAISS-HNSW index approximates -- against the exact Lorentz lists
+    recall = None
+    if rank == 0:
+        rs = 512
+        blocks = [0, max(0, V - rs)] if V > rs else [0]
+        hits_exact, hits_klein, total, bit_equal = 0.0, 0.0, 0, True
+        for b0 in blocks:
+            ex_i = torch.empty((rs, k), dtype=torch.int32, device=dev)
+            ex_d = torch.empty((rs, k), dtype=torch.float32, device=dev)
+            check(L.hyp_allpairs_topk(ptr(E), D, V, b0, rs, D, 1.0, sem, k, ptr(ex_i), ptr(ex_d), sp))
+            torch.cuda.synchronize()
+            got_i, got_d = gi[b0:b0 + rs], gd[b0:b0 + rs]
+            bit_equal &= bool(torch.equal(got_i, ex_i)) and bool(torch.equal(got_d.view(torch.int32), ex_d.view(torch.int32)))
+            hits_exact += knn.recall_at_k(got_i, ex_i) * rs
+            rows = torch.arange(b0, b0 + rs, device=dev)
+            hits_klein += knn.recall_at_k(knn.klein_l2_topk(E, k, rows), ex_i) * rs
+            total += rs
+        recall = {"rows": total, "k": k, "timed_engine_vs_exact_bruteforce": hits_exact / total,
+                  "bit_identical_to_exact_kernel": bit_equal,
+                  "reference_klein_l2_knn_vs_exact_lorentz": hits_klein / total,
+                  "note": "FAISS is not installable in this image: the second figure is for EXACT L2 kNN over Klein "
+                          "coordinates xs/(x0+1e-8), the list a perfect HNSW search of the reference's index returns "
+                          "(fast_hyperbolic_merge.py:195-240, :286-304); Klein-L2 order is not Lorentz-distance order"}
+    flops = 2.0 * V * V * D                                      # one full distance matrix
+    pk, kind = peaks()
+    if tf32:
+        tf32_peak, peak_kind = tf32["tf32_tflops"], "measured here: " + tf32["how"]
+    else:
+        tf32_peak, peak_kind = pk.get("bf16_tflops", 1590.0) / 2.0, kind + " bf16/2 (TF32 peak not measured in this run)"
+    # hardware FLOPs of the tc engine: the collect pass visits every column tile, the bound pass every `step`-th
+    # (same rule as hyp_gram_topk: 2, fewer while that leaves under 4k sampled tiles); K padded d+1 -> 104
+    col_tiles = (V + 127) // 128
+    tc_step = max(1, int(os.environ.get("HYP_TC_SUB", "2")))
+    while tc_step > 1 and (col_tiles + tc_step - 1) // tc_step < 4 * k:
+        tc_step -= 1
+    hw = (1.0 + 1.0 / tc_step) if a.engine == "tc" else 1.0
+    shard_flops = 2.0 * nrows * V * D
+    kern_s = ms_local * 1e-3
+    ach = hw * shard_flops / kern_s / 1e12
+    launches = (6 if a.engine == "tc" else 1) + (1 if (ctx is not None and world > 1) else 0)
+    line = {"metric": "all-pairs Lorentz dist TFLOP/s (V=100k,d=100,top-k=32)", "value": flops / (ms_fused * 1e-3) / 1e12,
+            "unit": "TFLOP/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_fused,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "tf32+f32 rescore",
+            "data": "synthetic",
+            "config": {"workload": f"c3: all-pairs Lorentz distance + top-{k}, V={V}, d={d}, rows sharded over "
+                                   f"{world} GPU(s), (V/G, k) lists all-gathered inside the timed region",
+                       "engine": a.engine, "semantics": a.semantics,
+                       "exchange": ("peer memory (hyp_ctx): finishing kernels store into every rank's buffer + barrier kernel"
+                                    if ctx is not None and world > 1 else "NCCL all_gather_into_tensor of interleaved records"
+                                    if world > 1 else "none (1 GPU)"),
+                       "rows_redone_exactly": flagged, "barrier_status": status, "l2": "flushed between timed steps",
+                       "ms_local_only": ms_local, "ms_with_nccl_allgather": ms_nccl,
+                       "allgather_ms": ms_fused - ms_local},
+            "gpu_launches": launches * a.steps,
+            "launches_note": "per step: tc_pack, gram_tc<1>, kth_select, gram_tc<2>, tc_finish, allpairs_topk (redo, "
+                             "returns at once when no row is flagged)" + (", ctx_barrier" if ctx is not None and world > 1 else ""),
+            "roofline": {"bound": "tensor", "kernel": "gram_tc_kernel<1> + <2> (+pack/select/finish)",
+                         "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                         "algorithmic_tflops_local": shard_flops / kern_s / 1e12,
+                         "algorithmic_frac": shard_flops / kern_s / 1e12 / tf32_peak,
+                         "traffic": None, "peak_kind": peak_kind,
+                         "note": "hardware FLOPs: the tc engine runs the Gram GEMM over every column tile once (collect pass) "
+                                 "and over every 2nd tile once more (bound pass); `value` counts the algorithmic "
+                                 "2*V^2*(d+1) once; achieved is per GPU on its shard, local kernels only"},
+            "clocks": clocks}
+    if recall:
+        line["recall"] = recall
+    if tf32:
+        line["tf32_peak"] = tf32
+    return line
+
+
+# ------------------------------------------------------------------------------------------------
+# c4 (pair counting part): 1 GiB synthetic token stream per rank
+# ------------------------------------------------------------------------------------------------
+def bench_c4(a, env: Env) -> dict:
+    from hyptokenizer_b200._lib import check, ptr
+    from hyptokenizer_b200.pair_count import pairs_to_dict
+    from hyptokenizer_b200.synth import synthetic_corpus
+    L, dev, rank, world, dist = env.L, env.dev, env.rank, env.world, env.dist
+    nbytes = a.c4_bytes                                  # per rank: every GPU counts its own stream (weak scaling)
+    host = torch.from_numpy(synthetic_corpus(nbytes, seed=rank)).pin_memory()
+    text = host.to(dev)
+    cap = 1 << 20
+    asc = torch.empty(128 * 128, dtype=torch.int64, device=dev)
+    keys = torch.empty(cap, dtype=torch.int64, device=dev)
+    vals = torch.empty(cap, dtype=torch.int64, device=dev)
+    ovf = torch.empty(1, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    ts, tk = [], []
+    sampler = None
+    for it in range(a.warmup + a.steps):
+        if it == a.warmup:
+            env.barrier()
+            sampler = ClockSampler(env.local) if rank == 0 else None
+        e0.record(stream)
+        check(L.hyp_pair_count(ptr(text), nbytes, ptr(asc), ptr(keys), ptr(vals), cap, ptr(ovf), stream.cuda_stream))
+        e1.record(stream)
+        if world > 1:
+            dist.all_reduce(asc, op=dist.ReduceOp.SUM)   # the shards' only exchange: the dense 128x128 histogram
+        e2.record(stream)
+        torch.cuda.synchronize()
+        if it >= a.warmup:
+            ts.append(e0.elapsed_time(e2))
+            tk.append(e0.elapsed_time(e1))
+    env.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = env.reduce(float(sum(ts)), "max") / a.steps
+    if rank != 0:
+        return {}
+    # end to end: pinned host bytes -> H2D -> kernel -> D2H of the tables -> dict
+    t0 = time.perf_counter()
+    t2 = host.to(dev, non_blocking=True)
+    check(L.hyp_pair_count(ptr(t2), nbytes, ptr(asc), ptr(keys), ptr(vals), cap, ptr(ovf), stream.cuda_stream))
+    counts = pairs_to_dict(asc, keys, vals)
+    e2e_s = time.perf_counter() - t0
+    pk, kind = peaks()
+    gbs = world * nbytes / (ms * 1e-3) / 1e9
+    kgbs = nbytes / (float(np.mean(tk)) * 1e-3) / 1e9
+    variant = os.environ.get("HYP_PAIR_COUNT", "default")
+    line = {"metric": "pair counting GB/s (1 GB token stream)", "value": gbs, "unit": "GB/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"c4 (pair-count part): {nbytes / 2 ** 30:g} GiB ASCII stream per GPU, lines of 20 random "
+                                   "words; input larger than L2" + ("; histograms summed with one all_reduce per step"
+                                                                    if world > 1 else ""),
+                       "kernel_variant": variant,
+                       "distinct_pairs": len(counts), "total_pairs": int(sum(counts.values()))},
+            "gpu_launches": a.steps,
+            "roofline": {"bound": "hbm", "kernel": "pair_count kernel (" + variant + ")", "achieved": kgbs,
+                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": kgbs / pk["hbm_gbs"],
+                         "traffic": None, "peak_kind": kind},
+            "clocks": clocks,
+            "e2e": {"value": nbytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes,
+                    # what pairs_to_dict reads back: the dense table and the USED entries of the open-addressing table
+                    "d2h_bytes_per_step": int(asc.numel() * 8 + 16 * int((keys != -1).sum().item()))}}
+    if not a.no_cpu_baseline:
+        from oracle.pair_count import count_pairs_c
+        sample = host[: min(nbytes, 256 << 20)].numpy()
+        t0 = time.perf_counter()
+        ref = count_pairs_c(sample)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": sample.size / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+                                "sample": "first 256 MiB of the same stream, C restatement (oracle/pair_count.c), one thread; "
+                                          "the reference's Python dict loop measured 2.5 MB/s (BASELINE.md)"}
+        if sample.size == nbytes:
+            line["config"]["dict_equals_oracle"] = bool(ref == counts)
+    return line
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: cost model of one reference step at n = V0 (port), and the reference itself where it can run
 # ------------------------------------------------------------------------------------------------
 def _cpu_sample(a, rows: int):
     """One bounded sample of one reference merge step at n = V0: the reference recomputes all n x n
@@ -317,9 +608,25 @@ def cpu_baseline(a, rows: int = 1024):
     _cpu_sample(a, 64)
     t, ncand = _cpu_sample(a, rows)
     return {"value": 1.0 / t, "unit": "merges/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"one brute-force merge step of the reference at n={a.v0} (all-pairs recompute + candidate "
-                      f"extraction, vectorised), {rows} of {a.v0} query rows timed and scaled by n/rows; the "
-                      f"reference itself cannot run this size (n^2*d*4 B = {a.v0 ** 2 * a.dim * 4 / 1e9:.0f} GB temporary)"}
+            "sample": f"COST MODEL, not a run: one brute-force merge step of the reference at n={a.v0} (all-pairs recompute + "
+                      f"candidate extraction, vectorised), {rows} of {a.v0} query rows timed and scaled by n/rows; the "
+                      f"reference itself cannot run this size (n^2*d*4 B = {a.v0 ** 2 * a.dim * 4 / 1e9:.0f} GB temporary); "
+                      "`bench.py --impl reference` times the real reference at the largest size it runs"}
+
+
+def _reference_modules():
+    """The unmodified reference from the staged copy (or /root/reference in the build container), imported through
+    oracle/gen_golden.py, which also holds the three-function geometry correction (`lorentz` semantics)."""
+    for root in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(root, "tokenizer")) and os.path.isdir(os.path.join(root, "embedding")):
+            os.environ["HYP_REFERENCE_ROOT"] = root
+            import logging
+            import warnings
+            warnings.filterwarnings("ignore")
+            logging.disable(logging.CRITICAL)
+            from oracle import gen_golden as G
+            return G, root
+    return None, None
 
 
 def run_reference(a):
@@ -329,245 +636,67 @@ def run_reference(a):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    rows = 1024
-    for _ in range(a.warmup):
-        _cpu_sample(a, rows)
-    ts = []
-    for _ in range(a.steps):
-        t, _ = _cpu_sample(a, rows)
-        ts.append(t)
-    value = len(ts) / sum(ts)
-    sample = (f"each step = one brute-force merge step of the reference algorithm at n={a.v0}, d={a.dim} "
-              f"({rows} of {a.v0} query rows timed, scaled by n/rows); oracle port, torch CPU eager fp32")
-    line = {"impl": "reference", "metric": "merges/sec at V=50k,d=100", "value": value, "unit": "merges/s",
-            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"c2: d={a.dim}, V0={a.v0} -> {a.target}", "semantics": a.semantics,
-                       "note": "per-step cost grows as n^2; n=V0 is the CHEAPEST step of the job, so this flatters the reference"},
-            "cpu_baseline": {"value": value, "unit": "merges/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample},
-            "e2e": {"value": value, "unit": "merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
-
-
-# ------------------------------------------------------------------------------------------------
-# config 3: all-pairs Lorentz distance + top-k over V=100k, row-sharded, all-gather of the lists
-# ------------------------------------------------------------------------------------------------
-def run_c3(a):
-    import torch.distributed as dist
-    from hyptokenizer_b200 import _lib, knn
-    from hyptokenizer_b200._lib import SEM, check, ptr
-    from hyptokenizer_b200.synth import synthetic_embeddings
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    L = _lib.lib()
-    _lib.check_device(dev)
-    V, d, k = 100000, a.dim, 32
-    D = d + 1
-    sem = SEM[a.semantics]
-    E = synthetic_embeddings(V, d, scale=SCALE, seed=42).to(dev)       # every rank holds all columns
-    row0, nrows, per = knn.shard_rows(V, world, rank)
-    idx = torch.empty((per, k), dtype=torch.int32, device=dev)
-    dd = torch.empty((per, k), dtype=torch.float32, device=dev)
-    all_i = torch.empty((world * per, k), dtype=torch.int32, device=dev)
-    all_d = torch.empty((world * per, k), dtype=torch.float32, device=dev)
-    flags = torch.zeros(per, dtype=torch.int32, device=dev)
-    nbytes = L.hyp_gram_topk_workspace_bytes(V, nrows, D)
-    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
-    wsp = ws.data_ptr() + ((-ws.data_ptr()) % 256)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
-    sp = stream.cuda_stream
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-
-    def step():
-        flush.fill_(1)
-        e0.record(stream)
-        if a.engine == "tc":
-            check(L.hyp_gram_topk(ptr(E), D, V, row0, nrows, D, 1.0, sem, k, ptr(idx), ptr(dd), ptr(flags), wsp, nbytes, sp))
-        else:
-            check(L.hyp_allpairs_topk(ptr(E), D, V, row0, nrows, D, 1.0, sem, k, ptr(idx), ptr(dd), sp))
-        e1.record(stream)
-        if world > 1:
-            dist.all_gather_into_tensor(all_i, idx)
-            dist.all_gather_into_tensor(all_d, dd)
-        e2.record(stream)
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e2), e0.elapsed_time(e1)
-
-    for _ in range(a.warmup):
-        step()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    tot, ker = [], []
-    for _ in range(a.steps):
-        t, t1 = step()
-        tot.append(t)
-        ker.append(t1)
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop() if sampler else None
-    flagged = int(flags[:nrows].sum().item())
-    tmax = torch.tensor([sum(tot)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        flops = 2.0 * V * V * D                                      # one full distance matrix
-        secs = float(tmax.item()) * 1e-3 / a.steps
-        pk, kind = peaks()
-        kern_s = float(np.mean(ker)) * 1e-3
-        shard_flops = 2.0 * nrows * V * D
-        tf32_peak = pk.get("bf16_tflops", 1590.0) / 2.0               # TF32 dense = half the bf16 rate
-        # hardware FLOPs of the tc engine: the collect pass visits every column tile, the bound pass every
-        # `step`-th (same rule as hyp_gram_topk: 2, fewer while that leaves under 4k sampled tiles)
-        col_tiles = (V + 127) // 128
-        tc_step = max(1, int(os.environ.get("HYP_TC_SUB", "2")))
-        while tc_step > 1 and (col_tiles + tc_step - 1) // tc_step < 4 * k:
-            tc_step -= 1
-        hw = 1.0 + 1.0 / tc_step
-        line = {"metric": "all-pairs Lorentz dist TFLOP/s (V=100k,d=100,top-k=32)", "value": flops / secs / 1e12,
-                "unit": "TFLOP/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": secs * 1e3,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "tf32+f32 rescore",
-                "data": "synthetic",
-                "config": {"workload": f"c3: all-pairs Lorentz distance + top-{k}, V={V}, d={d}, rows sharded over "
-                                       f"{world} GPU(s), all-gather of the (V/G, k) lists", "engine": a.engine,
-                           "semantics": a.semantics, "rows_flagged_for_exact_redo": flagged,
-                           "l2": "flushed between timed steps"},
-                "gpu_launches": (5 if a.engine == "tc" else 1) * a.steps,
-                "roofline": {"bound": "tensor", "kernel": "gram_tc_kernel x2 (+pack/select/finish)",
-                             "achieved": hw * shard_flops / kern_s / 1e12 if a.engine == "tc" else shard_flops / kern_s / 1e12,
-                             "peak": tf32_peak, "unit": "TFLOP/s",
-                             "frac": (hw * shard_flops / kern_s / 1e12 if a.engine == "tc" else shard_flops / kern_s / 1e12) / tf32_peak,
-                             "traffic": None, "peak_kind": kind + " bf16/2",
-                             "note": "hardware FLOPs: the tc engine runs the Gram GEMM over every column tile once (collect pass) "
-                                     "and over every 2nd tile once more (bound pass); "
-                                     "`value` counts the algorithmic 2*V^2*(d+1) once"},
-                "clocks": clocks}
-        # recall (north star): the timed engine against exact brute force, and the reference's own candidate generator --
-        # exact L2 kNN over Klein coordinates, which its FAISS-HNSW index approximates -- against the exact Lorentz lists
-        rs = min(1024, nrows)
-        g = torch.Generator().manual_seed(0)
-        rows = (row0 + torch.randperm(nrows, generator=g)[:rs]).sort().values.to(dev)
-        got = idx[(rows - row0)].to(torch.int64)
-        ex_i = torch.empty((rs, k), dtype=torch.int32, device=dev)
-        ex_d = torch.empty((rs, k), dtype=torch.float32, device=dev)
-        hits = 0
-        for j, r in enumerate(rows.tolist()):                         # the exact CUDA-core engine, row by row
-            check(L.hyp_allpairs_topk(ptr(E), D, V, r, 1, D, 1.0, sem, k, ex_i[j].data_ptr(), ex_d[j].data_ptr(), sp))
-        torch.cuda.synchronize()
-        line["recall"] = {"rows": rs, "k": k,
-                          "timed_engine_vs_exact_bruteforce": knn.recall_at_k(got, ex_i),
-                          "reference_klein_l2_knn_vs_exact_lorentz": knn.recall_at_k(knn.klein_l2_topk(E, k, rows), ex_i),
-                          "note": "FAISS is not installable in this image: the second figure is for EXACT L2 kNN over Klein "
-                                  "coordinates xs/(x0+1e-8), the list a perfect HNSW search of the reference's index returns "
-                                  "(fast_hyperbolic_merge.py:195-240, :286-304); Klein-L2 order is not Lorentz-distance order"}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-
-
-# ------------------------------------------------------------------------------------------------
-# config 4 (pair counting part): 1 GB synthetic token stream
-# ------------------------------------------------------------------------------------------------
-def run_c4(a):
-    import torch.distributed as dist
-    from hyptokenizer_b200 import _lib
-    from hyptokenizer_b200._lib import check, ptr
-    from hyptokenizer_b200.pair_count import pairs_to_dict
-    from hyptokenizer_b200.synth import synthetic_corpus
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    L = _lib.lib()
-    _lib.check_device(dev)
-    nbytes = 1 << 30                                   # per rank: every GPU counts its own GiB (weak scaling)
-    host = torch.from_numpy(synthetic_corpus(nbytes, seed=rank)).pin_memory()
-    text = host.to(dev)
-    cap = 1 << 20
-    asc = torch.empty(128 * 128, dtype=torch.int64, device=dev)
-    keys = torch.empty(cap, dtype=torch.int64, device=dev)
-    vals = torch.empty(cap, dtype=torch.int64, device=dev)
-    ovf = torch.empty(1, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream()
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    ts, tk = [], []
-    sampler = None
-    for it in range(a.warmup + a.steps):
-        if it == a.warmup:
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-                torch.cuda.synchronize()
-            sampler = ClockSampler(local) if rank == 0 else None
-        e0.record(stream)
-        check(L.hyp_pair_count(ptr(text), nbytes, ptr(asc), ptr(keys), ptr(vals), cap, ptr(ovf), stream.cuda_stream))
-        e1.record(stream)
-        if world > 1:
-            dist.all_reduce(asc, op=dist.ReduceOp.SUM)   # the shards' only exchange: the dense 128x128 histogram
-        e2.record(stream)
-        torch.cuda.synchronize()
-        if it >= a.warmup:
-            ts.append(e0.elapsed_time(e2))
-            tk.append(e0.elapsed_time(e1))
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
-    tot = torch.tensor([float(sum(ts))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    if rank != 0:
-        dist.destroy_process_group()
+    G, root = _reference_modules()
+    base = {"impl": "reference", "metric": "merges/sec at V=50k,d=100", "unit": "merges/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic"}
+    if G is None:
+        # no staged reference: the oracle port's cost model (never on the GPU box of a normal round: build() stages it)
+        rows = 1024
+        for _ in range(a.warmup):
+            _cpu_sample(a, rows)
+        ts = [_cpu_sample(a, rows)[0] for _ in range(a.steps)]
+        value = len(ts) / sum(ts)
+        base.update({"value": value, "ms_per_step": 1e3 * sum(ts) / len(ts),
+                     "config": {"workload": f"c2 cost model: d={a.dim}, n={a.v0}", "semantics": a.semantics,
+                                "note": "baseline/_ref missing; oracle port, one step at n=V0 scaled from 1024 query rows"},
+                     "cpu_baseline": {"value": value, "unit": "merges/s", "cores": torch.get_num_threads(), "kind": "port",
+                                      "sample": "cost model (see config.note)"},
+                     "e2e": {"value": value, "unit": "merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(base))
         return
-    # end to end: pinned host bytes -> H2D -> kernel -> D2H of the tables -> dict
-    t0 = time.perf_counter()
-    t2 = host.to(dev, non_blocking=True)
-    check(L.hyp_pair_count(ptr(t2), nbytes, ptr(asc), ptr(keys), ptr(vals), cap, ptr(ovf), stream.cuda_stream))
-    counts = pairs_to_dict(asc, keys, vals)
-    e2e_s = time.perf_counter() - t0
-    pk, kind = peaks()
-    ms = float(tot.item()) / a.steps
-    gbs = world * nbytes / (ms * 1e-3) / 1e9
-    kgbs = nbytes / (float(np.mean(tk)) * 1e-3) / 1e9
-    line = {"metric": "pair counting GB/s (1 GB token stream)", "value": gbs, "unit": "GB/s", "n_gpus": world,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "c4 (pair-count part): 1 GiB ASCII stream per GPU, lines of 20 random words; input "
-                                   "larger than L2" + ("; histograms summed with one all_reduce per step" if world > 1 else ""),
-                       "distinct_pairs": len(counts), "total_pairs": int(sum(counts.values()))},
-            "gpu_launches": a.steps, "roofline": {"bound": "hbm", "kernel": "pair_count_v2_kernel" if os.environ.get("HYP_PAIR_COUNT", "v2") != "v1" else "pair_count_kernel", "achieved": kgbs,
-                                                  "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": kgbs / pk["hbm_gbs"],
-                                                  "traffic": 1078586856 if os.environ.get("HYP_PAIR_COUNT", "v2") != "v1" else None,
-                                                  "traffic_source": "profiles/r01_prof_pair_v2_raw.csv: dram__bytes_read.sum + "
-                                                                    "dram__bytes_write.sum of one launch over 1 GiB (ncu --set full)",
-                                                  "peak_kind": kind},
-            "clocks": clocks,
-            "e2e": {"value": nbytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes,
-                    # what pairs_to_dict reads back: the dense table and the USED entries of the open-addressing table
-                    "d2h_bytes_per_step": int(asc.numel() * 8 + 16 * int((keys != -1).sum().item()))}}
-    if not a.no_cpu_baseline:
-        from oracle.pair_count import count_pairs_c
-        sample = host[: 256 << 20].numpy()
-        t0 = time.perf_counter()
-        ref = count_pairs_c(sample)
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": sample.size / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
-                                "sample": "first 256 MiB of the same stream, C restatement (oracle/pair_count.c), one thread; "
-                                          "the reference's Python dict loop measured 2.5 MB/s (BASELINE.md)"}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    from hyptokenizer_b200.synth import synthetic_embeddings, synthetic_vocab
+    v0, d = a.ref_v0, a.dim
+    emb = synthetic_embeddings(v0, d, scale=SCALE, seed=42)
+    vocab = synthetic_vocab(v0)
+
+    def one_cycle(sem: str) -> float:
+        """FastHyperbolicTokenizer.optimize_merges(steps=101) on a fresh tokenizer: one candidate search (all-pairs
+        batch_distance + Python extraction + sort + cache) and the 100 merges its pop-100 cache serves."""
+        with G.semantics(sem):
+            G.set_seeds(42)
+            tok = G.RF.FastHyperbolicTokenizer(list(vocab), torch.nn.Parameter(emb.clone()), curvature=1.0,
+                                               merge_threshold=THRESHOLD, device=torch.device("cpu"),
+                                               max_vocab_size=v0 + REF_CYCLE + 8, use_approximate_search=False)
+            t0 = time.perf_counter()
+            tok.optimize_merges(steps=REF_CYCLE, log_every=10 ** 9)
+            dt = time.perf_counter() - t0
+        assert len(tok.merge_history) == REF_CYCLE, "the reference stopped early"
+        return dt
+
+    for _ in range(a.warmup):
+        one_cycle(a.semantics)
+    ts = [one_cycle(a.semantics) for _ in range(a.steps)]
+    value = REF_CYCLE * len(ts) / sum(ts)
+    shipped = REF_CYCLE / one_cycle("reference") if a.semantics != "reference" else value
+    sample = (f"each step = FastHyperbolicTokenizer.optimize_merges(steps={REF_CYCLE}) of the UNMODIFIED reference ({root}) "
+              f"at V0={v0}, d={d}, torch CPU eager fp32, {torch.get_num_threads()} threads: measured wall time, nothing scaled")
+    base.update({"value": value, "ms_per_step": 1e3 * sum(ts) / len(ts),
+                 "config": {"workload": f"c2 at the largest size the reference runs: FastHyperbolicTokenizer d={d}, V0={v0}, "
+                                        f"{REF_CYCLE} merges per step (one pop-100 cache cycle); V0=10 000 needs a "
+                                        f"{10000 ** 2 * d * 4 / 1e9:.0f} GB broadcast temporary (lorentz_model.py:155-163)",
+                            "semantics": a.semantics,
+                            "semantics_note": "lorentz = the reference with the three-function geometry correction of SURVEY.md "
+                                              "Appendix B monkey-patched (distance / batch_distance / log_map); loop, candidate "
+                                              "extraction, cache and threshold logic are the shipped code",
+                            "as_shipped_merges_per_s": shipped,
+                            "note": "the shipped class merges from a stale pop-100 cache (one all-pairs search per 101 merges); "
+                                    "our arm's default is the always-fresh exact search (the brute-force HyperbolicTokenizer "
+                                    "sequence), which costs the reference one all-pairs search per merge"},
+                 "cpu_baseline": {"value": value, "unit": "merges/s", "cores": torch.get_num_threads(), "kind": "reference",
+                                  "sample": sample},
+                 "e2e": {"value": value, "unit": "merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -647,18 +776,10 @@ def run_c2_sharded(a):
     every rank derives the same winner -- the multi-GPU form of the merge loop the north star describes.  Timed
     to show where it stands against the single-GPU device-resident loop (it never wins while the table fits one
     GPU: the step is one NVLink/NCCL latency, not bandwidth)."""
-    import torch.distributed as dist
-    from hyptokenizer_b200 import _lib
     from hyptokenizer_b200._lib import SEM, check, ptr
     from hyptokenizer_b200.synth import synthetic_embeddings
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    L = _lib.lib()
+    env = Env()
+    L, dev, rank, world, dist = env.L, env.dev, env.rank, env.world, env.dist
     V, d = a.target, a.dim
     D = d + 1
     sem = SEM[a.semantics]
@@ -687,29 +808,71 @@ def run_c2_sharded(a):
 
     for _ in range(50):
         one_merge(n_local)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    env.barrier()
     e0.record(stream)
     for m in range(merges):
         one_merge(n_local + (m // world))
     e1.record(stream)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = env.reduce(e0.elapsed_time(e1), "max")
     if rank == 0:
-        us = float(t.item()) * 1e3 / merges
+        us = ms * 1e3 / merges
         print(json.dumps({"metric": "merges/sec, row-sharded per-merge step with NCCL all-gather (crossover experiment)",
                           "value": 1e6 / us, "unit": "merges/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                          "ms_per_step": float(t.item()) / a.steps, "higher_is_better": True, "scaling": "strong",
+                          "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": f"c2-sharded: V={V}, d={d}, rows r = rank mod {world}, host-driven step: "
                                                  "midpoint + shard scan + all-gather of one 32-byte record per rank",
                                      "us_per_merge": us}, "gpu_launches": merges * 2}))
-    if world > 1:
-        dist.destroy_process_group()
+    env.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# c5 (BASELINE configs[4]) at size: the enhanced tokenizer's step, host / device split
+# ------------------------------------------------------------------------------------------------
+def run_c5(a):
+    from hyptokenizer_b200.bench_c5 import run as run5
+    env = Env()
+    line = run5(a, env)
+    if env.rank == 0:
+        print(json.dumps(line))
+    env.close()
+
+
+def run_ours(a):
+    env = Env()
+    if a.workload == "c3":
+        tf32 = None if a.no_tf32_peak else measure_tf32_peak(env.dev)
+        line = bench_c3(a, env, tf32)
+    elif a.workload == "c4":
+        line = bench_c4(a, env)
+    else:
+        line = bench_c2(a, env)
+        if env.rank == 0 and not a.no_cpu_baseline and env.world == 1:
+            line["cpu_baseline"] = cpu_baseline(a)
+        if a.workload == "all":
+            # the other driver-visible figures of the path ride in the same line: numeric fields under config, full
+            # lines under `secondary`
+            tf32 = None if a.no_tf32_peak else measure_tf32_peak(env.dev)
+            c3 = bench_c3(a, env, tf32)
+            c4 = bench_c4(a, env)
+            if env.rank == 0:
+                cfg = line["config"]
+                cfg.update({"c3_ms": c3["ms_per_step"], "c3_tflops": c3["value"],
+                            "c3_frac": c3["roofline"]["frac"], "c3_algorithmic_frac": c3["roofline"]["algorithmic_frac"],
+                            "c3_allgather_ms": c3["config"]["allgather_ms"], "c3_local_ms": c3["config"]["ms_local_only"],
+                            "c3_nccl_ms": c3["config"]["ms_with_nccl_allgather"],
+                            "c3_recall_exact": c3["recall"]["timed_engine_vs_exact_bruteforce"],
+                            "c3_bit_identical": c3["recall"]["bit_identical_to_exact_kernel"],
+                            "c3_recall_klein": c3["recall"]["reference_klein_l2_knn_vs_exact_lorentz"],
+                            "c3_tf32_peak_tflops": c3["roofline"]["peak"],
+                            "c4_gbs": c4["value"], "c4_kernel_gbs": c4["roofline"]["achieved"],
+                            "c4_frac": c4["roofline"]["frac"]})
+                line["secondary"] = {"c3": c3, "c4": c4}
+                line["gpu_launches"] += c3["gpu_launches"] + c4["gpu_launches"]
+    if env.rank == 0:
+        print(json.dumps(line))
+    env.close()
 
 
 if __name__ == "__main__":
@@ -720,9 +883,7 @@ if __name__ == "__main__":
         run_c2_sharded(args)
     elif args.workload == "tok":
         run_tok(args)
-    elif args.workload == "c4":
-        run_c4(args)
-    elif args.workload == "c3":
-        run_c3(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)

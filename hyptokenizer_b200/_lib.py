@@ -61,6 +61,13 @@ _SIGNATURES = {
     "hyp_allpairs_topk": ([_p, _i64, _i64, _i64, _i64, _i32, _f, _i32, _i32, _p, _p, _p], C.c_int),
     "hyp_gram_topk_workspace_bytes": ([_i64, _i64, _i32], _i64),
     "hyp_gram_topk": ([_p, _i64, _i64, _i64, _i64, _i32, _f, _i32, _i32, _p, _p, _p, _p, _i64, _p], C.c_int),
+    "hyp_ctx_create": ([C.POINTER(_p), _i32, _i32, _i64], C.c_int),
+    "hyp_ctx_export": ([_p, _p], C.c_int),
+    "hyp_ctx_connect": ([_p, _p], C.c_int),
+    "hyp_ctx_status": ([_p, C.POINTER(C.c_int)], C.c_int),
+    "hyp_ctx_destroy": ([_p], C.c_int),
+    "hyp_allgather_topk": ([_p, _p, _i64, C.POINTER(_p), _p], C.c_int),
+    "hyp_gram_topk_allgather": ([_p, _p, _i64, _i64, _i32, _f, _i32, _i32, _p, _p, _i64, C.POINTER(_p), _p], C.c_int),
     "hyp_distance_backward": ([_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _f, _i32, _p], C.c_int),
     "hyp_batch_distance_backward_coef": ([_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i32, _f, _i32, _p],
                                          C.c_int),

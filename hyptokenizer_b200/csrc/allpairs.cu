@@ -294,9 +294,13 @@ __global__ void __launch_bounds__(NTHREADS) allpairs_tile_kernel(const Params p)
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxTopK = 64;
 
+// With `row_list` (shard-relative row numbers, *row_count of them, both in device memory) the kernel serves only
+// those rows, 64 list entries per tile: the device-driven redo of the rows the tensor-core filter flagged
+// (gram_tc.cu), launched without the host knowing how many there are.
 __global__ void __launch_bounds__(NTHREADS)
 allpairs_topk_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D,
-                     float sqrt_c, float sgn, int k, int32_t *__restrict__ out_idx, float *__restrict__ out_d) {
+                     float sqrt_c, float sgn, int k, const TopkSink sink, const int32_t *__restrict__ row_list,
+                     const int32_t *__restrict__ row_count) {
   extern __shared__ __align__(16) float smem[];
   const int d = D - 1;
   float *As = smem;
@@ -310,19 +314,26 @@ allpairs_topk_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int64_
   unsigned long long *lists = reinterpret_cast<unsigned long long *>(smem + lists_off);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int64_t col_tiles = (n + TN - 1) / TN;
-  const int64_t row_tiles = (nrows + TM - 1) / TM;
+  const int64_t n_listed = row_list ? (int64_t)*row_count : nrows;
+  const int64_t row_tiles = (n_listed + TM - 1) / TM;
   const unsigned long long kEmpty = 0xffffffffffffffffULL;
+  const int64_t i_end = (row0 + nrows < n) ? row0 + nrows : n;
+  // table row served by slot r of tile rt (-1: none)
+  auto row_of = [&](int64_t rt, int r) -> int64_t {
+    const int64_t pos = rt * TM + r;
+    if (pos >= n_listed) return -1;
+    const int64_t gr = row_list ? row0 + row_list[pos] : row0 + pos;
+    return gr < i_end ? gr : -1;
+  };
 
   for (int64_t rt = blockIdx.x; rt < row_tiles; rt += gridDim.x) {
-    const int64_t i0 = row0 + rt * TM;
-    const int64_t i_end = (row0 + nrows < n) ? row0 + nrows : n;
     __syncthreads();
-    // rows of this tile: [i0, i0+64) clipped to the shard
+    // rows of this tile: [i0, i0+64) clipped to the shard, or 64 entries of the list
     {
       const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
       for (int r = w; r < TM; r += NTHREADS / 32) {
-        const int64_t gr = i0 + r;
-        const bool ok = gr < i_end;
+        const int64_t gr = row_of(rt, r);
+        const bool ok = gr >= 0;
         const float *row = E + (ok ? gr : 0) * ldE;
         for (int kk = lane; kk < d; kk += 32) As[kk * TPAD + r] = ok ? row[1 + kk] : 0.f;
         if (lane == 0) a0[r] = ok ? row[0] : 0.f;
@@ -350,8 +361,8 @@ allpairs_topk_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int64_
       __syncthreads();
       if (threadIdx.x < TM) {
         const int r = threadIdx.x;
-        const int64_t gi = i0 + r;
-        if (gi < i_end) {
+        const int64_t gi = row_of(rt, r);
+        if (gi >= 0) {
           unsigned long long *mine = lists + (size_t)r * k;
           const int64_t jn = (j0 + TN < n) ? TN : n - j0;
           for (int c = 0; c < (int)jn; ++c) {
@@ -380,8 +391,8 @@ allpairs_topk_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int64_
     // sort each row's list (insertion sort by its owner; k <= 64) and write out
     if (threadIdx.x < TM) {
       const int r = threadIdx.x;
-      const int64_t gi = i0 + r;
-      if (gi < i_end) {
+      const int64_t gi = row_of(rt, r);
+      if (gi >= 0) {
         unsigned long long *mine = lists + (size_t)r * k;
         for (int a = 1; a < k; ++a) {
           unsigned long long v = mine[a];
@@ -393,8 +404,8 @@ allpairs_topk_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int64_
         for (int q = 0; q < k; ++q) {
           const unsigned long long v = mine[q];
           const bool empty = v == kEmpty;
-          out_idx[orow * k + q] = empty ? -1 : (int32_t)(v & 0xffffffffu);
-          out_d[orow * k + q] = empty ? __int_as_float(0x7f800000) : __uint_as_float((unsigned int)(v >> 32));
+          sink_write(sink, orow, k, q, empty ? -1 : (int32_t)(v & 0xffffffffu),
+                     empty ? __int_as_float(0x7f800000) : __uint_as_float((unsigned int)(v >> 32)));
         }
       }
     }
@@ -514,16 +525,11 @@ extern "C" int hyp_allpairs_emit(const float *E, int64_t ldE, int64_t n, int D, 
   return launch_tiles<kEmit>(p, st, "hyp_allpairs_emit");
 }
 
-extern "C" int hyp_allpairs_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c,
-                                 int semantics, int k, int32_t *out_idx, float *out_d, void *stream) {
-  if (n < 0 || row0 < 0 || nrows < 0 || row0 + nrows > n || D < 2 || D > HYP_MAX_D || !(c > 0.f) || k < 1 ||
-      k > kMaxTopK) {
-    set_error("hyp_allpairs_topk: bad arguments (n=%lld row0=%lld nrows=%lld D=%d k=%d, k <= %d)", (long long)n,
-              (long long)row0, (long long)nrows, D, k, kMaxTopK);
-    return HYP_ERR_ARG;
-  }
-  if (nrows == 0) return HYP_OK;
-  if (!E || !out_idx || !out_d) return HYP_ERR_ARG;
+namespace hyp {
+// Shared by hyp_allpairs_topk and the tensor-core path's redo of flagged rows (row_list / row_count in device memory).
+int launch_allpairs_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c,
+                         int semantics, int k, const TopkSink &sink, const int32_t *row_list, const int32_t *row_count,
+                         cudaStream_t st) {
   const size_t smem = tile_smem_bytes(D) + ((size_t)TM * (TN + 1) + 4) * sizeof(float) + (size_t)TM * k * 8 + 16;
   if (smem > 200 * 1024) {
     set_error("hyp_allpairs_topk: D=%d k=%d needs %zu bytes of shared memory per CTA", D, k, smem);
@@ -542,7 +548,25 @@ extern "C" int hyp_allpairs_topk(const float *E, int64_t ldE, int64_t n, int64_t
   int64_t row_tiles = (nrows + TM - 1) / TM;
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > row_tiles) grid = row_tiles;
-  allpairs_topk_kernel<<<(int)grid, NTHREADS, smem, (cudaStream_t)stream>>>(
-      E, ldE, n, row0, nrows, D, sqrtf(c), semantics == HYP_SEM_REFERENCE ? -1.f : 1.f, k, out_idx, out_d);
+  allpairs_topk_kernel<<<(int)grid, NTHREADS, smem, st>>>(E, ldE, n, row0, nrows, D, sqrtf(c),
+                                                          semantics == HYP_SEM_REFERENCE ? -1.f : 1.f, k, sink, row_list,
+                                                          row_count);
   return check_launch("hyp_allpairs_topk");
+}
+}  // namespace hyp
+
+extern "C" int hyp_allpairs_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c,
+                                 int semantics, int k, int32_t *out_idx, float *out_d, void *stream) {
+  if (n < 0 || row0 < 0 || nrows < 0 || row0 + nrows > n || D < 2 || D > HYP_MAX_D || !(c > 0.f) || k < 1 ||
+      k > kMaxTopK) {
+    set_error("hyp_allpairs_topk: bad arguments (n=%lld row0=%lld nrows=%lld D=%d k=%d, k <= %d)", (long long)n,
+              (long long)row0, (long long)nrows, D, k, kMaxTopK);
+    return HYP_ERR_ARG;
+  }
+  if (nrows == 0) return HYP_OK;
+  if (!E || !out_idx || !out_d) return HYP_ERR_ARG;
+  TopkSink sink{};
+  sink.idx = out_idx;
+  sink.d = out_d;
+  return launch_allpairs_topk(E, ldE, n, row0, nrows, D, c, semantics, k, sink, nullptr, nullptr, (cudaStream_t)stream);
 }

@@ -240,6 +240,33 @@ __device__ __forceinline__ Key warp_key_min(Key k) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Where a per-row top-k list goes.  Separate arrays (idx[r][k], d[r][k]) for single-GPU callers, and/or
+// interleaved {idx, d bits} records written straight into the gather buffers of every rank of a
+// hyp_ctx (peer memory over NVLink): pairs[g] is rank g's buffer, already offset to this shard's first
+// row, so the kernel that produces a row also performs its part of the all-gather.
+// ---------------------------------------------------------------------------------------------
+struct TopkSink {
+  int32_t *idx;
+  float *d;
+  int2 *pairs[HYP_MAX_PEERS];
+  int n_pairs;
+};
+__device__ __forceinline__ void sink_write(const TopkSink &s, int64_t r, int k, int q, int32_t j, float dv) {
+  if (s.idx) s.idx[r * k + q] = j;
+  if (s.d) s.d[r * k + q] = dv;
+  const int2 rec = make_int2(j, __float_as_int(dv));
+#pragma unroll
+  for (int g = 0; g < HYP_MAX_PEERS; ++g)      // (static indices: a dynamic one would copy the parameter struct to local memory)
+    if (g < s.n_pairs) s.pairs[g][r * k + q] = rec;
+}
+
+// allpairs.cu: exact per-row top-k of rows [row0, row0+nrows) -- or, with row_list / row_count (device memory), of the
+// listed shard-relative rows only -- into `sink`.
+int launch_allpairs_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c,
+                         int semantics, int k, const TopkSink &sink, const int32_t *row_list, const int32_t *row_count,
+                         cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------
 // the midpoint chain of hyperbolic_merge.py:323-340, one warp, rows in shared or global memory.
 // `v` is scratch for D floats (shared).  Writes D floats to out (any address space).
 // ---------------------------------------------------------------------------------------------

@@ -3,29 +3,35 @@
 // Replaces the O(n^2 d) broadcast of embedding/lorentz_model.py:141-178 + the neighbour search the
 // reference delegates to FAISS (fast_hyperbolic_merge.py:301-304) for per-row top-k at large V.
 //
-//   S[i][j] = sum_k xs_i[k] xs_j[k]              tcgen05.mma kind::tf32, A/B tiles fed by TMA
-//                                                 (SWIZZLE_128B, K-major), fp32 accumulators in TMEM
-//   u~      = x0_i x0_j - S                       epilogue, fp32 (time-like term kept OUT of the MMA,
-//                                                 it would cost ~1e-4 in d)
-//   key     = max(sgn * u~, 1)                    clamped pre-acosh value; acosh is monotone, so the
+//   u'[i][j] = sgn * (x0_i x0_j - sum_k xs_i[k] xs_j[k])
+//                                                 ONE tcgen05.mma kind::tf32 chain per tile: A/B tiles fed by
+//                                                 TMA (SWIZZLE_128B, K-major), fp32 accumulators in TMEM; the
+//                                                 time-like term rides inside the MMA as hi/lo TF32 parts of
+//                                                 x0 in the K padding (tc_pack_kernel), so the accumulator IS u'
+//   key      = max(u', 1)                         clamped pre-acosh value; acosh is monotone, so the
 //                                                 order of keys is the order of distances
 //
-// TF32 keeps 10 mantissa bits of each operand, so |u~ - u| <= eps_i = 2^-9 |xs_i| max_j|xs_j| (+ fp32
+// TF32 keeps 10 mantissa bits of each operand, so |u' - u| <= eps_i = 2^-9 |xs_i| max_j|xs_j| (+ fp32
 // accumulation slack).  The kernel therefore never DECIDES anything; it bounds and filters:
-//   pass 1  per row, the minimum key of every 128-column tile          -> tilemin[tile][row]
+//   pass 1  per row, the minimum key of every `step`-th 128-column tile  -> tilemin[tile][row]
 //           (k distinct tiles' minima are k distinct elements, so the k-th smallest tile minimum is an
-//            upper bound tau_i of the row's true k-th smallest key; with V/128 tiles it is tight)
+//            upper bound tau_i of the row's true k-th smallest key)
 //   select  tau_i = k-th smallest of the row's tile minima              (kth_select_kernel)
-//   pass 2  collect every column with key <= tau_i + 2 eps_i            -> cand[row][<= CAP]
-//           a certified superset of the exact top-k, typically k+3 entries
+//   pass 2  collect every column with key <= tau_i + 2 eps_i            -> cand[row][segment][<= cap]
+//           a certified superset of the exact top-k
 //   finish  exact fp32 re-score of the candidates in ATen order (allpairs.cu arithmetic), sort by
-//           (d, j), emit k; rows whose candidate buffer overflowed are flagged and re-done by the exact
-//           CUDA-core kernel, so the result is ALWAYS the exact one.
+//           (d, j), emit k -- into the caller's arrays and/or straight into the gather buffers of every
+//           rank of a hyp_ctx (peer memory over NVLink: the producing kernel performs the all-gather)
+//   redo    rows whose candidate buffers overflowed (massive ties) are listed on the device and
+//           recomputed by the exact CUDA-core kernel, so the result is ALWAYS the exact one.
 //
-// Warp roles per CTA (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
-// warps 2..9 epilogue: two groups of four warps drain alternate accumulator tiles (thread <-> row = TMEM lane).  A CTA owns a 128-row block (its A
-// tile stays in shared memory) and streams all column tiles through a 2-stage B ring; accumulators are
-// quadruple-buffered in TMEM (4 x 128 columns) so the epilogue of tile t overlaps the MMA of tile t+1.
+// Work item = (pair of 128-row blocks, column segment): a shard of a few dozen row blocks (V/8 rows per
+// GPU) still fills all 148 SMs, and the last wave of a big shard is short.
+// Warp roles per CTA (352 threads): warp 0 TMA producer, warps 1 and 10 one MMA issuer thread per row
+// block of the pair (warp 1 also owns the TMEM allocation), warps 2..9 epilogue, four per row block
+// (thread <-> accumulator row = TMEM lane).  The A tiles of the pair stay in shared memory for the whole
+// item, the column tiles stream through a 2-stage B ring shared by both row blocks; accumulators are
+// double-buffered per row block in TMEM (4 x 128 columns) so the epilogue of tile t overlaps the MMA of t+1.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -45,8 +51,9 @@ constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_ACC = 4;           // accumulator buffers in TMEM (4 x 128 columns = all 512)
 constexpr int TC_EPI_WARPS = 8;    // 2 per TMEM lane quadrant: each handles one 64-column half of the tile
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS + 32;   // TMA, MMA issuer 0, 8 epilogue warps, MMA issuer 1
-constexpr int TC_CAPH = 128;       // candidate capacity per row and epilogue group
-constexpr int TC_CAP = 2 * TC_CAPH;
+constexpr int TC_CAND_ROW = 512;   // candidate slots per row in the workspace, split evenly over the column segments
+constexpr int TC_CAP = 384;        // most candidates of one row the finish kernel re-scores (more: exact redo)
+constexpr int TC_MAX_SEG = 16;     // column segments per row block pair
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -202,64 +209,93 @@ constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)
 // MMA, and the epilogue needs neither the column time components nor an FMA per element.
 // Also nrm[r] = |xs_r| and its maximum, for the error bound.
 // ---------------------------------------------------------------------------------------------
-__global__ void tc_pack_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int D, int Kp, float sgn,
-                               float *__restrict__ XA, float *__restrict__ XB, float *__restrict__ nrm,
-                               unsigned int *__restrict__ max_nrm_bits) {
+// One warp per row, one float4 of each packed table per lane (Kp / 4 <= 32 of them), two rows in flight.  XB and
+// nrm cover the whole table (every rank scores its rows against ALL columns), XA only the shard's rows.
+__global__ void __launch_bounds__(256)
+tc_pack_kernel(const float *__restrict__ E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, int Kp,
+               float sgn, float *__restrict__ XA, float *__restrict__ XB, float *__restrict__ nrm,
+               unsigned int *__restrict__ max_nrm_bits) {
   const int lane = threadIdx.x & 31;
   const int d = D - 1;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r = warp; r < n; r += nwarps) {
-    const float *row = E + r * ldE;
-    const float x0 = row[0];
-    const float hi = __uint_as_float(__float_as_uint(x0) & 0xffffe000u);
-    const float lo = x0 - hi;                      // exact; NaN / inf propagate into the accumulator as they should
-    float ss = 0.f;
-    for (int k = lane; k < Kp; k += 32) {
-      float a = 0.f, b = 0.f;
-      if (k < d) {
-        a = row[1 + k];
-        b = -sgn * a;
-        ss = fmaf(a, a, ss);
-      } else if (k < d + 4) {
-        const int t = k - d;
-        a = (t & 1) ? lo : hi;                     // hi, lo, hi, lo
-        b = sgn * (t < 2 ? hi : lo);               // hi, hi, lo, lo
+  const bool active = 4 * lane < Kp;
+  float wmax = 0.f;
+  for (int64_t r0 = 2 * warp; r0 < n; r0 += 2 * nwarps) {
+    float a[2][4], x0[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t r = r0 + h < n ? r0 + h : r0;
+      const float *row = E + r * ldE;
+      x0[h] = __ldg(row);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int k = 4 * lane + t;
+        a[h][t] = k < d ? __ldg(row + 1 + k) : 0.f;
       }
-      XA[r * Kp + k] = a;
-      XB[r * Kp + k] = b;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(HYP_FULL_MASK, ss, o);
-    if (lane == 0) {
-      float nr = sqrtf(ss);
-      nrm[r] = nr;
-      if (nr == nr) atomicMax(max_nrm_bits, __float_as_uint(nr));
+    for (int h = 0; h < 2; ++h) {
+      const int64_t r = r0 + h;
+      if (r >= n) break;
+      const float hi = __uint_as_float(__float_as_uint(x0[h]) & 0xffffe000u);
+      const float lo = x0[h] - hi;                 // exact; NaN / inf propagate into the accumulator as they should
+      float va[4], vb[4], ss = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int k = 4 * lane + t;
+        if (k < d) {
+          va[t] = a[h][t];
+          vb[t] = -sgn * a[h][t];
+          ss = fmaf(a[h][t], a[h][t], ss);
+        } else if (k < d + 4) {
+          const int q = k - d;
+          va[t] = (q & 1) ? lo : hi;               // hi, lo, hi, lo
+          vb[t] = sgn * (q < 2 ? hi : lo);         // hi, hi, lo, lo
+        } else {
+          va[t] = 0.f;
+          vb[t] = 0.f;
+        }
+      }
+      if (active) {
+        *reinterpret_cast<float4 *>(XB + r * Kp + 4 * lane) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+        if (r >= row0 && r < row0 + nrows)
+          *reinterpret_cast<float4 *>(XA + (r - row0) * Kp + 4 * lane) = make_float4(va[0], va[1], va[2], va[3]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(HYP_FULL_MASK, ss, o);
+      const float nr = sqrtf(ss);
+      if (lane == 0) nrm[r] = nr;
+      if (nr == nr) wmax = fmaxf(wmax, nr);
     }
   }
+  if (lane == 0 && wmax > 0.f) atomicMax(max_nrm_bits, __float_as_uint(wmax));
 }
 
 struct TcParams {
   int64_t n;          // table rows (columns of the Gram matrix)
-  int64_t row0;       // shard start
+  int64_t row0;       // shard start (XA and its tensor map start at this row)
   int64_t nrows;      // shard rows
   int n_slabs;        // full 128-byte-row slabs (32 floats each)
   int tail_row_bytes; // 0, 32 or 64: one more slab with narrow rows for K mod 32 in {8, 16}
   int stage_bytes;    // bytes of one operand tile in shared memory (1024-aligned)
   int n_stages;       // depth of the B ring
-  int n_ksteps;       // ceil(d / 8) MMAs per tile
+  int n_ksteps;       // ceil((d + 4) / 8) MMAs per tile
   int debug;          // HYP_TC_DEBUG bit 0: epilogue skips TMEM loads + math, bit 1: no MMAs issued, bit 2: no TMA,
                       //              bit 3: epilogue loads TMEM but skips the math
-  int rb_per_cta;     // 2: two row blocks share each B tile; 1: small shards (fewer than two row blocks per SM)
+  int rb_per_cta;     // 2: two row blocks share each B tile; 1: one row block per item
   int64_t n_ct;       // column tiles this pass visits: ct = t * ct_step, t in [0, n_ct)
-  int ct_step;        // 1 = every tile; pass 1 may sample (see hyp_gram_topk)
+  int ct_step;        // 1 = every tile; pass 1 samples (see hyp_gram_topk)
+  int n_seg;          // column segments: work item w = (row pair w / n_seg, segment w % n_seg)
+  int64_t seg_tiles;  // visited tiles per segment: t in [s * seg_tiles, min((s + 1) * seg_tiles, n_ct))
   // pass 1
-  float *tilemin;     // [col_tiles][ld_tm]
+  float *tilemin;     // [n_ct][ld_tm]
   int64_t ld_tm;
   // pass 2
   const float *thr;   // [nrows] tau + 2 eps
-  int32_t *cand;      // [nrows][TC_CAP]
-  int32_t *cand_cnt;  // [nrows][2]: the list as two halves of <= TC_CAPH entries (second > TC_CAPH == overflow)
+  int32_t *cand;      // [nrows][TC_CAND_ROW]: segment s of a row owns slots [s * seg_cap, (s + 1) * seg_cap)
+  int32_t *cand_cnt;  // [nrows][TC_MAX_SEG]: hits per segment (> seg_cap == overflow)
+  int seg_cap;
 };
 
 template <int PASS>
@@ -284,7 +320,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row_blocks = (p.nrows + TC_M - 1) / TC_M;
-  const int64_t row_pairs = (row_blocks + p.rb_per_cta - 1) / p.rb_per_cta;   // work items: pairs (or single blocks)
+  const int64_t row_pairs = (row_blocks + p.rb_per_cta - 1) / p.rb_per_cta;   // pairs (or single blocks)
+  const int64_t items = row_pairs * p.n_seg;       // work items: (row pair, column segment), segment fastest
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1);
@@ -309,18 +346,21 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t bstage = 0, bphase = 0, aphase = 0;
-      for (int64_t rp = blockIdx.x; rp < row_pairs; rp += gridDim.x) {
+      for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
+        const int64_t rp = w / p.n_seg;
+        const int64_t t0 = (w - rp * p.n_seg) * p.seg_tiles;
+        const int64_t t1 = t0 + p.seg_tiles < p.n_ct ? t0 + p.seg_tiles : p.n_ct;
         mbar_wait(a_empty, aphase ^ 1);
         mbar_expect_tx(a_full, p.rb_per_cta * tile_tx);
         for (int h = 0; h < p.rb_per_cta; ++h) {
-          // (rows past the table are zero-filled by TMA; their results are never written)
+          // (the A map covers the shard's rows only; rows past it are zero-filled by TMA, their results never written)
           uint8_t *dstA = sA + (size_t)h * p.stage_bytes;
-          const int arow = (int)(p.row0 + (p.rb_per_cta * rp + h) * TC_M);
+          const int arow = (int)((p.rb_per_cta * rp + h) * TC_M);
           for (int s = 0; s < p.n_slabs; ++s) tma_load_2d(&tmapA, a_full, dstA + s * TC_SLAB_BYTES, s * TC_KSLAB, arow);
           if (p.tail_row_bytes) tma_load_2d(&tmapA_tail, a_full, dstA + p.n_slabs * TC_SLAB_BYTES, tail_elem0, arow);
         }
         aphase ^= 1;
-        for (int64_t t = 0; t < p.n_ct; ++t) {
+        for (int64_t t = t0; t < t1; ++t) {
           const int64_t ct = t * p.ct_step;
           mbar_wait(b_empty + bstage, bphase ^ 1);
           if (p.debug & 4) { mbar_arrive(b_full + bstage); if (++bstage == (uint32_t)p.n_stages) { bstage = 0; bphase ^= 1; } continue; }
@@ -361,10 +401,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       const int nk = (p.debug & 2) ? 0 : p.n_ksteps;
       uint32_t bstage = 0, bphase = 0, aphase = 0;
       uint32_t tt = 0;                      // tiles issued by this CTA: accumulators 2*(tt&1)+h, use number tt>>1
-      for (int64_t rp = blockIdx.x; rp < row_pairs; rp += gridDim.x) {
+      for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
+        const int64_t t0 = (w % p.n_seg) * p.seg_tiles;
+        const int64_t t1 = t0 + p.seg_tiles < p.n_ct ? t0 + p.seg_tiles : p.n_ct;
         mbar_wait(a_full, aphase);
         aphase ^= 1;
-        for (int64_t t = 0; t < p.n_ct; ++t, ++tt) {
+        for (int64_t t = t0; t < t1; ++t, ++tt) {
           mbar_wait(b_full + bstage, bphase);
           const uint32_t b_lo = ((smem_u32(sB + (size_t)bstage * p.stage_bytes) >> 4) & 0x3fff) | (1u << 16);
           if (!idle) {
@@ -403,34 +445,20 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     const int lane_base = 32 * quad;
     const int r_in_block = lane_base + lane;         // row of the tile
     const float inf = __int_as_float(0x7f800000);
-    const int64_t my_pairs = (row_pairs > blockIdx.x) ? (row_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total = grp < p.rb_per_cta ? my_pairs * p.n_ct : 0;
-    int64_t cur_rbi = -1, blk0 = 0, gi = 0;
-    bool row_ok = false;
-    float thr = 0.f;
-    int cnt = 0;
-    int32_t *my_cand = p.cand;
-    auto flush_count = [&]() {
-      // the finish kernel reads a row's list as two halves of TC_CAPH entries (they are contiguous)
-      const int c0 = cnt < TC_CAPH ? cnt : TC_CAPH;
-      p.cand_cnt[(gi - p.row0) * 2] = c0;
-      p.cand_cnt[(gi - p.row0) * 2 + 1] = cnt - c0;        // > TC_CAPH  <=>  overflow
-    };
-    // (tile counters are carried, not divided out of T: two 64-bit divisions per tile were as expensive as the math)
-    int64_t rbi = 0, tix = 0;
-    for (int64_t T = 0; T < total; ++T, ++tix) {
-      if (tix == p.n_ct) { tix = 0; ++rbi; }
+    uint32_t T = 0;                                  // tiles drained by this group so far (accumulator ring position)
+    for (int64_t w = blockIdx.x; w < items && grp < p.rb_per_cta; w += gridDim.x) {
+      const int64_t rp = w / p.n_seg;
+      const int seg = (int)(w - rp * p.n_seg);
+      const int64_t t0 = seg * p.seg_tiles;
+      const int64_t t1 = t0 + p.seg_tiles < p.n_ct ? t0 + p.seg_tiles : p.n_ct;
+      const int64_t blk0 = p.row0 + (rp * p.rb_per_cta + grp) * TC_M;
+      const int64_t gi = blk0 + r_in_block;
+      const bool row_ok = gi < p.row0 + p.nrows;
+      const float thr = (PASS == 2 && row_ok) ? __ldg(p.thr + (gi - p.row0)) : -inf;
+      int cnt = 0;
+      int32_t *const my_cand = p.cand + (gi - p.row0) * TC_CAND_ROW + (int64_t)seg * p.seg_cap;
+      for (int64_t tix = t0; tix < t1; ++tix, ++T) {
       const int64_t ct = tix * p.ct_step;
-      if (rbi != cur_rbi) {
-        if (PASS == 2 && cur_rbi >= 0 && row_ok) flush_count();
-        cur_rbi = rbi;
-        blk0 = p.row0 + ((blockIdx.x + rbi * gridDim.x) * p.rb_per_cta + grp) * TC_M;
-        gi = blk0 + r_in_block;
-        row_ok = gi < p.row0 + p.nrows;
-        if (PASS == 2) thr = row_ok ? __ldg(p.thr + (gi - p.row0)) : -inf;
-        cnt = 0;
-        my_cand = p.cand + (gi - p.row0) * TC_CAP;
-      }
       const uint32_t abuf = 2 * (uint32_t)(T & 1) + grp, accphase = (uint32_t)((T >> 1) & 1);
       const int64_t j0 = ct * TC_N;
       mbar_wait(acc_full + abuf, accphase);
@@ -468,7 +496,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             hits &= hits - 1;
             const int64_t gj = j0 + chunk * 32 + c;
             if (!checked || (gj < p.n && gj != gi)) {
-              if (cnt < TC_CAP) my_cand[cnt] = (int32_t)gj;
+              if (cnt < p.seg_cap) my_cand[cnt] = (int32_t)gj;
               ++cnt;
             }
           }
@@ -501,8 +529,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + abuf);
       if (PASS == 1 && row_ok) p.tilemin[tix * p.ld_tm + (gi - p.row0)] = fmaxf(tmin, 1.0f);
+      }
+      // hits of this (row, segment); every segment of every shard row is written by exactly one item
+      if (PASS == 2 && row_ok) p.cand_cnt[(gi - p.row0) * TC_MAX_SEG + seg] = cnt;
     }
-    if (PASS == 2 && cur_rbi >= 0 && row_ok) flush_count();
   }
 
   tc_fence_before();
@@ -550,20 +580,39 @@ __global__ void kth_select_kernel(const float *__restrict__ tilemin, int64_t ld_
   thr[r] = tau + 2.f * eps;
 }
 
-// exact fp32 re-score of each row's candidates (ATen order), sort by (d, j), write the first k.
-// One warp per row.  flags[r] = 1 when the candidate buffer overflowed (row must be redone exactly).
+// exact fp32 re-score of each row's candidates (ATen order), sort by (d, j), write the first k into `sink`.
+// One warp per row.  A row whose candidate buffers overflowed (massive ties) is not written: flags[r] = 1 and the
+// row is appended to flist for the exact redo that follows on the same stream.
 __global__ void __launch_bounds__(128)
 tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, int64_t nrows, float sqrt_c, float sgn,
-                 int k, const int32_t *__restrict__ cand, const int32_t *__restrict__ cand_cnt,
-                 int32_t *__restrict__ out_idx, float *__restrict__ out_d, int32_t *__restrict__ flags) {
+                 int k, const int32_t *__restrict__ cand, const int32_t *__restrict__ cand_cnt, int n_seg, int seg_cap,
+                 const TopkSink sink, int32_t *__restrict__ flags, int32_t *__restrict__ flist,
+                 int32_t *__restrict__ nflag) {
   __shared__ unsigned long long keys[4][TC_CAP];
+  __shared__ int32_t cj[4][TC_CAP];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const unsigned long long kEmpty = 0xffffffffffffffffULL;
   for (int64_t r = (int64_t)blockIdx.x * 4 + w; r < nrows; r += (int64_t)gridDim.x * 4) {
-    const int c0 = cand_cnt[2 * r], c1 = cand_cnt[2 * r + 1];
-    const bool overflow = c0 > TC_CAPH || c1 > TC_CAPH || c0 < 0 || c1 < 0;
-    const int m0 = overflow ? 0 : c0, m1 = overflow ? 0 : c1;
-    for (int q = lane; q < m0 + m1; q += 32) keys[w][q] = kEmpty;
+    // the row's candidates: n_seg lists (one per column segment) -> one contiguous list in shared memory
+    const int c_mine = lane < n_seg ? cand_cnt[r * TC_MAX_SEG + lane] : 0;
+    int incl = c_mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(HYP_FULL_MASK, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const int mtot_raw = __shfl_sync(HYP_FULL_MASK, incl, 31);
+    const bool overflow = __any_sync(HYP_FULL_MASK, c_mine < 0 || c_mine > seg_cap) || mtot_raw > TC_CAP;
+    const int mtot = overflow ? 0 : mtot_raw;
+    if (!overflow) {
+      for (int sg = 0; sg < n_seg; ++sg) {
+        const int cs = __shfl_sync(HYP_FULL_MASK, c_mine, sg);
+        const int os = __shfl_sync(HYP_FULL_MASK, incl, sg) - cs;
+        const int32_t *src = cand + r * TC_CAND_ROW + (int64_t)sg * seg_cap;
+        for (int t = lane; t < cs; t += 32) cj[w][os + t] = src[t];
+      }
+    }
+    for (int q = lane; q < mtot; q += 32) keys[w][q] = kEmpty;
     __syncwarp();
     // exact re-score, four candidates per warp pass: a group of 8 lanes IS ATen's 8 summation lanes
     // (lane l owns elements 8k+l, partial k mod 4), so the order is reproduced with 4 registers per lane
@@ -577,7 +626,7 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
 #pragma unroll
       for (int kk = 0; kk < 16; ++kk) xr[kk] = kk < vs ? __ldg(xi + 1 + 8 * kk + l8) : 0.f;
       const float xi0 = __ldg(xi);
-      for (int q0 = 0; q0 < m0 + m1; q0 += 4 * kInFlight) {
+      for (int q0 = 0; q0 < mtot; q0 += 4 * kInFlight) {
         // kInFlight candidates per 8-lane group and pass: their loads are issued together
         float Ll[kInFlight], tailv[kInFlight], xj0[kInFlight];
         int jv[kInFlight];
@@ -585,9 +634,8 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
 #pragma unroll
         for (int h = 0; h < kInFlight; ++h) {
           const int q = q0 + 4 * h + grp;
-          livev[h] = q < m0 + m1;
-          const int qq = livev[h] ? q : 0;
-          jv[h] = qq < m0 ? cand[(2 * r) * TC_CAPH + qq] : cand[(2 * r + 1) * TC_CAPH + (qq - m0)];
+          livev[h] = q < mtot;
+          jv[h] = cj[w][livev[h] ? q : 0];
         }
         float yv[kInFlight][16];
 #pragma unroll
@@ -625,8 +673,8 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
         }
       }
     } else {
-      for (int q = 0; q < m0 + m1; ++q) {
-        const int j = q < m0 ? cand[(2 * r) * TC_CAPH + q] : cand[(2 * r + 1) * TC_CAPH + (q - m0)];
+      for (int q = 0; q < mtot; ++q) {
+        const int j = cj[w][q];
         const float mm = warp_mdot(xi, E + (int64_t)j * ldE, D, lane);
         if (lane == 0) {
           const float dv = dist_from_mdot(mm, sgn, sqrt_c);
@@ -635,28 +683,27 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
       }
     }
     __syncwarp();
-    // rank sort of the m0 + m1 keys, all distinct (distinct j)
-    const int mtot = m0 + m1;
-    for (int q = lane; q < mtot; q += 32) {
-      const unsigned long long mine = keys[w][q];
-      if (mine == kEmpty) continue;
-      int rank = 0;
-      for (int t = 0; t < mtot; ++t) rank += keys[w][t] < mine;
-      if (rank < k) {
-        out_idx[r * k + rank] = (int32_t)(mine & 0xffffffffu);
-        out_d[r * k + rank] = __uint_as_float((unsigned int)(mine >> 32));
+    if (!overflow) {
+      // rank sort of the keys, all distinct (distinct j)
+      for (int q = lane; q < mtot; q += 32) {
+        const unsigned long long mine = keys[w][q];
+        if (mine == kEmpty) continue;
+        int rank = 0;
+        for (int t = 0; t < mtot; ++t) rank += keys[w][t] < mine;
+        if (rank < k)
+          sink_write(sink, r, k, rank, (int32_t)(mine & 0xffffffffu), __uint_as_float((unsigned int)(mine >> 32)));
       }
-    }
-    // pad (fewer than k valid candidates can only happen with < k finite distances in the row)
-    int valid = 0;
-    for (int t = lane; t < mtot; t += 32) valid += keys[w][t] != kEmpty;
+      // pad (fewer than k valid candidates can only happen with < k finite distances in the row)
+      int valid = 0;
+      for (int t = lane; t < mtot; t += 32) valid += keys[w][t] != kEmpty;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(HYP_FULL_MASK, valid, o);
-    for (int q = valid + lane; q < k; q += 32) {
-      out_idx[r * k + q] = -1;
-      out_d[r * k + q] = __int_as_float(0x7f800000);
+      for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(HYP_FULL_MASK, valid, o);
+      for (int q = valid + lane; q < k; q += 32) sink_write(sink, r, k, q, -1, __int_as_float(0x7f800000));
     }
-    if (lane == 0) flags[r] = overflow ? 1 : 0;
+    if (lane == 0) {
+      flags[r] = overflow ? 1 : 0;
+      if (overflow) flist[atomicAdd(nflag, 1)] = (int32_t)r;
+    }
     __syncwarp();
   }
 }
@@ -684,7 +731,7 @@ static EncodeTiledFn get_encode() {
 struct TcLayout {
   int Kp, n_slabs, n_ksteps, tail_row_bytes, stage_bytes, n_stages;
   int64_t ld_tm, col_tiles;
-  size_t off_xp, off_x0, off_nrm, off_max, off_tilemin, off_thr, off_cand, off_cnt, off_flags, total;
+  size_t off_xa, off_xb, off_nrm, off_max, off_tilemin, off_thr, off_cand, off_cnt, off_flist, total;
 };
 
 static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
@@ -699,7 +746,7 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
   if (rem == 24) { L.n_slabs += 1; rem = 0; }   // 96-byte rows have no swizzle mode: take a full slab
   L.tail_row_bytes = rem * 4;
   L.stage_bytes = ((L.n_slabs * TC_SLAB_BYTES + TC_M * L.tail_row_bytes + 1023) / 1024) * 1024;
-  const int budget = 226 * 1024 - 4096;     // two A tiles + the B ring (+ 1 KB alignment, colx0, barriers)
+  const int budget = 226 * 1024 - 4096;     // two A tiles + the B ring (+ 1 KB alignment, barriers)
   L.n_stages = (budget - 2 * L.stage_bytes) / L.stage_bytes;
   if (L.n_stages > 2) L.n_stages = 2;      // measured: a deeper B ring does not help (the MMA issue rate and the
                                             // TMEM drain, not TMA latency, bound the tile loop); HYP_TC_STAGES overrides
@@ -712,43 +759,50 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
   L.ld_tm = ((nrows + 31) / 32) * 32;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
-  L.off_xp = take((size_t)n * L.Kp * 4);     // XA
-  L.off_x0 = take((size_t)n * L.Kp * 4);     // XB
+  L.off_xa = take((size_t)nrows * L.Kp * 4);   // XA: the shard's rows as A operands
+  L.off_xb = take((size_t)n * L.Kp * 4);       // XB: every row as a B operand
   L.off_nrm = take((size_t)n * 4);
-  L.off_max = take(256);
+  L.off_max = take(256);                       // [0] max norm bits, [1] number of flagged rows
   L.off_tilemin = take((size_t)L.col_tiles * L.ld_tm * 4);
   L.off_thr = take((size_t)nrows * 4);
-  L.off_cand = take((size_t)nrows * TC_CAP * 4);
-  L.off_cnt = take((size_t)nrows * 2 * 4);
-  L.off_flags = take((size_t)nrows * 4);
+  L.off_cand = take((size_t)nrows * TC_CAND_ROW * 4);
+  L.off_cnt = take((size_t)nrows * TC_MAX_SEG * 4);
+  L.off_flist = take((size_t)nrows * 4);
   L.total = o;
   return L;
 }
 
-}  // namespace hyp
-
-using namespace hyp;
-
-extern "C" int64_t hyp_gram_topk_workspace_bytes(int64_t n, int64_t nrows, int D) {
-  if (n < 0 || nrows < 0 || D < 2 || D - 1 + 4 > TC_MAX_SLABS * TC_KSLAB) return -1;
-  return (int64_t)tc_layout(n, nrows, D).total;
+// Work decomposition of one pass: `pairs` row block pairs (or single blocks) x n_seg column segments over `sms`
+// persistent CTAs.  Cost model in tile-times: waves * (tiles per segment + 2 for the A tiles of the item); the
+// smallest segment count that reaches the minimum wins (fewer A loads, longer candidate lists per segment).
+static void tc_segments(int64_t pairs, int64_t n_ct, int sms, int &n_seg, int64_t &seg_tiles) {
+  if (n_ct < 1) n_ct = 1;
+  int lo = 1, hi = TC_MAX_SEG;
+  if (const char *e = getenv("HYP_TC_SEG")) {          // force a segment count (tests, tuning)
+    const int f = atoi(e);
+    if (f >= 1 && f <= TC_MAX_SEG) lo = hi = f;
+  }
+  double best = 1e300;
+  n_seg = 1;
+  seg_tiles = n_ct;
+  for (int S = lo; S <= hi; ++S) {
+    const int64_t st = (n_ct + S - 1) / S;
+    if (lo != hi && S > 1 && st < 12) break;           // segments too short to amortise their A tiles
+    const int64_t seff = (n_ct + st - 1) / st;         // no empty segments
+    const int64_t waves = (pairs * seff + sms - 1) / sms;
+    const double cost = (double)waves * (double)(st + 2);
+    if (cost < best * 0.995) {
+      best = cost;
+      n_seg = (int)seff;
+      seg_tiles = st;
+    }
+  }
 }
 
-extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c,
-                             int semantics, int k, int32_t *out_idx, float *out_d, int32_t *row_flags, void *workspace,
-                             int64_t workspace_bytes, void *stream) {
-  if (n < 0 || row0 < 0 || nrows < 0 || row0 + nrows > n || D < 2 || !(c > 0.f) || k < 1 || k > 32) {
-    set_error("hyp_gram_topk: bad arguments (n=%lld row0=%lld nrows=%lld D=%d k=%d, k <= %d)", (long long)n,
-              (long long)row0, (long long)nrows, D, k, 32);
-    return HYP_ERR_ARG;
-  }
-  if (D - 1 + 4 > TC_MAX_SLABS * TC_KSLAB) {
-    set_error("hyp_gram_topk: d=%d (+4 time-like columns) exceeds the %d columns one shared-memory tile holds", D - 1,
-              TC_MAX_SLABS * TC_KSLAB);
-    return HYP_ERR_UNSUPPORTED;
-  }
-  if (nrows == 0) return HYP_OK;
-  if (!E || !out_idx || !out_d || !row_flags || !workspace) return HYP_ERR_ARG;
+// The whole pipeline on `st`: pack, bound pass, select, collect pass, finish, exact redo of flagged rows.
+int gram_topk_run(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c, int semantics,
+                  int k, const TopkSink &sink, int32_t *row_flags, void *workspace, int64_t workspace_bytes,
+                  cudaStream_t st) {
   const TcLayout L = tc_layout(n, nrows, D);
   if (workspace_bytes < (int64_t)L.total) {
     set_error("hyp_gram_topk: workspace %lld < %zu bytes", (long long)workspace_bytes, L.total);
@@ -763,13 +817,14 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
     set_error("hyp_gram_topk: cuTensorMapEncodeTiled is unavailable in this driver");
     return HYP_ERR_UNSUPPORTED;
   }
-  cudaStream_t st = (cudaStream_t)stream;
   uint8_t *ws = (uint8_t *)workspace;
-  float *XA = (float *)(ws + L.off_xp), *XB = (float *)(ws + L.off_x0), *nrm = (float *)(ws + L.off_nrm);
+  float *XA = (float *)(ws + L.off_xa), *XB = (float *)(ws + L.off_xb), *nrm = (float *)(ws + L.off_nrm);
   const float sgn = semantics == HYP_SEM_REFERENCE ? -1.f : 1.f;
   unsigned int *maxn = (unsigned int *)(ws + L.off_max);
+  int32_t *nflag = (int32_t *)(ws + L.off_max) + 1;
   float *tilemin = (float *)(ws + L.off_tilemin), *thr = (float *)(ws + L.off_thr);
   int32_t *cand = (int32_t *)(ws + L.off_cand), *cnt = (int32_t *)(ws + L.off_cnt);
+  int32_t *flist = (int32_t *)(ws + L.off_flist);
 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -777,20 +832,24 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
 
   // HYP_TC_TIMING=1: per-stage device times on stderr (synchronises; for tuning only)
   const bool timing = getenv("HYP_TC_TIMING") != nullptr;
-  cudaEvent_t tev[6];
+  cudaEvent_t tev[7];
   if (timing) {
     for (auto &e : tev) cudaEventCreate(&e);
     cudaEventRecord(tev[0], st);
   }
-  cudaMemsetAsync(maxn, 0, 4, st);
-  cudaMemsetAsync(cnt, 0, (size_t)nrows * 2 * sizeof(int32_t), st);
-  tc_pack_kernel<<<sms * 4, 256, 0, st>>>(E, ldE, n, D, L.Kp, sgn, XA, XB, nrm, maxn);
+  cudaMemsetAsync(maxn, 0, 8, st);           // max norm and the flagged-row counter
+  {
+    int64_t blocks = (n + 15) / 16;            // 8 warps x 2 rows per block and sweep
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    tc_pack_kernel<<<(int)blocks, 256, 0, st>>>(E, ldE, n, row0, nrows, D, L.Kp, sgn, XA, XB, nrm, maxn);
+  }
   int rc = check_launch("hyp_gram_topk(pack)");
   if (rc) return rc;
 
   if (timing) cudaEventRecord(tev[1], st);
 
-  const cuuint64_t gdim[2] = {(cuuint64_t)L.Kp, (cuuint64_t)n};
+  const cuuint64_t gdimA[2] = {(cuuint64_t)L.Kp, (cuuint64_t)nrows};
+  const cuuint64_t gdimB[2] = {(cuuint64_t)L.Kp, (cuuint64_t)n};
   const cuuint64_t gstride[1] = {(cuuint64_t)L.Kp * 4};
   const cuuint32_t box[2] = {(cuuint32_t)TC_KSLAB, (cuuint32_t)TC_M};
   const cuuint32_t tbox[2] = {(cuuint32_t)(L.tail_row_bytes ? L.tail_row_bytes / 4 : TC_KSLAB), (cuuint32_t)TC_M};
@@ -802,9 +861,9 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
     const CUtensorMapSwizzle sw = !tail || !L.tail_row_bytes ? CU_TENSOR_MAP_SWIZZLE_128B
                                   : L.tail_row_bytes == 32   ? CU_TENSOR_MAP_SWIZZLE_32B
                                                              : CU_TENSOR_MAP_SWIZZLE_64B;
-    CUresult cr = encode(&maps[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, tail ? tbox : box, estride,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult cr = encode(&maps[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, m < 2 ? gdimA : gdimB, gstride,
+                         tail ? tbox : box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
       set_error("hyp_gram_topk: cuTensorMapEncodeTiled failed (%d) for map %d", (int)cr, m);
       return HYP_ERR_CUDA;
@@ -822,22 +881,26 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int64_t row_blocks = (nrows + TC_M - 1) / TC_M;
-  p.rb_per_cta = row_blocks >= 2 * (int64_t)sms ? 2 : 1;     // pairing only pays once every SM has a pair
+  // Two row blocks per item halve the L2 -> SM traffic of the column stream (the first bound this kernel hit); the
+  // column segments provide the parallelism a small shard lacks, so pairing needs only two row blocks.
+  p.rb_per_cta = row_blocks >= 2 ? 2 : 1;
   if (const char *e = getenv("HYP_TC_PAIR")) p.rb_per_cta = atoi(e) == 1 ? 1 : 2;
   const int64_t row_pairs = (row_blocks + p.rb_per_cta - 1) / p.rb_per_cta;
-  const int grid = (int)(row_pairs < sms ? row_pairs : sms);
 
   // Pass 1 only has to BOUND each row's k-th best from above, and the k-th smallest minimum over ANY >= k distinct
   // column tiles does that: it visits every `step`-th tile.  The bound sits near rank k*step instead of k, so pass 2
   // collects ~step times as many candidates for the exact re-score; the two costs balance at step 2-3 at V=100k
-  // (7.4 / 7.5 ms; HYP_TC_SUB overrides).  Small tables keep every tile (at least 4k sampled tiles are required).
+  // (HYP_TC_SUB overrides).  Small tables keep every tile (at least 4k sampled tiles are required).
   int step = 2;
   if (const char *e = getenv("HYP_TC_SUB")) step = atoi(e);
   if (step < 1) step = 1;
   while (step > 1 && (L.col_tiles + step - 1) / step < 4 * (int64_t)k) --step;
   p.ct_step = step;
   p.n_ct = (L.col_tiles + step - 1) / step;
-  k1<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  tc_segments(row_pairs, p.n_ct, sms, p.n_seg, p.seg_tiles);
+  p.seg_cap = 0;
+  int64_t items = row_pairs * p.n_seg;
+  k1<<<(int)(items < sms ? items : sms), TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   rc = check_launch("hyp_gram_topk(pass 1)");
   if (rc) return rc;
   if (timing) cudaEventRecord(tev[2], st);
@@ -848,23 +911,71 @@ extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row
   if (timing) cudaEventRecord(tev[3], st);
   p.ct_step = 1;
   p.n_ct = L.col_tiles;
-  k2<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  tc_segments(row_pairs, p.n_ct, sms, p.n_seg, p.seg_tiles);
+  p.seg_cap = (TC_CAND_ROW / p.n_seg) & ~7;
+  if (p.seg_cap > TC_CAP) p.seg_cap = TC_CAP;
+  items = row_pairs * p.n_seg;
+  k2<<<(int)(items < sms ? items : sms), TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   rc = check_launch("hyp_gram_topk(pass 2)");
   if (rc) return rc;
   int64_t fb = (nrows + 3) / 4;
   if (fb > sms * 16) fb = sms * 16;
   if (timing) cudaEventRecord(tev[4], st);
-  tc_finish_kernel<<<(int)fb, 128, 0, st>>>(E, ldE, D, row0, nrows, sqrtf(c), sgn, k, cand, cnt, out_idx, out_d,
-                                           row_flags);
+  tc_finish_kernel<<<(int)fb, 128, 0, st>>>(E, ldE, D, row0, nrows, sqrtf(c), sgn, k, cand, cnt, p.n_seg, p.seg_cap,
+                                           sink, row_flags, flist, nflag);
   rc = check_launch("hyp_gram_topk(finish)");
+  if (rc) return rc;
+  if (timing) cudaEventRecord(tev[5], st);
+  // flagged rows (none on non-degenerate data): the exact kernel reads their number from the device and returns at once
+  // when there is nothing to do
+  rc = launch_allpairs_topk(E, ldE, n, row0, nrows, D, c, semantics, k, sink, flist, nflag, st);
   if (timing) {
-    cudaEventRecord(tev[5], st);
-    cudaEventSynchronize(tev[5]);
-    float ms[5];
-    for (int q = 0; q < 5; ++q) cudaEventElapsedTime(&ms[q], tev[q], tev[q + 1]);
-    fprintf(stderr, "[hyp_gram_topk] step=%d pack %.3f  pass1 %.3f  select %.3f  pass2 %.3f  finish %.3f ms\n", step, ms[0],
-            ms[1], ms[2], ms[3], ms[4]);
+    cudaEventRecord(tev[6], st);
+    cudaEventSynchronize(tev[6]);
+    float ms[6];
+    for (int q = 0; q < 6; ++q) cudaEventElapsedTime(&ms[q], tev[q], tev[q + 1]);
+    fprintf(stderr, "[hyp_gram_topk] step=%d seg=%d/%d rb=%d pack %.3f  pass1 %.3f  select %.3f  pass2 %.3f  finish %.3f  "
+                    "redo %.3f ms\n", step, p.n_seg, (int)p.seg_tiles, p.rb_per_cta, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5]);
     for (auto &e : tev) cudaEventDestroy(e);
   }
   return rc;
+}
+
+}  // namespace hyp
+
+using namespace hyp;
+
+extern "C" int64_t hyp_gram_topk_workspace_bytes(int64_t n, int64_t nrows, int D) {
+  if (n < 0 || nrows < 0 || D < 2 || D - 1 + 4 > TC_MAX_SLABS * TC_KSLAB) return -1;
+  return (int64_t)tc_layout(n, nrows, D).total;
+}
+
+namespace hyp {
+int gram_topk_check_args(int64_t n, int64_t row0, int64_t nrows, int D, float c, int k) {
+  if (n < 0 || row0 < 0 || nrows < 0 || row0 + nrows > n || D < 2 || !(c > 0.f) || k < 1 || k > 32) {
+    set_error("hyp_gram_topk: bad arguments (n=%lld row0=%lld nrows=%lld D=%d k=%d, k <= %d)", (long long)n,
+              (long long)row0, (long long)nrows, D, k, 32);
+    return HYP_ERR_ARG;
+  }
+  if (D - 1 + 4 > TC_MAX_SLABS * TC_KSLAB) {
+    set_error("hyp_gram_topk: d=%d (+4 time-like columns) exceeds the %d columns one shared-memory tile holds", D - 1,
+              TC_MAX_SLABS * TC_KSLAB);
+    return HYP_ERR_UNSUPPORTED;
+  }
+  return HYP_OK;
+}
+}  // namespace hyp
+
+extern "C" int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c,
+                             int semantics, int k, int32_t *out_idx, float *out_d, int32_t *row_flags, void *workspace,
+                             int64_t workspace_bytes, void *stream) {
+  int rc = gram_topk_check_args(n, row0, nrows, D, c, k);
+  if (rc) return rc;
+  if (nrows == 0) return HYP_OK;
+  if (!E || !out_idx || !out_d || !row_flags || !workspace) return HYP_ERR_ARG;
+  TopkSink sink{};
+  sink.idx = out_idx;
+  sink.d = out_d;
+  return gram_topk_run(E, ldE, n, row0, nrows, D, c, semantics, k, sink, row_flags, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
 }

@@ -596,10 +596,10 @@ extern "C" int hyp_pair_count(const uint8_t *text, int64_t n_bytes, unsigned lon
     return (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;     // HYP_PAIR_COUNT=v1 selects the atomics-only kernel
   }();
   if (variant == 2) {
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaFuncSetAttribute(pair_count_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kV2Smem);
-      attr2 = true;
+    // (per device, so set before every launch: a process-wide "already set" flag would skip it on a second GPU)
+    if (cudaFuncSetAttribute(pair_count_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kV2Smem) != cudaSuccess) {
+      set_error("hyp_pair_count: cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+      return HYP_ERR_CUDA;
     }
     const int64_t chunks2 = (n_bytes + kV2Chunk - 1) / kV2Chunk;
     const int grid2 = (int)(chunks2 < (int64_t)sms ? chunks2 : (int64_t)sms);
@@ -608,10 +608,9 @@ extern "C" int hyp_pair_count(const uint8_t *text, int64_t n_bytes, unsigned lon
     return check_launch("hyp_pair_count");
   }
   const size_t smem = 128 * 128 * sizeof(uint32_t) + kChunk + 2 * kHalo;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
+  if (cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_error("hyp_pair_count: cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+    return HYP_ERR_CUDA;
   }
   int64_t chunks = (n_bytes + kChunk - 1) / kChunk;
   int grid = (int)(chunks < (int64_t)sms * 2 ? chunks : (int64_t)sms * 2);

@@ -214,10 +214,10 @@ extern "C" int hyp_midpoint(const float *E, int64_t ldE, const int32_t *idx_i, c
   if (n == 0) return HYP_OK;
   if (!E || !idx_i || !idx_j || !len_i || !len_j || !out) return HYP_ERR_ARG;
   size_t smem = (size_t)kWarpsPerBlock * 2 * D * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(midpoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
+  // (per device, so set before every launch: a process-wide "already set" flag would skip it on a second GPU)
+  if (cudaFuncSetAttribute(midpoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) {
+    set_error("hyp_midpoint: cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+    return HYP_ERR_CUDA;
   }
   midpoint_kernel<<<grid_for(n), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
       E, ldE, idx_i, idx_j, len_i, len_j, out, ldo, n, D, c, semantics, project);

@@ -40,6 +40,7 @@ extern "C" {
 #define HYP_SEM_LORENTZ 1
 
 #define HYP_MAX_D 1025 /* largest supported row length D = d+1 */
+#define HYP_MAX_PEERS 8 /* GPUs of one NVSwitch domain a hyp_ctx can span */
 
 int hyp_abi_version(void);
 const char *hyp_last_error(void);
@@ -133,16 +134,52 @@ int hyp_allpairs_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int6
                       float c, int semantics, int k, int32_t *out_idx, float *out_d, void *stream);
 
 /* ---- K2 (tensor-core path): the same per-row top-k through a tcgen05 TF32 Gram GEMM ----------
- * (TMA-fed tiles, TMEM accumulators, fused x0_i*x0_j - S / sign / clamp epilogue), used as a
+ * (TMA-fed tiles, TMEM accumulators; the signed Minkowski product, time-like term included as hi/lo
+ * TF32 parts of x0, is ONE MMA chain, so the accumulator is the pre-clamp value itself), used as a
  * certified FILTER: two GEMM passes bound each row's k-th best and collect a provable superset of
- * the exact top-k, which is re-scored in fp32 (ATen order) and sorted.  Results are bit-identical
- * to hyp_allpairs_topk for every row whose row_flags[r] == 0; rows with row_flags[r] != 0 (candidate
- * buffer overflow: massive ties, e.g. the shipped semantics where every distance is 0) must be
- * recomputed with hyp_allpairs_topk by the caller.  k <= 32, d <= 128.  workspace 256-B aligned. */
+ * the exact top-k, which is re-scored in fp32 (ATen order) and sorted.  Rows whose candidate buffers
+ * overflow (massive ties, e.g. the shipped semantics where every distance is 0) are recomputed by the
+ * exact kernel inside the same call (device-driven, no host round trip), so the output is always
+ * bit-identical to hyp_allpairs_topk; row_flags[r] != 0 marks the rows that took that route.
+ * k <= 32, d <= 124.  workspace 256-B aligned. */
 int64_t hyp_gram_topk_workspace_bytes(int64_t n, int64_t nrows, int D);
 int hyp_gram_topk(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t nrows, int D, float c,
                   int semantics, int k, int32_t *out_idx, float *out_d, int32_t *row_flags,
                   void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ---- K8: multi-GPU context and the sharded all-pairs / top-k (BASELINE configs[2]) --------
+ * The reference has no multi-GPU path; this is the north star's "rows shard across the GPUs of one box,
+ * per-shard top-k merged by an all-gather".  A hyp_ctx owns, on every rank, a double-buffered gather buffer
+ * of `world` slots (cudaMalloc) that every peer maps through CUDA IPC, so a kernel on rank r stores its
+ * results straight into all ranks' buffers over NVLink; the remaining collective is one barrier kernel
+ * (release flag to every peer, acquire spin on the local flags, bounded: a missing peer sets the status
+ * word instead of hanging).  One host thread per ctx, one process per GPU, all ranks call in the same order.
+ *   hyp_ctx_create   on the current device; slot_bytes = the most one rank contributes to one gather,
+ *                    a multiple of 256
+ *   hyp_ctx_export   this rank's 64-byte IPC handle (host memory), to be exchanged by the caller
+ *                    (torch.distributed / MPI / files: the library does no host-side communication)
+ *   hyp_ctx_connect  handles of all ranks, rank-major (host memory, world * 64 bytes); world == 1 needs none
+ *   hyp_ctx_status   0, or 1 after a barrier timed out (synchronous copy) */
+typedef struct hyp_ctx hyp_ctx;
+#define HYP_IPC_HANDLE_BYTES 64
+int hyp_ctx_create(hyp_ctx **ctx, int rank, int world, int64_t slot_bytes);
+int hyp_ctx_export(hyp_ctx *ctx, void *handle_out);
+int hyp_ctx_connect(hyp_ctx *ctx, const void *handles);
+int hyp_ctx_status(hyp_ctx *ctx, int *status_out);
+int hyp_ctx_destroy(hyp_ctx *ctx);
+/* All-gather of one slot per rank: `local` (device, 16-byte aligned, bytes % 16 == 0, bytes <= slot_bytes) is
+ * stored into slot `rank` of every rank's buffer; *gathered = this rank's buffer (device pointer, slot g at
+ * g * slot_bytes), complete for every rank once the call's work on `stream` is done.  It stays valid until
+ * the second next gather on this context. */
+int hyp_allgather_topk(hyp_ctx *ctx, const void *local, int64_t bytes, void **gathered, void *stream);
+/* hyp_gram_topk over this rank's row shard [rank * per, ...), per = ceil(n / world), fused with the
+ * all-gather: the finishing kernels write each row's k records {int32 idx, float d} into every rank's buffer.
+ * *gathered: slot g (at g * slot_bytes) = [per][k] records of table rows g * per + r (rows >= n are
+ * unspecified); with slot_bytes == per * k * 8 the buffer is the dense [world * per][k] table.  Needs
+ * slot_bytes >= per * k * 8.  row_flags[per], workspace as for hyp_gram_topk(n, per, D). */
+int hyp_gram_topk_allgather(hyp_ctx *ctx, const float *E, int64_t ldE, int64_t n, int D, float c,
+                            int semantics, int k, int32_t *row_flags, void *workspace,
+                            int64_t workspace_bytes, void **gathered, void *stream);
 
 /* ---- K4/K5: incremental merge loop (hyperbolic_merge.py:309-412, the loop of
  * scripts/train_hyperbolic_tokenizer.py:236-283, fast_hyperbolic_merge.py:467-576) ------------

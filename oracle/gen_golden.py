@@ -24,7 +24,9 @@ import warnings
 
 import numpy as np
 
-REF = "/root/reference"
+# /root/reference in the build container; bench.py --impl reference points this at the staged copy (baseline/_ref,
+# written by tools/stage_reference.py) on the GPU box
+REF = os.environ.get("HYP_REFERENCE_ROOT", "/root/reference")
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 warnings.filterwarnings("ignore")

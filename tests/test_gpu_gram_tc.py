@@ -13,11 +13,14 @@ pytestmark = pytest.mark.gpu
                                                     (2100, 124, 8, 0.1, None, 0), (1500, 7, 4, 0.2, None, 0),
                                                     (3000, 48, 8, 0.1, None, 0), (2000, 16, 4, 0.2, 700, 1300),
                                                     (2500, 90, 8, 0.1, None, 0), (2500, 64, 8, 0.1, None, 0)])
-@pytest.mark.parametrize("pair", ["1", "2"])
-def test_tc_equals_exact(monkeypatch, pair, n, d, k, scale, nrows, row0):
+@pytest.mark.parametrize("pair,seg", [("1", None), ("2", None), ("2", "1"), ("2", "5"), ("1", "16")])
+def test_tc_equals_exact(monkeypatch, pair, seg, n, d, k, scale, nrows, row0):
+    from hyptokenizer_b200 import knn
     from hyptokenizer_b200.knn import lorentz_topk
     from hyptokenizer_b200.synth import synthetic_embeddings
-    monkeypatch.setenv("HYP_TC_PAIR", pair)      # one or two row blocks per CTA (the library picks by shard size)
+    monkeypatch.setenv("HYP_TC_PAIR", pair)      # one or two row blocks per work item
+    if seg is not None:
+        monkeypatch.setenv("HYP_TC_SEG", seg)    # column segments per row pair (default: the library's cost model)
     E = synthetic_embeddings(n, d, scale=scale, seed=n + d, device="cuda")
     nrows = n - row0 if nrows is None else nrows
     ei, ed = lorentz_topk(E, k, 1.0, "lorentz", n, row0, nrows, engine="exact")
@@ -27,8 +30,8 @@ def test_tc_equals_exact(monkeypatch, pair, n, d, k, scale, nrows, row0):
     # with at least ~1.5 k column tiles the filter, not the fallback, does the work on non-degenerate data
     # (fewer than k tiles cannot bound the k-th best: every row is flagged and redone exactly)
     if n >= 128 * k * 3 // 2:
-        assert lorentz_topk.last_flagged <= max(2, nrows // 100)
-    print("flagged", lorentz_topk.last_flagged, "of", nrows)
+        assert knn.last_flagged() <= max(2, nrows // 100)
+    print("flagged", knn.last_flagged(), "of", nrows)
 
 
 def test_tc_degenerate_inputs_fall_back():
@@ -58,7 +61,8 @@ def test_tc_full_size_shard_equals_exact():
     ei, ed = lorentz_topk(E, k, 1.0, "lorentz", n, row0, nrows, engine="exact")
     ti, td = lorentz_topk(E, k, 1.0, "lorentz", n, row0, nrows, engine="tc")
     assert torch.equal(ti, ei) and same_bits(td, ed)
-    assert lorentz_topk.last_flagged == 0
+    from hyptokenizer_b200 import knn
+    assert knn.last_flagged() == 0
 
 
 def test_tc_dimension_limit_and_large_scale():

@@ -113,24 +113,36 @@ def _nccl_worker(rank, world, port, n, k, out):
     from hyptokenizer_b200 import knn
     from hyptokenizer_b200.synth import synthetic_embeddings
     E = synthetic_embeddings(n, 100, scale=0.05, seed=9, device=f"cuda:{rank}")
-    gi, gd = knn.lorentz_topk_sharded(E, k, 1.0, "lorentz")
-    best = knn.best_pair_from_topk(gi, gd)
-    torch.save({"idx": gi.cpu(), "d": gd.cpu(), "best": best}, f"{out}.{rank}")
+    res = {}
+    for engine in ("exact", "tc"):
+        for exchange in ("nccl", "p2p"):
+            for rep in range(3):            # repeated calls exercise the double-buffered gather slots and the epoch flags
+                gi, gd = knn.lorentz_topk_sharded(E, k, 1.0, "lorentz", engine=engine, exchange=exchange)
+            res[f"{engine}/{exchange}"] = (gi.cpu(), gd.cpu(), knn.best_pair_from_topk(gi, gd))
+    ctx = knn.topk_context(n, k, E.device)
+    res["status"] = ctx.status()
+    torch.save(res, f"{out}.{rank}")
+    dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_sharded_topk_nccl(tmp_path):
+@pytest.mark.parametrize("n,k", [(5001, 32), (9000, 5)])
+def test_sharded_topk_multi_gpu(tmp_path, n, k):
+    """Row shards on every GPU of the box, both engines, both exchanges (NCCL all-gather of interleaved records; peer
+    memory: the finishing kernels store into every rank's buffer, hyp_ctx): every rank ends with the single-GPU lists."""
     import torch.multiprocessing as mp
     from hyptokenizer_b200.knn import lorentz_topk
     from hyptokenizer_b200.synth import synthetic_embeddings
     world = min(torch.cuda.device_count(), 8)
-    n, k = 5001, 32
     out = str(tmp_path / "r")
     mp.spawn(_nccl_worker, args=(world, _free_port(), n, k, out), nprocs=world, join=True)
     E = synthetic_embeddings(n, 100, scale=0.05, seed=9, device="cuda:0")
     wi, wd = lorentz_topk(E, k, 1.0, "lorentz")
     res = [torch.load(f"{out}.{r}") for r in range(world)]
     for r in res:
-        assert torch.equal(r["idx"], wi.cpu()) and same_bits(r["d"], wd.cpu())
-        assert r["best"] == res[0]["best"]
+        assert r["status"] == 0
+        for key in ("exact/nccl", "exact/p2p", "tc/nccl", "tc/p2p"):
+            gi, gd, best = r[key]
+            assert torch.equal(gi, wi.cpu()) and same_bits(gd, wd.cpu()), key
+            assert best == res[0]["exact/nccl"][2]
