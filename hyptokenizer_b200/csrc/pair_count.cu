@@ -566,6 +566,326 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// v3 (default): count first, correct later.
+//
+// v2 decides per pair whether it counts (strip() and line breaks) BEFORE touching a counter: three table lookups and a
+// mask computation per byte, and a two-phase update because two lanes share a column -- 33 thread instructions and 7
+// shared-memory operations per byte (ncu, round 1), 10 % of the HBM roofline.  v3 turns it around:
+//  * every adjacent byte pair of an all-ASCII 16-byte group is counted UNCONDITIONALLY in the private table.  A line
+//    break has the junk rank, so pairs that touch one land in junk bins by themselves; what strip() excludes -- pairs
+//    inside the leading / trailing white space of a line -- always contains two ADJACENT bytes <= 0x20, which one AND /
+//    OR per byte over the table entries detects.  Only such a group (and one with a byte outside the private alphabet, a
+//    non-ASCII byte or an end of the text) enters the cold path, which classifies it exactly like v2 and CORRECTS: -1 in
+//    the global table for a private pair that did not count, +1 for a counted pair outside the private alphabet;
+//  * one table lookup per byte: tab[c] = row offset << 16 | flags | column offset, a pair's counter is at
+//    row(first) + column(second) + the lane's base, one IADD3;
+//  * one column of 28 x 28 one-byte bins per LANE, word-interleaved (lane L owns bank L): plain LDS.U8 / +1 / STS.U8 in
+//    ONE phase, conflict-free for any data.  Two consecutive pairs are updated together (both loads, then both stores);
+//    when they hit the same bin the second store carries +2.  8 warps per SM (8 x 24.5 KB of counters), so the stream
+//    is prefetched four 4 KiB steps ahead into registers to keep ~16 KB per SM in flight.
+// Result bits are identical to v1 / v2 for any input (tests/test_gpu_paircount.py runs all three).
+constexpr int kV3Syms = 28;                                // 27 private symbols + the junk rank
+constexpr uint32_t kV3Junk = kV3Syms - 1;
+constexpr int kV3Threads = 256, kV3Warps = kV3Threads / 32;
+constexpr int kV3Chunk = kV3Threads * 16;                  // 4 KiB of text per CTA step
+constexpr int kV3RowBytes = (kV3Syms / 4) * 128;           // a row of 28 bins = 7 words per lane x 32 lanes
+constexpr int kV3PrivPerWarp = kV3Syms * kV3RowBytes;      // 25 088 bytes
+constexpr int kV3Depth = 4;                                // steps in flight per thread
+constexpr size_t kV3Smem = (size_t)kV3Warps * kV3PrivPerWarp + 64 * 64 * 4 + 256 * 4 + 256 * 4 + 256 + 64 + 64;
+constexpr uint32_t kV3FlagJ = 1u << 12;                    // ASCII byte outside the private alphabet (not a line break)
+constexpr uint32_t kV3FlagW = 1u << 13;                    // byte <= 0x20: every str.isspace() ASCII byte and line break
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v)); }
+
+struct V3Cold {
+  uint32_t *hist64;
+  const uint8_t *sym;
+  const uint32_t *tabC;
+  unsigned long long *ascii_counts, *hkeys, *hvals;
+  uint32_t cap_mask;
+  int *overflow;
+  const uint8_t *text;
+  int64_t n;
+};
+
+// does the pair at (pp, pp + 1), neither byte a line break, survive strip()?  (general scans over the text)
+__device__ __noinline__ bool v3_pair_counts(const Text &T, int64_t pp, int64_t n) {
+  auto sp = [&](uint32_t c) -> bool { return (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x20); };
+  const uint32_t a = T.at(pp), bch = T.at(pp + 1);
+  bool left = !sp(a), right = !sp(bch);
+  if (!left) {
+    int64_t q = pp - 1;
+    while (q >= 0) {
+      const uint32_t cq = T.at(q);
+      if (cq >= 0x80) {
+        int l2;
+        const int64_t qs = T.is_start(q) ? q : T.prev_start(q);
+        const uint32_t cp = T.decode(qs, l2);
+        if (!is_space(cp)) { left = true; break; }
+        q = qs - 1;
+        continue;
+      }
+      if (is_nl(cq)) break;
+      if (!sp(cq)) { left = true; break; }
+      --q;
+    }
+  }
+  if (left && !right) {
+    int64_t q = pp + 2;
+    while (q < n) {
+      int l2;
+      const uint32_t cq = T.decode(q, l2);
+      if (is_nl(cq)) break;
+      if (!is_space(cq)) { right = true; break; }
+      q += l2;
+    }
+  }
+  return left && right;
+}
+
+// Everything the hot loop does not decide, for ONE 16-byte group (called by the lanes that need it, diverged).
+//   wrap     bit i: the private counter of pair i passed 255 (carry 256 into the global table)
+//   classify the group may hold pairs that strip() excludes or bytes outside the private alphabet
+//   general  the group was not counted at all (non-ASCII byte or an end of the text nearby): per-position path
+__device__ __noinline__ void v3_cold(const V3Cold k, int64_t base, uint32_t wrap, bool classify, bool general,
+                                     uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5) {
+  const Text T{k.text, k.n, nullptr, 0, 0};
+  auto add = [&](uint32_t a, uint32_t b) {
+    const uint32_t ra = k.sym[a], rb = k.sym[b];
+    if ((ra | rb) < 64u) atomicAdd(&k.hist64[ra * 64u + rb], 1u);
+    else atomicAdd(k.ascii_counts + a * 128u + b, 1ULL);
+  };
+  while (wrap) {
+    const int i = __ffs(wrap) - 1;
+    wrap &= wrap - 1;
+    const uint32_t a = T.at(base + i), b = T.at(base + i + 1);
+    if (k.sym[a] < kV3Junk && k.sym[b] < kV3Junk) atomicAdd(k.ascii_counts + a * 128u + b, 256ULL);   // (junk bins wrap too)
+  }
+  if (classify) {
+    const uint32_t W[6] = {w0, w1, w2, w3, w4, w5};
+    auto byte_at = [&](int j) -> uint32_t { return (W[(j + 4) >> 2] >> (8 * ((j + 4) & 3))) & 0xffu; };
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int j = 17; j >= -1; --j) {
+      const uint32_t c = byte_at(j);
+      if (j >= 9) hi = hi * 2u + k.tabC[c];
+      else lo = lo * 2u + k.tabC[c];
+    }
+    // planes as in v2_prepare: bit q = position q - 1; pair i: prev at bit i, a at i + 1, b at i + 2, next at i + 3
+    const uint32_t S = (lo & 0x3ffu) | ((hi & 0x1ffu) << 10);
+    const uint32_t N = ((lo >> 10) & 0x3ffu) | (((hi >> 10) & 0x1ffu) << 10);
+    const uint32_t P = ((lo >> 20) & 0x3ffu) | (((hi >> 20) & 0x1ffu) << 10);
+    const uint32_t valid = ~((N >> 1) | (N >> 2)) & 0xffffu;
+    const uint32_t left_unres = (S >> 1) & S & ~N, right_unres = (S >> 2) & (S >> 3) & ~(N >> 3);
+    const uint32_t counted = valid & (~(S >> 1) | ~S) & (~(S >> 2) | ~(S >> 3));
+    const uint32_t slow = valid & (left_unres | right_unres);
+    const uint32_t priv = valid & ~((P >> 1) | (P >> 2));      // both bytes in the private alphabet: the hot loop counted it
+    uint32_t minus = priv & ~counted & ~slow;                  // ... but strip() excludes it
+    while (minus) {
+      const int i = __ffs(minus) - 1;
+      minus &= minus - 1;
+      atomicAdd(k.ascii_counts + byte_at(i) * 128u + byte_at(i + 1), ~0ULL);
+    }
+    uint32_t other = counted & ~priv;                          // counts, and the hot loop put it into a junk bin
+    while (other) {
+      const int i = __ffs(other) - 1;
+      other &= other - 1;
+      add(byte_at(i), byte_at(i + 1));
+    }
+    uint32_t rest = slow;
+    while (rest) {
+      const int i = __ffs(rest) - 1;
+      rest &= rest - 1;
+      const bool counts = v3_pair_counts(T, base + i, k.n);
+      const bool is_priv = (priv >> i) & 1u;
+      if (is_priv && !counts) atomicAdd(k.ascii_counts + byte_at(i) * 128u + byte_at(i + 1), ~0ULL);
+      if (!is_priv && counts) add(byte_at(i), byte_at(i + 1));
+    }
+  }
+  if (general) {
+    const int64_t p_end = (base + 16 < k.n) ? base + 16 : k.n;
+    for (int64_t p = base; p < p_end; ++p) {
+      if (!T.is_start(p)) continue;
+      int la, lb;
+      const uint32_t a = T.decode(p, la);
+      if (is_nl(a)) continue;
+      const int64_t pb = p + la;
+      if (pb >= k.n) continue;
+      const uint32_t b = T.decode(pb, lb);
+      if (is_nl(b)) continue;
+      bool left = !is_space(a);
+      if (!left) {
+        int64_t q = T.prev_start(p);
+        while (q >= 0) {
+          int l2;
+          const uint32_t cq = T.decode(q, l2);
+          if (is_nl(cq)) break;
+          if (!is_space(cq)) { left = true; break; }
+          q = T.prev_start(q);
+        }
+      }
+      if (!left) continue;
+      bool right = !is_space(b);
+      if (!right) {
+        int64_t q = pb + lb;
+        while (q < k.n) {
+          int l2;
+          const uint32_t cq = T.decode(q, l2);
+          if (is_nl(cq)) break;
+          if (!is_space(cq)) { right = true; break; }
+          q += l2;
+        }
+      }
+      if (!right) continue;
+      if (a < 128 && b < 128) add(a, b);
+      else hash_add(k.hkeys, k.hvals, k.cap_mask, ((unsigned long long)a << 32) | b, k.overflow);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kV3Threads, 1)
+pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long long *__restrict__ ascii_counts,
+                     unsigned long long *hkeys, unsigned long long *hvals, uint32_t cap_mask, int *overflow) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t *priv = smem_raw;                                                     // [warps][28 rows][7 words][32 lanes][4]
+  uint32_t *hist64 = reinterpret_cast<uint32_t *>(smem_raw + kV3Warps * kV3PrivPerWarp);   // [64*64]
+  uint32_t *tab = hist64 + 64 * 64;                                             // byte -> row << 16 | flags | column
+  uint32_t *tabC = tab + 256;                                                   // byte -> class planes (cold path)
+  uint8_t *sym = reinterpret_cast<uint8_t *>(tabC + 256);                       // byte -> frequency rank, 0xff = none
+  uint8_t *inv = sym + 256;                                                     // rank -> byte
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n_chunks = (n + kV3Chunk - 1) / kV3Chunk;
+
+  int64_t ch = blockIdx.x;
+  if (ch >= n_chunks) return;
+  for (int q = tid; q < 256; q += kV3Threads) hist64[q] = 0;
+  __syncthreads();
+  {  // frequency ranks of the ASCII bytes of this CTA's first chunk
+    const int64_t c0 = ch * kV3Chunk, c1 = (c0 + kV3Chunk < n) ? c0 + kV3Chunk : n;
+    for (int64_t b = c0 + tid; b < c1; b += kV3Threads) atomicAdd(&hist64[__ldg(text + b)], 1u);
+    __syncthreads();
+    uint32_t rank = 0xffu;
+    if (tid < 128 && tid != 0x0a && tid != 0x0d) {
+      const uint32_t mine = hist64[tid];
+      rank = 0;
+      for (int w = 0; w < 128; ++w) {
+        const uint32_t c = hist64[w];
+        rank += (w != 0x0a && w != 0x0d && (c > mine || (c == mine && w < tid))) ? 1u : 0u;
+      }
+      if (rank >= 64u) rank = 0xffu;
+    }
+    __syncthreads();
+    if (tid < 128) {
+      const uint32_t pr = rank < kV3Junk ? rank : kV3Junk;
+      const uint32_t t = tid;
+      const uint32_t is_sp = (t >= 0x09 && t <= 0x0d) || (t >= 0x1c && t <= 0x20), is_br = t == 0x0a || t == 0x0d;
+      const uint32_t junk_off = (kV3Junk * kV3RowBytes) << 16 | ((kV3Junk >> 2) * 128u + (kV3Junk & 3u));
+      sym[tid] = (uint8_t)rank;
+      sym[128 + tid] = 0xff;
+      tab[tid] = ((pr * kV3RowBytes) << 16) | ((pr >> 2) * 128u + (pr & 3u)) |
+                 ((pr == kV3Junk && !is_br) ? kV3FlagJ : 0u) | (t <= 0x20 ? kV3FlagW : 0u);
+      tab[128 + tid] = junk_off;
+      tabC[tid] = is_sp | (is_br << 10) | ((pr == kV3Junk ? 1u : 0u) << 20);
+      tabC[128 + tid] = 1u << 20;
+      if (rank != 0xffu) inv[rank] = (uint8_t)tid;
+    }
+    uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
+    const int nz = (kV3Warps * kV3PrivPerWarp + 64 * 64 * 4) / 16;
+    for (int q = tid; q < nz; q += kV3Threads) z[q] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+  }
+  const uint32_t lane_base = (uint32_t)__cvta_generic_to_shared(priv) + warp * kV3PrivPerWarp + 4 * lane;
+  const V3Cold cold{hist64, sym, tabC, ascii_counts, hkeys, hvals, cap_mask, overflow, text, n};
+
+  const int64_t step = (int64_t)gridDim.x * kV3Chunk;
+  int64_t base = ch * kV3Chunk + 16 * (int64_t)tid;
+  uint32_t Wq[kV3Depth][6];
+#pragma unroll
+  for (int sidx = 0; sidx < kV3Depth; ++sidx) v2_load(Wq[sidx], text, n, base + sidx * step);
+
+  for (;;) {
+#pragma unroll
+    for (int sidx = 0; sidx < kV3Depth; ++sidx) {
+      if (ch >= n_chunks) goto done;           // (uniform over the CTA)
+      uint32_t W[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) W[q] = Wq[sidx][q];
+      v2_load(Wq[sidx], text, n, base + kV3Depth * step);     // the step four ahead (reads as 0x80.. past the end)
+
+      const bool exists = base < n;
+      const bool plain = exists && (((W[0] | W[1] | W[2] | W[3] | W[4] | W[5]) & 0x80808080u) == 0);
+      // hot view of positions 0..16: a group that is not plain counts line breaks (junk bins) and is redone below
+      uint32_t H[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) H[q] = plain ? W[q + 1] : 0x0a0a0a0au;
+      uint32_t t[17];
+#pragma unroll
+      for (int j = 0; j < 17; ++j) t[j] = tab[(H[j >> 2] >> (8 * (j & 3))) & 0xffu];
+      uint32_t adj = 0, any = t[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        adj |= t[j] & t[j + 1];
+        any |= t[j];
+      }
+      uint32_t wacc[4] = {0, 0, 0, 0};         // byte 3 - (i & 3) of wacc[i >> 2]: bit 0 set if the counter of pair i passed 255
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        const uint32_t a0 = (t[i] >> 16) + (t[i + 1] & 0x3ffu) + lane_base;
+        const uint32_t a1 = (t[i + 1] >> 16) + (t[i + 2] & 0x3ffu) + lane_base;
+        uint32_t c0 = lds_u8(a0);
+        uint32_t c1 = lds_u8(a1);
+        c0 += 1u;
+        c1 += (a0 == a1) ? 2u : 1u;            // same bin: the second store carries both
+        sts_u8(a0, c0);
+        sts_u8(a1, c1);
+        wacc[i >> 2] = __byte_perm(wacc[i >> 2], c0, 0x2105);
+        wacc[i >> 2] = __byte_perm(wacc[i >> 2], c1, 0x2105);
+      }
+      // white space next to white space or a line break (positions -1 .. 17), a byte outside the private alphabet
+      const uint32_t cm1 = W[0] >> 24, c17 = (W[5] >> 8) & 0xffu;
+      const bool edge = ((t[0] & kV3FlagW) && cm1 <= 0x20u) || ((t[16] & kV3FlagW) && c17 <= 0x20u);
+      const bool classify = plain && (((adj & kV3FlagW) | (any & kV3FlagJ)) != 0 || edge);
+      const bool general = exists && !plain;
+      uint32_t wrap = 0;
+      if ((wacc[0] | wacc[1] | wacc[2] | wacc[3]) & 0x01010101u) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) wrap |= ((wacc[i >> 2] >> (8 * (3 - (i & 3)))) & 1u) << i;
+        if (!plain) wrap = 0;                  // (a group that is not plain only touched the junk bin)
+      }
+      if (wrap | (uint32_t)classify | (uint32_t)general)
+        v3_cold(cold, base, wrap, classify, general, W[0], W[1], W[2], W[3], W[4], W[5]);
+      ch += gridDim.x;
+      base += step;
+    }
+  }
+done:
+  __syncthreads();
+
+  // flush: private counters (sum over the warp's 32 columns per bin), then the CTA histogram
+  const uint32_t *cols = reinterpret_cast<const uint32_t *>(priv + warp * kV3PrivPerWarp);
+  for (int g = 0; g < (int)kV3Junk * (kV3Syms / 4); ++g) {      // word rows of ranks 0 .. 26 (the junk row is dropped)
+    const uint32_t w = cols[g * 32 + lane];
+    const uint32_t s0 = __reduce_add_sync(HYP_FULL_MASK, w & 0xffu), s1 = __reduce_add_sync(HYP_FULL_MASK, (w >> 8) & 0xffu);
+    const uint32_t s2 = __reduce_add_sync(HYP_FULL_MASK, (w >> 16) & 0xffu), s3 = __reduce_add_sync(HYP_FULL_MASK, w >> 24);
+    if (lane < 4) {
+      const uint32_t s = lane == 0 ? s0 : lane == 1 ? s1 : lane == 2 ? s2 : s3;
+      const uint32_t ra = (uint32_t)g / (kV3Syms / 4), rb = 4u * ((uint32_t)g % (kV3Syms / 4)) + lane;
+      if (s && rb != kV3Junk) atomicAdd(ascii_counts + (uint32_t)inv[ra] * 128u + inv[rb], (unsigned long long)s);
+    }
+  }
+  for (int q = tid; q < 64 * 64; q += kV3Threads) {
+    const uint32_t v = hist64[q];
+    if (v) atomicAdd(ascii_counts + (uint32_t)inv[q >> 6] * 128u + inv[q & 63], (unsigned long long)v);
+  }
+}
+
 }  // namespace hyp
 
 using namespace hyp;
@@ -591,10 +911,20 @@ extern "C" int hyp_pair_count(const uint8_t *text, int64_t n_bytes, unsigned lon
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  static const int variant = [] {
-    const char *e = getenv("HYP_PAIR_COUNT");
-    return (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;     // HYP_PAIR_COUNT=v1 selects the atomics-only kernel
-  }();
+  // HYP_PAIR_COUNT=v1 / v2 selects the older kernels (same results; kept for A/B runs and as regression oracles of v3)
+  const char *ev = getenv("HYP_PAIR_COUNT");
+  const int variant = (ev && ev[0] == 'v' && ev[1] >= '1' && ev[1] <= '3') ? ev[1] - '0' : 3;
+  if (variant == 3) {
+    if (cudaFuncSetAttribute(pair_count_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kV3Smem) != cudaSuccess) {
+      set_error("hyp_pair_count: cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+      return HYP_ERR_CUDA;
+    }
+    const int64_t chunks3 = (n_bytes + kV3Chunk - 1) / kV3Chunk;
+    const int grid3 = (int)(chunks3 < (int64_t)sms ? chunks3 : (int64_t)sms);
+    pair_count_v3_kernel<<<grid3, kV3Threads, kV3Smem, st>>>(text, n_bytes, ascii_counts, hash_keys, hash_vals,
+                                                             (uint32_t)(hash_capacity - 1), overflow);
+    return check_launch("hyp_pair_count");
+  }
   if (variant == 2) {
     // (per device, so set before every launch: a process-wide "already set" flag would skip it on a second GPU)
     if (cudaFuncSetAttribute(pair_count_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kV2Smem) != cudaSuccess) {

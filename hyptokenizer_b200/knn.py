@@ -157,6 +157,7 @@ class TopkContext:
         class _Mem:
             pass
         m = _Mem()
+        m.owner = self      # the tensor's storage keeps `m`, hence the context (which owns the memory), alive
         m.__cuda_array_interface__ = {"shape": (self.world, self.slot_bytes // 8), "typestr": "<i8",
                                       "data": (address, False), "version": 3}
         flat = torch.as_tensor(m, device=self.device)

@@ -7,6 +7,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["v3", "v2"])
+def kernel_variant(request, monkeypatch):
+    """Every test of this file runs against the default kernel (v3: count first, correct later) and against v2 (decide
+    first); HYP_PAIR_COUNT is read at every call.  v1 has its own test below."""
+    monkeypatch.setenv("HYP_PAIR_COUNT", request.param)
+    return request.param
+
+
 def test_golden_pair_counts(golden):
     from hyptokenizer_b200.pair_count import count_pairs
     gd = golden("pair_counts.json")
@@ -47,10 +55,10 @@ def test_edge_cases(case):
     assert count_pairs(text.encode("utf-8")) == count_pairs_py(_lines(text))
 
 
-@pytest.mark.parametrize("chunk", [16384, 8192, 6144])
+@pytest.mark.parametrize("chunk", [16384, 8192, 6144, 4096])
 def test_chunk_boundaries(chunk):
     """Lines and whitespace runs straddling the CTA chunk boundaries (16 KiB in the v1 kernel, 8 KiB -- 6 KiB with the
-    32-symbol table -- in v2)."""
+    32-symbol table -- in v2, 4 KiB in v3)."""
     from hyptokenizer_b200.pair_count import count_pairs
     from oracle.merge import count_pairs_py
     parts = []
@@ -76,8 +84,28 @@ def test_wide_alphabet_and_counter_wraps():
     assert got == want
 
 
+def test_strip_corrections_dense():
+    """Leading / trailing white space on EVERY line, tabs and double spaces inside, CR LF breaks, symbols outside the
+    private alphabet: the cases where v3's unconditional count has to be corrected (-1 / +1 in the global table)."""
+    import numpy as np
+    from hyptokenizer_b200.pair_count import count_pairs
+    from oracle.pair_count import count_pairs_c
+    rng = np.random.default_rng(11)
+    words = ["".join(rng.choice(list("abcdefghij"), size=rng.integers(1, 7))) for _ in range(500)]
+    seps = [" ", "  ", "\t", " \t ", " "]
+    ends = ["\n", " \n", "  \r\n", "\t\n ", "\n\n", "\r", " \n  "]
+    parts = []
+    for k in range(120000):
+        parts.append(words[rng.integers(0, len(words))])
+        parts.append(seps[rng.integers(0, len(seps))] if k % 9 else ends[rng.integers(0, len(ends))])
+        if k % 1013 == 0:
+            parts.append("Q~#")                      # rare symbols: outside the 27 private ranks
+    data = np.frombuffer("".join(parts).encode("ascii"), np.uint8)
+    assert count_pairs(data) == count_pairs_c(data)
+
+
 def test_v1_kernel_matches_too():
-    """The atomics-only kernel stays selectable (HYP_PAIR_COUNT=v1, read once per process) and exact."""
+    """The atomics-only kernel stays selectable (HYP_PAIR_COUNT=v1) and exact."""
     import subprocess
     import sys
     code = (
