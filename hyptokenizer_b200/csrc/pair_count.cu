@@ -588,12 +588,24 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
 // Result bits are identical to v1 / v2 for any input (tests/test_gpu_paircount.py runs all three).
 constexpr int kV3Syms = 28;                                // 27 private symbols + the junk rank
 constexpr uint32_t kV3Junk = kV3Syms - 1;
+#ifndef HYP_V3_GROUPS
+#define HYP_V3_GROUPS 2     // 16-byte groups per thread and step: two give the scheduler two independent streams of table
+#endif                      // lookups / address arithmetic to interleave with the (ordered) counter updates
+constexpr int kV3Groups = HYP_V3_GROUPS;
+#ifdef HYP_V3_RACY16        // TIMING EXPERIMENT ONLY (wrong counts): 16 warps, warps w and w + 8 race on one block of columns
+constexpr int kV3Threads = 512, kV3Warps = 8;
+#else
 constexpr int kV3Threads = 256, kV3Warps = kV3Threads / 32;
-constexpr int kV3Chunk = kV3Threads * 16;                  // 4 KiB of text per CTA step
+#endif
+constexpr int kV3Chunk = kV3Threads * 16 * kV3Groups;      // bytes of text per CTA step (8 KiB)
+constexpr int kV3Words = 2 + 4 * kV3Groups;                // a thread's slot: its bytes + 4 bytes of context on either side
 constexpr int kV3RowBytes = (kV3Syms / 4) * 128;           // a row of 28 bins = 7 words per lane x 32 lanes
-constexpr int kV3PrivPerWarp = kV3Syms * kV3RowBytes;      // 25 088 bytes
-constexpr int kV3Depth = 4;                                // steps in flight per thread
-constexpr size_t kV3Smem = (size_t)kV3Warps * kV3PrivPerWarp + 64 * 64 * 4 + 256 * 4 + 256 * 4 + 256 + 64 + 64;
+constexpr int kV3PrivPerWarp = 25600;                      // 28 rows = 25 088 bytes, padded so that the low 10 bits of a
+                                                           // warp's base are zero (it is OR-ed into the offsets)
+static_assert(kV3PrivPerWarp >= kV3Syms * kV3RowBytes && (kV3PrivPerWarp & 1023) == 0, "v3 counter block");
+constexpr int kV3Depth = 4 / kV3Groups;                    // steps in flight per thread (16 KB per SM either way)
+constexpr int kV3Bins = kV3Syms * kV3Syms;                 // 784
+constexpr size_t kV3Smem = (size_t)kV3Warps * kV3PrivPerWarp + 64 * 64 * 4 + kV3Bins * 4 + 256 * 4 + 256 * 4 + 256 + 64 + 64;
 constexpr uint32_t kV3FlagJ = 1u << 12;                    // ASCII byte outside the private alphabet (not a line break)
 constexpr uint32_t kV3FlagW = 1u << 13;                    // byte <= 0x20: every str.isspace() ASCII byte and line break
 
@@ -651,10 +663,9 @@ __device__ __noinline__ bool v3_pair_counts(const Text &T, int64_t pp, int64_t n
 }
 
 // Everything the hot loop does not decide, for ONE 16-byte group (called by the lanes that need it, diverged).
-//   wrap     bit i: the private counter of pair i passed 255 (carry 256 into the global table)
 //   classify the group may hold pairs that strip() excludes or bytes outside the private alphabet
 //   general  the group was not counted at all (non-ASCII byte or an end of the text nearby): per-position path
-__device__ __noinline__ void v3_cold(const V3Cold k, int64_t base, uint32_t wrap, bool classify, bool general,
+__device__ __noinline__ void v3_cold(const V3Cold k, int64_t base, bool classify, bool general,
                                      uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5) {
   const Text T{k.text, k.n, nullptr, 0, 0};
   auto add = [&](uint32_t a, uint32_t b) {
@@ -662,12 +673,6 @@ __device__ __noinline__ void v3_cold(const V3Cold k, int64_t base, uint32_t wrap
     if ((ra | rb) < 64u) atomicAdd(&k.hist64[ra * 64u + rb], 1u);
     else atomicAdd(k.ascii_counts + a * 128u + b, 1ULL);
   };
-  while (wrap) {
-    const int i = __ffs(wrap) - 1;
-    wrap &= wrap - 1;
-    const uint32_t a = T.at(base + i), b = T.at(base + i + 1);
-    if (k.sym[a] < kV3Junk && k.sym[b] < kV3Junk) atomicAdd(k.ascii_counts + a * 128u + b, 256ULL);   // (junk bins wrap too)
-  }
   if (classify) {
     const uint32_t W[6] = {w0, w1, w2, w3, w4, w5};
     auto byte_at = [&](int j) -> uint32_t { return (W[(j + 4) >> 2] >> (8 * ((j + 4) & 3))) & 0xffu; };
@@ -756,7 +761,8 @@ pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t *priv = smem_raw;                                                     // [warps][28 rows][7 words][32 lanes][4]
   uint32_t *hist64 = reinterpret_cast<uint32_t *>(smem_raw + kV3Warps * kV3PrivPerWarp);   // [64*64]
-  uint32_t *tab = hist64 + 64 * 64;                                             // byte -> row << 16 | flags | column
+  uint32_t *carry = hist64 + 64 * 64;                                           // [28*28]: wraps of the one-byte counters
+  uint32_t *tab = carry + kV3Bins;                                              // byte -> row << 16 | flags | column
   uint32_t *tabC = tab + 256;                                                   // byte -> class planes (cold path)
   uint8_t *sym = reinterpret_cast<uint8_t *>(tabC + 256);                       // byte -> frequency rank, 0xff = none
   uint8_t *inv = sym + 256;                                                     // rank -> byte
@@ -797,70 +803,122 @@ pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
       if (rank != 0xffu) inv[rank] = (uint8_t)tid;
     }
     uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
-    const int nz = (kV3Warps * kV3PrivPerWarp + 64 * 64 * 4) / 16;
+    const int nz = (kV3Warps * kV3PrivPerWarp + 64 * 64 * 4 + kV3Bins * 4) / 16;
     for (int q = tid; q < nz; q += kV3Threads) z[q] = make_uint4(0, 0, 0, 0);
     __syncthreads();
   }
-  const uint32_t lane_base = (uint32_t)__cvta_generic_to_shared(priv) + warp * kV3PrivPerWarp + 4 * lane;
+  // A counter's byte offset inside the warp's block is row(first) + column(second) + 4 * lane.  The column offsets use
+  // bits 0-1 and 7-9, 4 * lane bits 2-6: `(t & 0x383) | lane4` is one LOP3, the row is added by one LEA.HI, and the warp's
+  // base rides in the address mode of LDS / STS.  volatile: the read-modify-writes of one thread stay in program order.
+  volatile uint8_t *const col = priv;
+  const uint32_t lane4 = 4u * lane | (uint32_t)(warp % kV3Warps) * kV3PrivPerWarp;   // (+ the warp's block: bits 10 and up)
   const V3Cold cold{hist64, sym, tabC, ascii_counts, hkeys, hvals, cap_mask, overflow, text, n};
 
   const int64_t step = (int64_t)gridDim.x * kV3Chunk;
-  int64_t base = ch * kV3Chunk + 16 * (int64_t)tid;
-  uint32_t Wq[kV3Depth][6];
+  int64_t base = ch * kV3Chunk + 16 * kV3Groups * (int64_t)tid;
+  // a thread's slot: bytes base-4 .. base+16G+3 as 2 + 4G words; whatever is not in the text reads as 0x80 (-> general)
+  auto load_slot = [&](uint32_t (&S)[kV3Words], int64_t at, bool checked) {
+    if (!checked || (at >= 4 && at + 16 * kV3Groups + 4 <= n)) {
+      const uint8_t *p = text + at;
 #pragma unroll
-  for (int sidx = 0; sidx < kV3Depth; ++sidx) v2_load(Wq[sidx], text, n, base + sidx * step);
+      for (int g = 0; g < kV3Groups; ++g) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + 16 * g));
+        S[1 + 4 * g] = v.x; S[2 + 4 * g] = v.y; S[3 + 4 * g] = v.z; S[4 + 4 * g] = v.w;
+      }
+      S[0] = __ldg(reinterpret_cast<const uint32_t *>(p - 4));
+      S[kV3Words - 1] = __ldg(reinterpret_cast<const uint32_t *>(p + 16 * kV3Groups));
+    } else {
+#pragma unroll
+      for (int q = 0; q < kV3Words; ++q) S[q] = 0x80808080u;
+      // a slot at either end of the text: whole words that exist are loaded, the rest stays 0x80
+      if (at < n) {
+#pragma unroll
+        for (int q = 0; q < kV3Words; ++q) {
+          const int64_t w = at - 4 + 4 * q;
+          if (w >= 0 && w + 4 <= n) S[q] = __ldg(reinterpret_cast<const uint32_t *>(text + w));
+        }
+        // a group needs its whole 24-byte neighbourhood: mark the first / last incomplete ones
+        if (at < 4) S[0] = 0x80808080u;
+      }
+    }
+  };
+  uint32_t Wq[kV3Depth][kV3Words];
+#pragma unroll
+  for (int sidx = 0; sidx < kV3Depth; ++sidx) load_slot(Wq[sidx], base + sidx * step, true);
+  // chunks whose slots all have their full neighbourhood inside the text are loaded without per-thread checks
+  const int64_t interior_hi = (n - 4) / kV3Chunk;          // chunk c is interior iff 1 <= c < interior_hi
 
   for (;;) {
 #pragma unroll
     for (int sidx = 0; sidx < kV3Depth; ++sidx) {
       if (ch >= n_chunks) goto done;           // (uniform over the CTA)
-      uint32_t W[6];
+      uint32_t WS[kV3Words];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) W[q] = Wq[sidx][q];
-      v2_load(Wq[sidx], text, n, base + kV3Depth * step);     // the step four ahead (reads as 0x80.. past the end)
-
-      const bool exists = base < n;
-      const bool plain = exists && (((W[0] | W[1] | W[2] | W[3] | W[4] | W[5]) & 0x80808080u) == 0);
-      // hot view of positions 0..16: a group that is not plain counts line breaks (junk bins) and is redone below
-      uint32_t H[5];
-#pragma unroll
-      for (int q = 0; q < 5; ++q) H[q] = plain ? W[q + 1] : 0x0a0a0a0au;
-      uint32_t t[17];
-#pragma unroll
-      for (int j = 0; j < 17; ++j) t[j] = tab[(H[j >> 2] >> (8 * (j & 3))) & 0xffu];
-      uint32_t adj = 0, any = t[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        adj |= t[j] & t[j + 1];
-        any |= t[j];
+      for (int q = 0; q < kV3Words; ++q) WS[q] = Wq[sidx][q];
+      {                                        // the step kV3Depth ahead
+        const int64_t chn = ch + (int64_t)kV3Depth * gridDim.x;
+        load_slot(Wq[sidx], base + kV3Depth * step, !(chn >= 1 && chn < interior_hi));
       }
-      uint32_t wacc[4] = {0, 0, 0, 0};         // byte 3 - (i & 3) of wacc[i >> 2]: bit 0 set if the counter of pair i passed 255
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        const uint32_t a0 = (t[i] >> 16) + (t[i + 1] & 0x3ffu) + lane_base;
-        const uint32_t a1 = (t[i + 1] >> 16) + (t[i + 2] & 0x3ffu) + lane_base;
-        uint32_t c0 = lds_u8(a0);
-        uint32_t c1 = lds_u8(a1);
-        c0 += 1u;
-        c1 += (a0 == a1) ? 2u : 1u;            // same bin: the second store carries both
-        sts_u8(a0, c0);
-        sts_u8(a1, c1);
-        wacc[i >> 2] = __byte_perm(wacc[i >> 2], c0, 0x2105);
-        wacc[i >> 2] = __byte_perm(wacc[i >> 2], c1, 0x2105);
-      }
-      // white space next to white space or a line break (positions -1 .. 17), a byte outside the private alphabet
-      const uint32_t cm1 = W[0] >> 24, c17 = (W[5] >> 8) & 0xffu;
-      const bool edge = ((t[0] & kV3FlagW) && cm1 <= 0x20u) || ((t[16] & kV3FlagW) && c17 <= 0x20u);
-      const bool classify = plain && (((adj & kV3FlagW) | (any & kV3FlagJ)) != 0 || edge);
-      const bool general = exists && !plain;
-      uint32_t wrap = 0;
-      if ((wacc[0] | wacc[1] | wacc[2] | wacc[3]) & 0x01010101u) {
+      for (int g = 0; g < kV3Groups; ++g) {
+        const int64_t gbase = base + 16 * g;
+        uint32_t W[6];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) wrap |= ((wacc[i >> 2] >> (8 * (3 - (i & 3)))) & 1u) << i;
-        if (!plain) wrap = 0;                  // (a group that is not plain only touched the junk bin)
+        for (int q = 0; q < 6; ++q) W[q] = WS[4 * g + q];
+        const bool exists = gbase < n;
+        const bool plain = exists && (((W[0] | W[1] | W[2] | W[3] | W[4] | W[5]) & 0x80808080u) == 0);
+        // hot view of positions 0..16: a group that is not plain counts line breaks (junk bins) and is redone below
+        uint32_t H[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) H[q] = plain ? W[q + 1] : 0x0a0a0a0au;
+        uint32_t t[17];
+#pragma unroll
+        for (int j = 0; j < 17; ++j) t[j] = tab[(H[j >> 2] >> (8 * (j & 3))) & 0xffu];
+        uint32_t adj = 0, any = t[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          adj |= t[j] & t[j + 1];
+          adj |= t[j + 1] & t[j + 2];
+          any |= t[j] | t[j + 1];
+        }
+        uint32_t wacc[4] = {0, 0, 0, 0};       // byte 3 - (i & 3) of wacc[i >> 2]: bit 0 set if the counter of pair i passed 255
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const uint32_t a0 = (t[i] >> 16) + ((t[i + 1] & 0x383u) | lane4);
+          const uint32_t a1 = (t[i + 1] >> 16) + ((t[i + 2] & 0x383u) | lane4);
+          uint32_t c0 = col[a0];
+          uint32_t c1 = col[a1];
+          c0 += 1u;
+          c1 += (a0 == a1) ? 2u : 1u;          // same bin: the second store carries both
+          col[a0] = (uint8_t)c0;
+          col[a1] = (uint8_t)c1;
+          wacc[i >> 2] = __byte_perm(wacc[i >> 2], c0, 0x2105);
+          wacc[i >> 2] = __byte_perm(wacc[i >> 2], c1, 0x2105);
+        }
+        // A one-byte counter passed 255 (about one lane in sixteen per group): +1 in the CTA's carry table, whose bins
+        // are worth 256 at the flush.  The bin is recomputed from the text bytes; no global access, no call.
+        if ((wacc[0] | wacc[1] | wacc[2] | wacc[3]) & 0x01010101u) {
+          uint32_t wrap = 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) wrap |= ((wacc[i >> 2] >> (8 * (3 - (i & 3)))) & 1u) << i;
+          while (wrap) {
+            const int i = __ffs(wrap) - 1;
+            wrap &= wrap - 1;
+            // bytes i and i + 1 of the hot view (H[4] holds byte 16)
+            const uint32_t lo = (i >> 2) == 0 ? H[0] : (i >> 2) == 1 ? H[1] : (i >> 2) == 2 ? H[2] : H[3];
+            const uint32_t hi = (i >> 2) == 0 ? H[1] : (i >> 2) == 1 ? H[2] : (i >> 2) == 2 ? H[3] : H[4];
+            const uint32_t two = __funnelshift_r(lo, hi, 8 * (i & 3));
+            const uint32_t ra = sym[two & 0xffu], rb = sym[(two >> 8) & 0xffu];
+            if (ra < kV3Junk && rb < kV3Junk) atomicAdd(&carry[ra * kV3Syms + rb], 1u);    // (junk bins wrap too)
+          }
+        }
+        // white space next to white space or a line break (positions -1 .. 17), a byte outside the private alphabet
+        const uint32_t cm1 = W[0] >> 24, c17 = (W[5] >> 8) & 0xffu;
+        const bool edge = ((t[0] & kV3FlagW) && cm1 <= 0x20u) || ((t[16] & kV3FlagW) && c17 <= 0x20u);
+        const bool classify = plain && (((adj & kV3FlagW) | (any & kV3FlagJ)) != 0 || edge);
+        const bool general = exists && !plain;
+        if (classify | general) v3_cold(cold, gbase, classify, general, W[0], W[1], W[2], W[3], W[4], W[5]);
       }
-      if (wrap | (uint32_t)classify | (uint32_t)general)
-        v3_cold(cold, base, wrap, classify, general, W[0], W[1], W[2], W[3], W[4], W[5]);
       ch += gridDim.x;
       base += step;
     }
@@ -869,7 +927,7 @@ done:
   __syncthreads();
 
   // flush: private counters (sum over the warp's 32 columns per bin), then the CTA histogram
-  const uint32_t *cols = reinterpret_cast<const uint32_t *>(priv + warp * kV3PrivPerWarp);
+  const uint32_t *cols = reinterpret_cast<const uint32_t *>(priv + (warp % kV3Warps) * kV3PrivPerWarp);
   for (int g = 0; g < (int)kV3Junk * (kV3Syms / 4); ++g) {      // word rows of ranks 0 .. 26 (the junk row is dropped)
     const uint32_t w = cols[g * 32 + lane];
     const uint32_t s0 = __reduce_add_sync(HYP_FULL_MASK, w & 0xffu), s1 = __reduce_add_sync(HYP_FULL_MASK, (w >> 8) & 0xffu);
@@ -883,6 +941,10 @@ done:
   for (int q = tid; q < 64 * 64; q += kV3Threads) {
     const uint32_t v = hist64[q];
     if (v) atomicAdd(ascii_counts + (uint32_t)inv[q >> 6] * 128u + inv[q & 63], (unsigned long long)v);
+  }
+  for (int q = tid; q < kV3Bins; q += kV3Threads) {
+    const uint32_t v = carry[q];
+    if (v) atomicAdd(ascii_counts + (uint32_t)inv[q / kV3Syms] * 128u + inv[q % kV3Syms], 256ULL * v);
   }
 }
 

@@ -666,7 +666,33 @@ def gen_persistence(tmpdir="/tmp"):
 GENS = {"persistence": gen_persistence, "trace_adaptive": gen_trace_adaptive, "trace_enhanced": gen_trace_enhanced, "trace_compress": gen_trace_compress, "trace_hier": gen_trace_hier, "lorentz_ops": gen_lorentz_ops, "trace_test9": gen_trace_test9, "trace_c1": gen_trace_c1,
         "trace_fast": gen_trace_fast, "pair_counts": gen_pair_counts, "trace_freq": gen_trace_freq}
 
+def gen_trace_c2_feasible(steps=300, v0=2000, d=100, scale=0.01, thr=0.1):
+    """BASELINE config 2 at the largest size the reference's own brute-force loop runs (V0 = 2 000, d = 100; V0 = 10 000
+    needs a 40 GB broadcast temporary): HyperbolicTokenizer.optimize_merges, the sequence the north star gates on, for
+    `steps` merges on the benchmark's synthetic vocabulary (hyptokenizer_b200/synth.py, seed 42).  The init is not
+    stored (800 KB of random mantissas): its sha256 is, and the test regenerates it."""
+    import hashlib
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from hyptokenizer_b200.synth import synthetic_embeddings, synthetic_vocab
+    emb = synthetic_embeddings(v0, d, scale=scale, seed=42)
+    digest = hashlib.sha256(emb.numpy().tobytes()).hexdigest()
+    out = {"v0": v0, "d": d, "scale": scale, "threshold": thr, "seed": 42, "init_sha256": digest, "runs": []}
+    for sem in ("lorentz", "reference"):
+        n_steps = steps if sem == "lorentz" else 3          # as shipped every step is (0, 1): 2e6 candidates in a Python loop
+        with semantics(sem):
+            tok = RH.HyperbolicTokenizer(synthetic_vocab(v0), torch.nn.Parameter(emb.clone()), curvature=1.0,
+                                         merge_threshold=thr, lr=1e-3, device=torch.device("cpu"),
+                                         max_vocab_size=v0 + n_steps + 8, use_approximate_search=False)
+            trace = run_base_loop(tok, n_steps)
+        n = tok.current_vocab_size
+        out["runs"].append({"semantics": sem, "trace": trace, "vocab_tail": list(tok.vocab[v0:]),
+                            "rows_tail": bits(tok.embeddings[n - 4:n])})
+        print("c2-feasible", sem, "merges", len(trace), "first", trace[:4], "last candidates", trace[-1][3])
+    dump("trace_c2_feasible.json", out)
+
+
 if __name__ == "__main__":
+    GENS["trace_c2_feasible"] = gen_trace_c2_feasible
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     ap.add_argument("--full-c1", action="store_true",

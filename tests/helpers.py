@@ -38,3 +38,39 @@ def ulp_diff(a, b) -> np.ndarray:
     d = np.abs(ma - mb)
     d[np.isnan(fa) & np.isnan(fb)] = 0
     return d
+
+
+class RowInjector:
+    """Tests-only strict-parity mode (hard part 1).
+
+    The Minkowski products the kernels select on are bit-identical to the reference's; what is not reproducible
+    between torch's CPU vector math and CUDA's libm is the last bit or two of acosh / cosh / sinh / sqrt, i.e. of
+    every APPENDED row.  In tie-heavy regimes (duplicated midpoint rows whose mutual product is 1 or 1 + 2^-23
+    depending on one bit of x0) that can flip a later choice.  To PROVE that a divergence has this cause and no
+    other, the injector wraps `_merge_tokens`: after every merge it checks that the row the device appended is
+    within `max_ulp` units in the last place of the reference's row (NaN pattern identical) and then REPLACES it by
+    the reference's bits.  If the merge sequence, candidate counts and distances are then identical to the golden
+    trace from the first step to the last, the only thing that separated the two runs was those last bits."""
+
+    def __init__(self, tok, ref_rows: np.ndarray, n0: int, max_ulp: int = 64):
+        self.max_seen = 0
+        self.rows = 0
+        self.max_ulp = max_ulp
+        ref = np.asarray(ref_rows, dtype=np.float32)
+        orig = tok._merge_tokens
+
+        def wrapped(i, j):
+            out = orig(i, j)
+            r = tok.current_vocab_size - 1
+            if n0 <= r < len(ref):
+                got = tok.embeddings.data[r].detach().cpu().numpy()
+                want = ref[r]
+                assert np.array_equal(np.isnan(got), np.isnan(want)), f"row {r}: NaN pattern differs from the reference"
+                u = int(ulp_diff(got, want).max())
+                self.max_seen = max(self.max_seen, u)
+                assert u <= self.max_ulp, f"row {r} is {u} ulp from the reference's row (> {self.max_ulp})"
+                tok.embeddings.data[r] = torch.from_numpy(want.copy()).to(tok.embeddings.device)
+                self.rows += 1
+            return out
+
+        tok._merge_tokens = wrapped

@@ -137,7 +137,7 @@ def test_enhanced_host_policy_against_reference_trace(host, run):
     gd, path = host
     r = gd["runs"][run]
     tok, merges, heads, curv = EC.run_golden(HostEnhanced, gd, r, path)
-    EC.check_run(tok, merges, heads, curv, gd, r)
+    EC.check_run(tok, merges, heads, curv, gd, r, strict=True)
 
 
 def test_save_load_round_trip(host, tmp_path):

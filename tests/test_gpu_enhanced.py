@@ -30,7 +30,20 @@ def test_enhanced_trace(corpus, run):
     r = gd["runs"][run]
     tok, merges, heads, curv = EC.run_golden(_cls(), gd, r, path)
     assert tok.embeddings.is_cuda
+    if EC.one_bit_tie_step(heads, r["heads"]) is None:
+        EC.check_run(tok, merges, heads, curv, gd, r, strict=True)
+        return
+    # The plain run meets a one-bit tie (two copies of a merged row whose mutual product is 1 or 1 + 2^-23 depending
+    # on the last bit of x0): identical up to there ...
     EC.check_run(tok, merges, heads, curv, gd, r)
+    # ... and PROVED to be nothing else: with the reference's bits injected into every appended row (each within a few
+    # ulp of what the device computed, asserted), the whole run is the reference's -- every merge, candidate count,
+    # threshold, phase, score, the statistics and the final table.
+    tok2, merges2, heads2, curv2 = EC.run_golden(_cls(), gd, r, path, inject_reference_rows=True)
+    EC.check_run(tok2, merges2, heads2, curv2, gd, r, strict=True)
+    assert tok2._row_injector.rows == len(r["merges_ij"])
+    print(f"run {run}: strict parity with {tok2._row_injector.rows} injected rows, max device-vs-reference row "
+          f"difference {tok2._row_injector.max_seen} ulp")
 
 
 def test_shipped_curvature_step_raises_like_the_reference(corpus):

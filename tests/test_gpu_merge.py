@@ -123,13 +123,45 @@ def test_fast_snapshot_trace(golden):
             assert tok.vocab == run["final"]["vocab"]
             cs, got = run["cache_stats"], tok.cache.get_stats()
             assert (got["size"], got["hit_count"], got["miss_count"]) == (cs["size"], cs["hit_count"], cs["miss_count"])
-        else:
-            # The first two cache generations (202 merges) are pinned.  The third refill happens after the
+        elif got_ij != run["merges_ij"]:
+            # The first two cache generations (202 merges) are identical.  The third refill happens after the
             # table holds duplicated midpoint rows whose mutual distance is 0 or acosh(1+2^-23) depending on
             # the LAST BIT of the row -- and rows go through acosh/cosh/sinh/sqrt, where torch's CPU (Sleef)
-            # and CUDA's libm differ by <= 1-2 ulp ("what is not bit-reproducible").
+            # and CUDA's libm differ by <= 1-2 ulp ("what is not bit-reproducible").  That this is the ONLY
+            # cause is proved by test_fast_snapshot_trace_strict_parity below.
             assert got_ij[:202] == run["merges_ij"][:202]
             assert len(got_ij) == len(run["merges_ij"])
+
+
+def test_fast_snapshot_trace_strict_parity(golden):
+    """Strict-parity proof for the snapshot traces in the corrected geometry: with every appended row replaced by the
+    reference's bits right after the device computed it (each within a few ulp, asserted), the WHOLE 250-merge trace of
+    the shipped pop-100 control flow -- merges, vocabulary, cache statistics, final threshold -- is the reference's."""
+    from helpers import RowInjector
+    from hyptokenizer_b200.tokenizer.fast_hyperbolic_merge import FastHyperbolicTokenizer
+    gd = golden("trace_fast300.json")
+    checked = 0
+    for run in gd["runs"]:
+        if run["semantics"] != "lorentz":
+            continue
+        fin = run["final"]
+        emb = from_bits(run["init"], 300, run["d"] + 1)
+        ref_rows = from_bits(fin["embeddings"], fin["n"], run["d"] + 1).numpy()
+        random.seed(42)
+        tok = FastHyperbolicTokenizer([f"w{k}" for k in range(300)], torch.nn.Parameter(emb),
+                                      merge_threshold=run["threshold0"], max_vocab_size=1024,
+                                      use_approximate_search=False, semantics="lorentz", cache_semantics="snapshot")
+        inj = RowInjector(tok, ref_rows, 300, max_ulp=64)
+        tok.optimize_merges(steps=250, log_every=1000)
+        assert [[a, b] for a, b, _ in tok.last_trace] == run["merges_ij"]
+        assert tok.vocab == fin["vocab"] and [list(m) for m in tok.merge_history] == fin["merges"]
+        assert abs(tok.merge_threshold - fin["merge_threshold"]) <= 1e-6 * fin["merge_threshold"]
+        cs, got = run["cache_stats"], tok.cache.get_stats()
+        assert (got["size"], got["hit_count"], got["miss_count"]) == (cs["size"], cs["hit_count"], cs["miss_count"])
+        assert inj.rows == 250
+        print(f"scale {run['scale']}: 250 rows injected, largest device-vs-reference row difference {inj.max_seen} ulp")
+        checked += 1
+    assert checked == 2
 
 
 @pytest.mark.parametrize("sem,scale,thr", [("reference", 0.01, 0.1), ("lorentz", 0.1, 0.9), ("lorentz", 0.01, 0.12)])
@@ -153,6 +185,62 @@ def test_fast_fresh_equals_bruteforce_oracle(sem, scale, thr):
     assert tok.vocab == ora.vocab
     want = np.array([t[2] for t in ora.trace], dtype=np.float32)
     assert np.all(np.abs(tok.last_trace["d"] - want) <= REL * np.abs(want))
+
+
+def test_c2_feasible_golden_trace(golden):
+    """BASELINE config 2 at the largest size the reference's own brute-force loop can run (V0=2000, d=100, the
+    benchmark's synthetic vocabulary): the golden trace written by the UNMODIFIED reference
+    (oracle/gen_golden.py gen_trace_c2_feasible) against FastHyperbolicTokenizer's default always-fresh device search --
+    merge for merge, candidate count for candidate count."""
+    import hashlib
+    from hyptokenizer_b200.synth import synthetic_embeddings, synthetic_vocab
+    from hyptokenizer_b200.tokenizer.fast_hyperbolic_merge import FastHyperbolicTokenizer
+    from hyptokenizer_b200.tokenizer.hyperbolic_merge import HyperbolicTokenizer
+    gd = golden("trace_c2_feasible.json")
+    v0, d = gd["v0"], gd["d"]
+    emb = synthetic_embeddings(v0, d, scale=gd["scale"], seed=gd["seed"])
+    if hashlib.sha256(emb.numpy().tobytes()).hexdigest() != gd["init_sha256"]:
+        pytest.skip("this host's torch CPU build produces different init bits than the container the golden was made in")
+    for run in gd["runs"]:
+        want = run["trace"]
+        steps = len(want)
+        tok = FastHyperbolicTokenizer(synthetic_vocab(v0), torch.nn.Parameter(emb.clone()), merge_threshold=gd["threshold"],
+                                      max_vocab_size=v0 + steps + 8, semantics=run["semantics"])
+        tok.optimize_merges(steps=steps, adaptive_threshold=False)
+        check_trace(tok.last_trace, want)
+        assert tok.vocab[v0:] == run["vocab_tail"]
+        n = tok.current_vocab_size
+        rows_close(tok.embeddings[n - 4:n], run["rows_tail"], 4, d + 1)
+        # the step-by-step API sees the reference's candidate counts (first and last recorded step)
+        base = HyperbolicTokenizer(synthetic_vocab(v0), torch.nn.Parameter(emb.clone()), merge_threshold=gd["threshold"],
+                                   max_vocab_size=v0 + 8, semantics=run["semantics"])
+        assert base._global_best(float(np.float32(gd["threshold"]))).count_lo == want[0][3]
+
+
+def test_bench_configuration_against_oracle():
+    """The benchmark's own configuration (bench.py c2: V0=10 000, d=100, init scale 0.01, threshold 0.1, corrected
+    geometry) against the oracle's brute-force loop -- a full all-pairs recompute of the 10 000 x 10 000 distance matrix
+    at every step, as the reference does -- for 20 merges: identical sequence, distances within 1e-5 relative, the
+    first step's candidate count identical.  (The reference itself cannot run this size: 40 GB temporary.)"""
+    from hyptokenizer_b200.synth import synthetic_embeddings, synthetic_vocab
+    from hyptokenizer_b200.tokenizer.fast_hyperbolic_merge import FastHyperbolicTokenizer
+    from oracle import merge as OM
+    n0, d, steps, thr = 10000, 100, 20, 0.1
+    emb = synthetic_embeddings(n0, d, scale=0.01, seed=42)
+    vocab = synthetic_vocab(n0)
+    ora = OM.OracleTokenizer(vocab, emb, 1.0, thr, n0 + steps + 8, "lorentz")
+    ora.optimize_merges(steps)
+    assert len(ora.trace) == steps
+    tok = FastHyperbolicTokenizer(vocab, torch.nn.Parameter(emb.clone()), merge_threshold=thr,
+                                  max_vocab_size=n0 + steps + 8, semantics="lorentz")
+    first = tok._global_best(float(np.float32(thr)))
+    assert (first.count_lo | (first.count_hi << 32)) == ora.n_candidates[0]
+    tok.optimize_merges(steps=steps, adaptive_threshold=False)
+    got = [(int(a), int(b)) for a, b in zip(tok.last_trace["i"], tok.last_trace["j"])]
+    assert got == [(a, b) for a, b, _ in ora.trace]
+    want = np.array([t[2] for t in ora.trace], dtype=np.float32)
+    assert np.all(np.abs(tok.last_trace["d"] - want) <= REL * np.abs(want))
+    assert tok.vocab == ora.vocab
 
 
 def test_running_argmin_equals_recompute_full_size():

@@ -126,13 +126,15 @@ def test_v1_kernel_matches_too():
 
 
 def test_large_ascii_vs_oracle():
-    """64 MB of synthetic config-4 text (lines of 20 random words).  Checksum property at full chunk
-    counts: total pairs == sum over lines of max(len(strip(line)) - 1, 0); exact dict on a sample."""
+    """64 MB of synthetic config-4 text (lines of 20 random words): the exact dict against the C oracle, the checksum
+    property total pairs == sum over lines of max(len(strip(line)) - 1, 0), and a sample against the Python oracle."""
     from hyptokenizer_b200.pair_count import count_pairs
     from hyptokenizer_b200.synth import synthetic_corpus
     from oracle.merge import count_pairs_py
+    from oracle.pair_count import count_pairs_c
     data = synthetic_corpus(64 << 20, seed=0)
     got = count_pairs(data)
+    assert got == count_pairs_c(data)               # the full dict against the C restatement of the reference's loop
     lines = data.tobytes().decode("ascii").split("\n")
     total = sum(max(len(ln.strip()) - 1, 0) for ln in lines)
     assert sum(got.values()) == total
