@@ -58,6 +58,9 @@ _SIGNATURES = {
     "hyp_allpairs_workspace_bytes": ([_i64], _i64),
     "hyp_allpairs_min": ([_p, _i64, _i64, _i32, _f, _i32, _f, _p, _p, _i64, _p], C.c_int),
     "hyp_allpairs_emit": ([_p, _i64, _i64, _i32, _f, _i32, _f, _p, _p, _p, _i64, _p, _p], C.c_int),
+    "hyp_allpairs_hist": ([_p, _i64, _i64, _i32, _f, _i32, _f, C.c_uint32, _i32, _i32, _p, _p], C.c_int),
+    "hyp_allpairs_row_ties": ([_p, _i64, _i64, _i32, _f, _i32, _f, C.c_uint32, _p, _p], C.c_int),
+    "hyp_allpairs_emit_cut": ([_p, _i64, _i64, _i32, _f, _i32, _f, C.c_uint32, _i64, _p, _p, _p, _i64, _p, _p], C.c_int),
     "hyp_allpairs_topk": ([_p, _i64, _i64, _i64, _i64, _i32, _f, _i32, _i32, _p, _p, _p], C.c_int),
     "hyp_gram_topk_workspace_bytes": ([_i64, _i64, _i32], _i64),
     "hyp_gram_topk": ([_p, _i64, _i64, _i64, _i64, _i32, _f, _i32, _i32, _p, _p, _p, _p, _i64, _p], C.c_int),

@@ -20,7 +20,8 @@ namespace hyp {
 constexpr int TM = 64, TN = 64, TPAD = 68, NTHREADS = 256;
 constexpr int kMaxBlocks = 148 * 8;
 
-enum Mode { kDense = 0, kMin = 1, kEmit = 2, kGradCoef = 3 };
+enum Mode { kDense = 0, kMin = 1, kEmit = 2, kGradCoef = 3, kHist = 4, kRowTies = 5 };
+constexpr int kHistBits = 12;              // bins per radix-select pass over the 31 significant bits of d >= 0
 
 struct MinWorkspace {
   unsigned int ticket;
@@ -51,6 +52,14 @@ struct Params {
   float *out_d;
   int64_t capacity;
   unsigned long long *emit_count;
+  // emit with a cut (global top-K): only pairs with bits(d) < cut_bits, or == cut_bits in rows <= cut_row
+  unsigned int cut_bits;
+  int64_t cut_row;
+  // hist: pairs whose distance bits start with `prefix` (prefix_len bits below the sign) are binned on the next
+  // kHistBits (or fewer) bits; row ties: pairs with bits(d) == cut_bits counted per row
+  unsigned int prefix, prefix_shift, bin_shift, bin_mask;
+  unsigned long long *hist;
+  unsigned int *row_ties;
   // tiles
   int64_t tiles_m, tiles_n, n_tiles;
   int triangular;
@@ -160,6 +169,11 @@ __global__ void __launch_bounds__(NTHREADS) allpairs_tile_kernel(const Params p)
   __shared__ Key s_keys[NTHREADS / 32];
   __shared__ unsigned long long s_cnt[NTHREADS / 32];
   __shared__ int s_last;
+  __shared__ unsigned int s_hist[MODE == kHist ? (1 << kHistBits) : 1];
+  if (MODE == kHist) {
+    for (int q = threadIdx.x; q < (1 << kHistBits); q += NTHREADS) s_hist[q] = 0;
+    __syncthreads();
+  }
 
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -209,6 +223,39 @@ __global__ void __launch_bounds__(NTHREADS) allpairs_tile_kernel(const Params p)
             if (gj < p.n2) p.out[gi * p.ldo + gj] = dist[c];
           }
         }
+      } else if (MODE == kHist) {
+        // radix-select pass: candidates (i < j, d < thr) whose distance bits carry the prefix, binned on the next bits.
+        // Equal bins of a thread's row are merged before they touch shared memory (in the shipped semantics every
+        // distance is 0: one bin).
+        unsigned int prev = 0xffffffffu, run = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int64_t gj = j0 + 4 * tx + c;
+          if (gi < gj && gj < p.n2 && gi < p.n1 && dist[c] == dist[c] && dist[c] < p.thr) {
+            const unsigned int bits = __float_as_uint(dist[c]);
+            if ((bits >> p.prefix_shift) == p.prefix || p.prefix_shift >= 32u) {
+              const unsigned int bin = (bits >> p.bin_shift) & p.bin_mask;
+              if (bin == prev) ++run;
+              else {
+                if (run) atomicAdd(&s_hist[prev], run);
+                prev = bin;
+                run = 1;
+              }
+            }
+          }
+        }
+        if (run) atomicAdd(&s_hist[prev], run);
+      } else if (MODE == kRowTies) {
+        unsigned int ties = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int64_t gj = j0 + 4 * tx + c;
+          if (gi < gj && gj < p.n2 && gi < p.n1 && dist[c] < p.thr && __float_as_uint(dist[c]) == p.cut_bits) ++ties;
+        }
+        // the 16 threads of a half warp share their four rows: one atomic per row and half warp
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) ties += __shfl_xor_sync(HYP_FULL_MASK, ties, o);
+        if (tx == 0 && ties && gi < p.n1) atomicAdd(p.row_ties + gi, ties);
       } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -219,11 +266,14 @@ __global__ void __launch_bounds__(NTHREADS) allpairs_tile_kernel(const Params p)
               Key k{dist[c], (int)gi, (int)gj};
               if (key_less(k, best)) best = k;
             } else if (dist[c] < p.thr) {
-              unsigned long long pos = atomicAdd(p.emit_count, 1ULL);
-              if ((int64_t)pos < p.capacity) {
-                p.out_i[pos] = (int)gi;
-                p.out_j[pos] = (int)gj;
-                p.out_d[pos] = dist[c];
+              const unsigned int bits = __float_as_uint(dist[c]);
+              if (bits < p.cut_bits || (bits == p.cut_bits && gi <= p.cut_row)) {
+                unsigned long long pos = atomicAdd(p.emit_count, 1ULL);
+                if ((int64_t)pos < p.capacity) {
+                  p.out_i[pos] = (int)gi;
+                  p.out_j[pos] = (int)gj;
+                  p.out_d[pos] = dist[c];
+                }
               }
             }
           }
@@ -232,6 +282,13 @@ __global__ void __launch_bounds__(NTHREADS) allpairs_tile_kernel(const Params p)
     }
   }
 
+  if (MODE == kHist) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < (1 << kHistBits); q += NTHREADS) {
+      const unsigned int v = s_hist[q];
+      if (v) atomicAdd(p.hist + q, (unsigned long long)v);
+    }
+  }
   if (MODE == kMin) {
     best = warp_key_min(best);
 #pragma unroll
@@ -522,7 +579,65 @@ extern "C" int hyp_allpairs_emit(const float *E, int64_t ldE, int64_t n, int D, 
   p.out_i = out_i; p.out_j = out_j; p.out_d = out_d;
   p.capacity = capacity;
   p.emit_count = count;
+  p.cut_bits = 0xffffffffu;                  // no cut: every candidate
+  p.cut_row = 0;
   return launch_tiles<kEmit>(p, st, "hyp_allpairs_emit");
+}
+
+extern "C" int hyp_allpairs_emit_cut(const float *E, int64_t ldE, int64_t n, int D, float c, int semantics,
+                                     float threshold, uint32_t cut_bits, int64_t cut_row, int32_t *out_i, int32_t *out_j,
+                                     float *out_d, int64_t capacity, unsigned long long *count, void *stream) {
+  Params p;
+  int rc = fill_params(p, E, ldE, n, E, ldE, n, D, c, semantics, 1);
+  if (rc) return rc;
+  if (!count || capacity < 0 || (capacity > 0 && (!out_i || !out_j || !out_d))) return HYP_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(count, 0, sizeof(unsigned long long), st);
+  if (n < 2) return HYP_OK;
+  p.thr = threshold;
+  p.out_i = out_i; p.out_j = out_j; p.out_d = out_d;
+  p.capacity = capacity;
+  p.emit_count = count;
+  p.cut_bits = cut_bits;
+  p.cut_row = cut_row;
+  return launch_tiles<kEmit>(p, st, "hyp_allpairs_emit_cut");
+}
+
+extern "C" int hyp_allpairs_hist(const float *E, int64_t ldE, int64_t n, int D, float c, int semantics, float threshold,
+                                 uint32_t prefix, int prefix_len, int bin_bits, unsigned long long *hist, void *stream) {
+  Params p;
+  int rc = fill_params(p, E, ldE, n, E, ldE, n, D, c, semantics, 1);
+  if (rc) return rc;
+  if (!hist || prefix_len < 0 || bin_bits < 1 || bin_bits > kHistBits || prefix_len + bin_bits > 31) {
+    set_error("hyp_allpairs_hist: bad arguments (prefix_len=%d bin_bits=%d: 1 <= bin_bits <= %d, prefix_len + bin_bits <= 31)",
+              prefix_len, bin_bits, kHistBits);
+    return HYP_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(hist, 0, sizeof(unsigned long long) << kHistBits, st);
+  if (n < 2) return HYP_OK;
+  p.thr = threshold;
+  p.prefix = prefix;
+  p.prefix_shift = prefix_len == 0 ? 32u : (unsigned int)(31 - prefix_len);
+  p.bin_shift = (unsigned int)(31 - prefix_len - bin_bits);
+  p.bin_mask = (1u << bin_bits) - 1u;
+  p.hist = hist;
+  return launch_tiles<kHist>(p, st, "hyp_allpairs_hist");
+}
+
+extern "C" int hyp_allpairs_row_ties(const float *E, int64_t ldE, int64_t n, int D, float c, int semantics,
+                                     float threshold, uint32_t d_bits, unsigned int *row_ties, void *stream) {
+  Params p;
+  int rc = fill_params(p, E, ldE, n, E, ldE, n, D, c, semantics, 1);
+  if (rc) return rc;
+  if (!row_ties && n > 0) return HYP_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > 0) cudaMemsetAsync(row_ties, 0, sizeof(unsigned int) * (size_t)n, st);
+  if (n < 2) return HYP_OK;
+  p.thr = threshold;
+  p.cut_bits = d_bits;
+  p.row_ties = row_ties;
+  return launch_tiles<kRowTies>(p, st, "hyp_allpairs_row_ties");
 }
 
 namespace hyp {

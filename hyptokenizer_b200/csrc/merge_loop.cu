@@ -34,8 +34,8 @@ struct LoopWorkspace {
   unsigned long long reserved[4];
   struct alignas(16) XSlot {       // resident loop: per-step exchange word, polled with ONE 128-bit load
     unsigned long long key;        //   RED.MIN target: d_bits << 32 | row (kNoKey when nobody improved on `best`)
-    unsigned int count;            //   arrivals, never reset: use u of a slot completes at count == G * u
-    unsigned int pad;
+    unsigned long long cw;         //   ONE 64-bit scalar: arrivals in the low word (never reset: use u of a slot
+                                   //   completes at G * u), CTAs that posted a key during this use in the high word
   } xring[kXRing];
   Key slot[2][kMaxLoopBlocks];     // L2 loop: per-CTA minima, double-buffered by step parity
   unsigned long long below[kMaxLoopBlocks];
@@ -74,14 +74,31 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned int *p, unsigned int v) 
 __device__ __forceinline__ void red_relaxed_add_u32(unsigned int *p, unsigned int v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_release_add_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_relaxed_add_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// Every wait on another CTA is bounded: ~2^24 polls (each an L2 round trip, some 10 s in all) and the kernel traps --
+// the launch fails with an error instead of hanging the GPU if the replicated state of the CTAs ever diverged.
+constexpr unsigned int kSpinLimit = 1u << 24;
+__device__ __forceinline__ void spin_guard(unsigned int &spins) {
+  if (++spins > kSpinLimit) __trap();
+}
 
 // All CTAs of a cooperative launch (co-resident by construction).
 __device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     red_release_add_u32(ctr, 1u);
-    while (ld_acquire_u32(ctr) < target) {
-    }
+    unsigned int spins = 0;
+    while (ld_acquire_u32(ctr) < target) spin_guard(spins);
   }
   __syncthreads();
 }
@@ -592,8 +609,7 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
   if (b == 0) {
     for (int sl = threadIdx.x; sl < kXRing; sl += blockDim.x) {
       p.ws->xring[sl].key = kNoKey;
-      p.ws->xring[sl].count = 0u;
-      p.ws->xring[sl].pad = 0u;
+      p.ws->xring[sl].cw = 0ull;
     }
   }
   grid_barrier(&p.ws->barrier, arrivals);
@@ -641,7 +657,9 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
         p.len[nn] = s_len[0] + s_len[1];
         p.log[kk] = hyp_merge_record{best.i, best.j, best.d, nn};
         // recycle the exchange slot used kXRing/2 merges ago (every CTA is past it) for its use kXRing/2 merges on
-        p.ws->xring[(kk + kXRing / 2) & (kXRing - 1)].key = kNoKey;
+        LoopWorkspace::XSlot *rs = &p.ws->xring[(kk + kXRing / 2) & (kXRing - 1)];
+        rs->key = kNoKey;
+        reinterpret_cast<unsigned int *>(&rs->cw)[1] = 0u;        // its "posted" word; the arrivals keep counting
       }
       __threadfence();
       __syncwarp();
@@ -672,8 +690,13 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
       }
     }
     if (OVER && has_over) {
-      if (lane == 0)
-        while (pub + 1u < nscan) pub = ld_acquire_u32(&p.ws->published);   // every earlier scan's append is visible
+      if (lane == 0) {
+        unsigned int spins = 0;
+        while (pub + 1u < nscan) {                                         // every earlier scan's append is visible
+          pub = ld_acquire_u32(&p.ws->published);
+          spin_guard(spins);
+        }
+      }
       __syncwarp();
       overflow_scan(p.E, p.ldE, over0, nn, q, D, p.sqrt_c, p.sgn, (int64_t)b * kWorkWarps + warp, (int64_t)G * kWorkWarps,
                     lane, my_d, my_r);
@@ -698,35 +721,50 @@ __global__ void __launch_bounds__(kResThreads, 1) merge_loop_resident_kernel(con
     }
   };
 
-  // ---- exchange on ONE 16-byte slot per merge (slot kk mod kXRing; its counter is never reset, use u completes at
-  // G * u).  A CTA posts its minimum (64-bit RED.MIN) only when it beats `best` -- every CTA holds the same `best`,
-  // so a key that does not beat it cannot change the outcome -- and then arrives (RED.ADD).  Arrival is a release
-  // only behind a posted key; everything else arrives relaxed (CTA 0's appends are published separately, see scan).  Every CTA reads the slot with a single 128-bit load: the load that sees the full count also
-  // carries the final minimum (a RED.MIN is ordered before its CTA's arrival, and the arrivals form one RMW chain
-  // on `count`), so there is no second round trip.  Thread 0 only.
+  // ---- exchange on ONE 16-byte slot per merge (slot kk mod kXRing; its arrival counter is never reset, use u completes
+  // at G * u).  A CTA posts its minimum (64-bit RED.MIN) only when it beats `best` -- every CTA holds the same `best`,
+  // so a key that does not beat it cannot change the outcome -- and then arrives with ONE 64-bit RED.ADD on `cw`:
+  // +1 arrival, and +1 in the high word if it posted (a release, ordered behind its RED.MIN; everything else arrives
+  // relaxed: CTA 0's appends are published separately, see scan).  Every CTA reads the slot with a single 128-bit
+  // load.  Memory-model argument: `cw` is one 64-bit scalar and all updates of it are RMWs, so the load that sees the
+  // full arrival count sees the exact number of posts of this use.  No post (the steady state): no RED.MIN on the slot
+  // exists since its reset, so the key element reads kNoKey whenever the hardware fetched it.  A post (a failed guess, rare):
+  // the count is re-read with an ACQUIRE, which synchronises with the posters' release arrivals, and only then the key
+  // is loaded.  So nothing relies on a vector load being one atomic access, and there is no second round trip on the
+  // path that matters.  Thread 0 only.
   auto arrive = [&](int kk, int nn) {
     LoopWorkspace::XSlot *xr = &p.ws->xring[kk & (kXRing - 1)];
     const bool post = c_r != 0xffffffffu && key_less(Key{__uint_as_float(c_d), (int)c_r, nn}, best);
     if (post) atomicMin(&xr->key, ((unsigned long long)c_d << 32) | c_r);
-    if (post) red_release_add_u32(&xr->count, 1u);
-    else red_relaxed_add_u32(&xr->count, 1u);
+    if (post) red_release_add_u64(&xr->cw, 0x100000001ull);
+    else red_relaxed_add_u64(&xr->cw, 1ull);
   };
   auto poll = [&](int kk) {
     const LoopWorkspace::XSlot *xr = &p.ws->xring[kk & (kXRing - 1)];
     const unsigned int target = (unsigned int)G * (unsigned int)((kk / kXRing) + 1);
     unsigned long long key = e_key, cc = e_cnt;
     if (!e_issued) ld_relaxed_v2_u64(xr, key, cc);
-    // (the pad word, always 0, is added in so that all four registers of the early load stay live until here:
-    //  a register of an in-flight load that the compiler reuses stalls the scan for the whole round trip)
-    while ((unsigned int)(cc & 0xffffffffu) + (unsigned int)(cc >> 32) < target) ld_relaxed_v2_u64(xr, key, cc);
+    unsigned int spins = 0;
+    while ((unsigned int)(cc & 0xffffffffu) < target) {
+      ld_relaxed_v2_u64(xr, key, cc);
+      spin_guard(spins);
+    }
     e_issued = false;
+    if ((unsigned int)(cc >> 32) != 0u) {
+      (void)ld_acquire_u64(&xr->cw);           // synchronises with the release arrival of every CTA that posted
+      key = ld_relaxed_u64(&xr->key);
+    }
+    // (no post: no RED.MIN on this slot exists since CTA 0 reset it -- every CTA's arrival is already in `cw` and none
+    //  of them posted -- so the key that came with the vector load IS kNoKey, whenever its element was read.  Using it
+    //  also keeps the register of the early load live until here: a register of an in-flight load that the compiler
+    //  reuses stalls the scan for the whole round trip.)
     s_win[kk & 1] = key;
   };
   // Thread 0: wait until CTA 0 has fenced the appends of every scan before the one in flight, then fence: what those
   // scans wrote (rows / len below n, recycled exchange slots) may be read after the next CTA barrier.
   auto wait_published = [&]() {
-    while (ld_relaxed_u32(&p.ws->published) + 1u < nscan) {
-    }
+    unsigned int spins = 0;
+    while (ld_relaxed_u32(&p.ws->published) + 1u < nscan) spin_guard(spins);
     __threadfence();
   };
 

@@ -341,8 +341,10 @@ __device__ __forceinline__ void v2_prepare(V2Group &g, int64_t base, int64_t n, 
 
 __global__ void __launch_bounds__(kV2Threads, 1)
 pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long long *__restrict__ ascii_counts,
-                     unsigned long long *hkeys, unsigned long long *hvals, uint32_t cap_mask, int *overflow) {
+                     unsigned long long *hkeys, unsigned long long *hvals, uint32_t cap_mask, int *overflow,
+                     const int *__restrict__ select) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  if (select && *select != 2) return;          // the stream's alphabet chose the other kernel (pair_count_select_kernel)
   uint8_t *priv = smem_raw;                                                    // [warps][256 word rows][32 lanes][4]
   uint32_t *hist64 = reinterpret_cast<uint32_t *>(smem_raw + kV2Warps * kPrivPerWarp);   // [64*64]
   uint16_t *tabA = reinterpret_cast<uint16_t *>(hist64 + 64 * 64);              // byte -> priv_off_a(private rank)
@@ -588,22 +590,17 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
 // Result bits are identical to v1 / v2 for any input (tests/test_gpu_paircount.py runs all three).
 constexpr int kV3Syms = 28;                                // 27 private symbols + the junk rank
 constexpr uint32_t kV3Junk = kV3Syms - 1;
-#ifndef HYP_V3_GROUPS
-#define HYP_V3_GROUPS 2     // 16-byte groups per thread and step: two give the scheduler two independent streams of table
-#endif                      // lookups / address arithmetic to interleave with the (ordered) counter updates
-constexpr int kV3Groups = HYP_V3_GROUPS;
 #ifdef HYP_V3_RACY16        // TIMING EXPERIMENT ONLY (wrong counts): 16 warps, warps w and w + 8 race on one block of columns
 constexpr int kV3Threads = 512, kV3Warps = 8;
 #else
 constexpr int kV3Threads = 256, kV3Warps = kV3Threads / 32;
 #endif
-constexpr int kV3Chunk = kV3Threads * 16 * kV3Groups;      // bytes of text per CTA step (8 KiB)
-constexpr int kV3Words = 2 + 4 * kV3Groups;                // a thread's slot: its bytes + 4 bytes of context on either side
+constexpr int kV3Chunk = kV3Threads * 16;                  // 4 KiB of text per CTA step, one 16-byte group per thread
 constexpr int kV3RowBytes = (kV3Syms / 4) * 128;           // a row of 28 bins = 7 words per lane x 32 lanes
 constexpr int kV3PrivPerWarp = 25600;                      // 28 rows = 25 088 bytes, padded so that the low 10 bits of a
                                                            // warp's base are zero (it is OR-ed into the offsets)
 static_assert(kV3PrivPerWarp >= kV3Syms * kV3RowBytes && (kV3PrivPerWarp & 1023) == 0, "v3 counter block");
-constexpr int kV3Depth = 4 / kV3Groups;                    // steps in flight per thread (16 KB per SM either way)
+constexpr int kV3Depth = 4;                                // steps in flight per thread: 16 KB per SM
 constexpr int kV3Bins = kV3Syms * kV3Syms;                 // 784
 constexpr size_t kV3Smem = (size_t)kV3Warps * kV3PrivPerWarp + 64 * 64 * 4 + kV3Bins * 4 + 256 * 4 + 256 * 4 + 256 + 64 + 64;
 constexpr uint32_t kV3FlagJ = 1u << 12;                    // ASCII byte outside the private alphabet (not a line break)
@@ -757,8 +754,10 @@ __device__ __noinline__ void v3_cold(const V3Cold k, int64_t base, bool classify
 
 __global__ void __launch_bounds__(kV3Threads, 1)
 pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long long *__restrict__ ascii_counts,
-                     unsigned long long *hkeys, unsigned long long *hvals, uint32_t cap_mask, int *overflow) {
+                     unsigned long long *hkeys, unsigned long long *hvals, uint32_t cap_mask, int *overflow,
+                     const int *__restrict__ select) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  if (select && *select != 3) return;          // the stream's alphabet chose the other kernel (pair_count_select_kernel)
   uint8_t *priv = smem_raw;                                                     // [warps][28 rows][7 words][32 lanes][4]
   uint32_t *hist64 = reinterpret_cast<uint32_t *>(smem_raw + kV3Warps * kV3PrivPerWarp);   // [64*64]
   uint32_t *carry = hist64 + 64 * 64;                                           // [28*28]: wraps of the one-byte counters
@@ -815,110 +814,92 @@ pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
   const V3Cold cold{hist64, sym, tabC, ascii_counts, hkeys, hvals, cap_mask, overflow, text, n};
 
   const int64_t step = (int64_t)gridDim.x * kV3Chunk;
-  int64_t base = ch * kV3Chunk + 16 * kV3Groups * (int64_t)tid;
-  // a thread's slot: bytes base-4 .. base+16G+3 as 2 + 4G words; whatever is not in the text reads as 0x80 (-> general)
-  auto load_slot = [&](uint32_t (&S)[kV3Words], int64_t at, bool checked) {
-    if (!checked || (at >= 4 && at + 16 * kV3Groups + 4 <= n)) {
-      const uint8_t *p = text + at;
+  int64_t base = ch * kV3Chunk + 16 * (int64_t)tid;
+  uint32_t Wq[kV3Depth][6];
 #pragma unroll
-      for (int g = 0; g < kV3Groups; ++g) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p + 16 * g));
-        S[1 + 4 * g] = v.x; S[2 + 4 * g] = v.y; S[3 + 4 * g] = v.z; S[4 + 4 * g] = v.w;
-      }
-      S[0] = __ldg(reinterpret_cast<const uint32_t *>(p - 4));
-      S[kV3Words - 1] = __ldg(reinterpret_cast<const uint32_t *>(p + 16 * kV3Groups));
-    } else {
-#pragma unroll
-      for (int q = 0; q < kV3Words; ++q) S[q] = 0x80808080u;
-      // a slot at either end of the text: whole words that exist are loaded, the rest stays 0x80
-      if (at < n) {
-#pragma unroll
-        for (int q = 0; q < kV3Words; ++q) {
-          const int64_t w = at - 4 + 4 * q;
-          if (w >= 0 && w + 4 <= n) S[q] = __ldg(reinterpret_cast<const uint32_t *>(text + w));
-        }
-        // a group needs its whole 24-byte neighbourhood: mark the first / last incomplete ones
-        if (at < 4) S[0] = 0x80808080u;
-      }
-    }
-  };
-  uint32_t Wq[kV3Depth][kV3Words];
-#pragma unroll
-  for (int sidx = 0; sidx < kV3Depth; ++sidx) load_slot(Wq[sidx], base + sidx * step, true);
-  // chunks whose slots all have their full neighbourhood inside the text are loaded without per-thread checks
-  const int64_t interior_hi = (n - 4) / kV3Chunk;          // chunk c is interior iff 1 <= c < interior_hi
+  for (int sidx = 0; sidx < kV3Depth; ++sidx) v2_load(Wq[sidx], text, n, base + sidx * step);
+  // chunks whose groups all have their full neighbourhood inside the text are loaded without per-thread checks
+  const int64_t interior_hi = (n - 20) / kV3Chunk;         // chunk c is interior iff 1 <= c < interior_hi
+  // (Tried: two 16-byte groups per thread and step, to give the scheduler two independent streams -- 970 GB/s against
+  //  1061 for this form on the config-4 stream; 16 warps racing on 8 warps' counters, as an upper bound for "more
+  //  warps": 1335.  The kernel is bound by dependent-issue latency at 2 warps per scheduler, see DESIGN.md.)
 
   for (;;) {
 #pragma unroll
     for (int sidx = 0; sidx < kV3Depth; ++sidx) {
       if (ch >= n_chunks) goto done;           // (uniform over the CTA)
-      uint32_t WS[kV3Words];
+      uint32_t W[6];
 #pragma unroll
-      for (int q = 0; q < kV3Words; ++q) WS[q] = Wq[sidx][q];
-      {                                        // the step kV3Depth ahead
+      for (int q = 0; q < 6; ++q) W[q] = Wq[sidx][q];
+      {                                        // the step four ahead
         const int64_t chn = ch + (int64_t)kV3Depth * gridDim.x;
-        load_slot(Wq[sidx], base + kV3Depth * step, !(chn >= 1 && chn < interior_hi));
+        const uint8_t *pn = text + base + kV3Depth * step;
+        if (chn >= 1 && chn < interior_hi) {
+          const uint4 mid = __ldg(reinterpret_cast<const uint4 *>(pn));
+          Wq[sidx][1] = mid.x; Wq[sidx][2] = mid.y; Wq[sidx][3] = mid.z; Wq[sidx][4] = mid.w;
+          Wq[sidx][0] = __ldg(reinterpret_cast<const uint32_t *>(pn - 4));
+          Wq[sidx][5] = __ldg(reinterpret_cast<const uint32_t *>(pn + 16));
+        } else {
+          v2_load(Wq[sidx], text, n, base + kV3Depth * step);   // (reads as 0x80.. past the end)
+        }
       }
+
+      const bool exists = base < n;
+      const bool plain = exists && (((W[0] | W[1] | W[2] | W[3] | W[4] | W[5]) & 0x80808080u) == 0);
+      // hot view of positions 0..16: a group that is not plain counts line breaks (junk bins) and is redone below
+      uint32_t H[5];
 #pragma unroll
-      for (int g = 0; g < kV3Groups; ++g) {
-        const int64_t gbase = base + 16 * g;
-        uint32_t W[6];
+      for (int q = 0; q < 5; ++q) H[q] = plain ? W[q + 1] : 0x0a0a0a0au;
+      uint32_t t[17];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) W[q] = WS[4 * g + q];
-        const bool exists = gbase < n;
-        const bool plain = exists && (((W[0] | W[1] | W[2] | W[3] | W[4] | W[5]) & 0x80808080u) == 0);
-        // hot view of positions 0..16: a group that is not plain counts line breaks (junk bins) and is redone below
-        uint32_t H[5];
+      for (int j = 0; j < 17; ++j) t[j] = tab[(H[j >> 2] >> (8 * (j & 3))) & 0xffu];
+      uint32_t adj = 0, any = t[16];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) H[q] = plain ? W[q + 1] : 0x0a0a0a0au;
-        uint32_t t[17];
-#pragma unroll
-        for (int j = 0; j < 17; ++j) t[j] = tab[(H[j >> 2] >> (8 * (j & 3))) & 0xffu];
-        uint32_t adj = 0, any = t[16];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          adj |= t[j] & t[j + 1];
-          adj |= t[j + 1] & t[j + 2];
-          any |= t[j] | t[j + 1];
-        }
-        uint32_t wacc[4] = {0, 0, 0, 0};       // byte 3 - (i & 3) of wacc[i >> 2]: bit 0 set if the counter of pair i passed 255
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const uint32_t a0 = (t[i] >> 16) + ((t[i + 1] & 0x383u) | lane4);
-          const uint32_t a1 = (t[i + 1] >> 16) + ((t[i + 2] & 0x383u) | lane4);
-          uint32_t c0 = col[a0];
-          uint32_t c1 = col[a1];
-          c0 += 1u;
-          c1 += (a0 == a1) ? 2u : 1u;          // same bin: the second store carries both
-          col[a0] = (uint8_t)c0;
-          col[a1] = (uint8_t)c1;
-          wacc[i >> 2] = __byte_perm(wacc[i >> 2], c0, 0x2105);
-          wacc[i >> 2] = __byte_perm(wacc[i >> 2], c1, 0x2105);
-        }
-        // A one-byte counter passed 255 (about one lane in sixteen per group): +1 in the CTA's carry table, whose bins
-        // are worth 256 at the flush.  The bin is recomputed from the text bytes; no global access, no call.
-        if ((wacc[0] | wacc[1] | wacc[2] | wacc[3]) & 0x01010101u) {
-          uint32_t wrap = 0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) wrap |= ((wacc[i >> 2] >> (8 * (3 - (i & 3)))) & 1u) << i;
-          while (wrap) {
-            const int i = __ffs(wrap) - 1;
-            wrap &= wrap - 1;
-            // bytes i and i + 1 of the hot view (H[4] holds byte 16)
-            const uint32_t lo = (i >> 2) == 0 ? H[0] : (i >> 2) == 1 ? H[1] : (i >> 2) == 2 ? H[2] : H[3];
-            const uint32_t hi = (i >> 2) == 0 ? H[1] : (i >> 2) == 1 ? H[2] : (i >> 2) == 2 ? H[3] : H[4];
-            const uint32_t two = __funnelshift_r(lo, hi, 8 * (i & 3));
-            const uint32_t ra = sym[two & 0xffu], rb = sym[(two >> 8) & 0xffu];
-            if (ra < kV3Junk && rb < kV3Junk) atomicAdd(&carry[ra * kV3Syms + rb], 1u);    // (junk bins wrap too)
-          }
-        }
-        // white space next to white space or a line break (positions -1 .. 17), a byte outside the private alphabet
-        const uint32_t cm1 = W[0] >> 24, c17 = (W[5] >> 8) & 0xffu;
-        const bool edge = ((t[0] & kV3FlagW) && cm1 <= 0x20u) || ((t[16] & kV3FlagW) && c17 <= 0x20u);
-        const bool classify = plain && (((adj & kV3FlagW) | (any & kV3FlagJ)) != 0 || edge);
-        const bool general = exists && !plain;
-        if (classify | general) v3_cold(cold, gbase, classify, general, W[0], W[1], W[2], W[3], W[4], W[5]);
+      for (int j = 0; j < 16; j += 2) {
+        adj |= t[j] & t[j + 1];
+        adj |= t[j + 1] & t[j + 2];
+        any |= t[j] | t[j + 1];
       }
+      uint32_t wacc[4] = {0, 0, 0, 0};         // byte 3 - (i & 3) of wacc[i >> 2]: bit 0 set if the counter of pair i passed 255
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        const uint32_t a0 = (t[i] >> 16) + ((t[i + 1] & 0x383u) | lane4);
+        const uint32_t a1 = (t[i + 1] >> 16) + ((t[i + 2] & 0x383u) | lane4);
+        uint32_t c0 = col[a0];
+        uint32_t c1 = col[a1];
+        // same bin: the first store writes the old value back, the second carries both increments (so that a wrap
+        // is seen once, in c1)
+        const bool same = a0 == a1;
+        c0 += same ? 0u : 1u;
+        c1 += same ? 2u : 1u;
+        col[a0] = (uint8_t)c0;
+        col[a1] = (uint8_t)c1;
+        wacc[i >> 2] = __byte_perm(wacc[i >> 2], c0, 0x2105);
+        wacc[i >> 2] = __byte_perm(wacc[i >> 2], c1, 0x2105);
+      }
+      // A one-byte counter passed 255: +1 in the CTA's carry table, whose bins are worth 256 at the flush.  The bin is
+      // recomputed from the text bytes; no global access, no call.
+      if ((wacc[0] | wacc[1] | wacc[2] | wacc[3]) & 0x01010101u) {
+        uint32_t wrap = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) wrap |= ((wacc[i >> 2] >> (8 * (3 - (i & 3)))) & 1u) << i;
+        while (wrap) {
+          const int i = __ffs(wrap) - 1;
+          wrap &= wrap - 1;
+          // bytes i and i + 1 of the hot view (H[4] holds byte 16)
+          const uint32_t lo = (i >> 2) == 0 ? H[0] : (i >> 2) == 1 ? H[1] : (i >> 2) == 2 ? H[2] : H[3];
+          const uint32_t hi = (i >> 2) == 0 ? H[1] : (i >> 2) == 1 ? H[2] : (i >> 2) == 2 ? H[3] : H[4];
+          const uint32_t two = __funnelshift_r(lo, hi, 8 * (i & 3));
+          const uint32_t ra = sym[two & 0xffu], rb = sym[(two >> 8) & 0xffu];
+          if (ra < kV3Junk && rb < kV3Junk) atomicAdd(&carry[ra * kV3Syms + rb], 1u);    // (junk bins wrap too)
+        }
+      }
+      // white space next to white space or a line break (positions -1 .. 17), a byte outside the private alphabet
+      const uint32_t cm1 = W[0] >> 24, c17 = (W[5] >> 8) & 0xffu;
+      const bool edge = ((t[0] & kV3FlagW) && cm1 <= 0x20u) || ((t[16] & kV3FlagW) && c17 <= 0x20u);
+      const bool classify = plain && (((adj & kV3FlagW) | (any & kV3FlagJ)) != 0 || edge);
+      const bool general = exists && !plain;
+      if (classify | general) v3_cold(cold, base, classify, general, W[0], W[1], W[2], W[3], W[4], W[5]);
       ch += gridDim.x;
       base += step;
     }
@@ -948,6 +929,80 @@ done:
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Which kernel for this stream?  v3 counts every pair of the 27 most frequent symbols unconditionally and repairs the
+// rest in a cold path; that pays while the cold path is rare.  One CTA looks at 16 windows of 4 KiB spread over the
+// stream: the share of bytes outside the 27 most frequent symbols of the sample (line breaks aside) and of adjacent
+// white-space bytes.  Above 0.4 % of the positions v2 -- which decides every pair before it counts, at a fixed cost --
+// is the faster one (wide alphabets, indented text).  The verdict is a device word both kernels read: the one that is
+// not chosen returns at once, so there is no host round trip.  Results are identical either way.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSelWindows = 16, kSelWindow = 4096, kSelThreads = 1024;
+__global__ void __launch_bounds__(kSelThreads)
+pair_count_select_kernel(const uint8_t *__restrict__ text, int64_t n, int *__restrict__ select) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int member[4];           // bit c: ASCII byte c is one of the 27 most frequent (or a line break)
+  __shared__ unsigned int bad;
+  const int tid = threadIdx.x;
+  if (tid < 256) hist[tid] = 0;
+  if (tid < 4) member[tid] = 0;
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  const int64_t span = n < (int64_t)kSelWindows * kSelWindow ? n : (int64_t)kSelWindows * kSelWindow;
+  const int64_t stride = n > span ? ((n - kSelWindow) / (kSelWindows - 1)) & ~(int64_t)15 : kSelWindow;
+  auto pos_of = [&](int64_t q) -> int64_t {    // q-th sampled byte -> position in the text
+    return n > span ? (q / kSelWindow) * stride + (q % kSelWindow) : q;
+  };
+  // frequency ranks from the first window only (what a counting CTA does with its first chunk)
+  const int64_t first = span < kSelWindow ? span : kSelWindow;
+  for (int64_t q = tid; q < first; q += kSelThreads) atomicAdd(&hist[__ldg(text + q)], 1u);
+  __syncthreads();
+  if (tid < 128) {
+    bool in = tid == 0x0a || tid == 0x0d;
+    if (!in) {
+      const unsigned int mine = hist[tid];
+      unsigned int rank = 0;
+      for (int w = 0; w < 128; ++w) {
+        const unsigned int c = hist[w];
+        rank += (w != 0x0a && w != 0x0d && (c > mine || (c == mine && w < tid))) ? 1u : 0u;
+      }
+      in = rank < 27u;
+    }
+    if (in) atomicOr(&member[tid >> 5], 1u << (tid & 31));
+  }
+  __syncthreads();
+  unsigned int mine_bad = 0;
+  for (int64_t q = tid; q < span; q += kSelThreads) {
+    const int64_t p = pos_of(q);
+    const unsigned int c = __ldg(text + p);
+    const unsigned int nx = p + 1 < n ? __ldg(text + p + 1) : 0x41u;
+    const bool outside = c >= 128u || !((member[c >> 5] >> (c & 31)) & 1u);
+    const bool ws_pair = c <= 0x20u && nx <= 0x20u;
+    mine_bad += (outside || ws_pair) ? 1u : 0u;
+  }
+  mine_bad = __reduce_add_sync(HYP_FULL_MASK, mine_bad);
+  if ((tid & 31) == 0 && mine_bad) atomicAdd(&bad, mine_bad);
+  __syncthreads();
+  if (tid == 0) *select = ((unsigned long long)bad * 250ull > (unsigned long long)span) ? 2 : 3;   // > 0.4 %
+}
+
+// a few device words per GPU for the selection verdicts of calls in flight (allocated on first use)
+static int *select_slot() {
+  constexpr int kDevs = 64, kSlots = 64;
+  static int *base[kDevs] = {nullptr};
+  static unsigned int next[kDevs] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kDevs) return nullptr;
+  if (!base[dev] && cudaMalloc((void **)&base[dev], kSlots * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    base[dev] = nullptr;
+    return nullptr;
+  }
+  return base[dev] + (next[dev]++ % kSlots);
+}
+
 }  // namespace hyp
 
 using namespace hyp;
@@ -973,31 +1028,45 @@ extern "C" int hyp_pair_count(const uint8_t *text, int64_t n_bytes, unsigned lon
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // HYP_PAIR_COUNT=v1 / v2 selects the older kernels (same results; kept for A/B runs and as regression oracles of v3)
+  // HYP_PAIR_COUNT=v1 | v2 | v3 forces one kernel (same results; A/B runs, and the tests run every one of them);
+  // default: v3 or v2 by the stream's alphabet, decided on the device (pair_count_select_kernel)
   const char *ev = getenv("HYP_PAIR_COUNT");
-  const int variant = (ev && ev[0] == 'v' && ev[1] >= '1' && ev[1] <= '3') ? ev[1] - '0' : 3;
-  if (variant == 3) {
-    if (cudaFuncSetAttribute(pair_count_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kV3Smem) != cudaSuccess) {
-      set_error("hyp_pair_count: cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
-      return HYP_ERR_CUDA;
+  const int variant = (ev && ev[0] == 'v' && ev[1] >= '1' && ev[1] <= '3') ? ev[1] - '0' : 0;
+  if (variant != 1) {
+    int *select = nullptr;
+    if (variant == 0) {
+      select = select_slot();
+      if (!select) {
+        set_error("hyp_pair_count: no device memory for the kernel selection word");
+        return HYP_ERR_CUDA;
+      }
+      pair_count_select_kernel<<<1, kSelThreads, 0, st>>>(text, n_bytes, select);
+      int rc = check_launch("hyp_pair_count(select)");
+      if (rc) return rc;
     }
-    const int64_t chunks3 = (n_bytes + kV3Chunk - 1) / kV3Chunk;
-    const int grid3 = (int)(chunks3 < (int64_t)sms ? chunks3 : (int64_t)sms);
-    pair_count_v3_kernel<<<grid3, kV3Threads, kV3Smem, st>>>(text, n_bytes, ascii_counts, hash_keys, hash_vals,
-                                                             (uint32_t)(hash_capacity - 1), overflow);
-    return check_launch("hyp_pair_count");
-  }
-  if (variant == 2) {
     // (per device, so set before every launch: a process-wide "already set" flag would skip it on a second GPU)
-    if (cudaFuncSetAttribute(pair_count_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kV2Smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(pair_count_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kV3Smem) != cudaSuccess ||
+        cudaFuncSetAttribute(pair_count_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kV2Smem) != cudaSuccess) {
       set_error("hyp_pair_count: cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
       return HYP_ERR_CUDA;
     }
-    const int64_t chunks2 = (n_bytes + kV2Chunk - 1) / kV2Chunk;
-    const int grid2 = (int)(chunks2 < (int64_t)sms ? chunks2 : (int64_t)sms);
-    pair_count_v2_kernel<<<grid2, kV2Threads, kV2Smem, st>>>(text, n_bytes, ascii_counts, hash_keys, hash_vals,
-                                                             (uint32_t)(hash_capacity - 1), overflow);
-    return check_launch("hyp_pair_count");
+    if (variant == 0 || variant == 3) {
+      const int64_t chunks3 = (n_bytes + kV3Chunk - 1) / kV3Chunk;
+      const int grid3 = (int)(chunks3 < (int64_t)sms ? chunks3 : (int64_t)sms);
+      pair_count_v3_kernel<<<grid3, kV3Threads, kV3Smem, st>>>(text, n_bytes, ascii_counts, hash_keys, hash_vals,
+                                                               (uint32_t)(hash_capacity - 1), overflow, select);
+      int rc = check_launch("hyp_pair_count(v3)");
+      if (rc) return rc;
+    }
+    if (variant == 0 || variant == 2) {
+      const int64_t chunks2 = (n_bytes + kV2Chunk - 1) / kV2Chunk;
+      const int grid2 = (int)(chunks2 < (int64_t)sms ? chunks2 : (int64_t)sms);
+      pair_count_v2_kernel<<<grid2, kV2Threads, kV2Smem, st>>>(text, n_bytes, ascii_counts, hash_keys, hash_vals,
+                                                               (uint32_t)(hash_capacity - 1), overflow, select);
+      int rc = check_launch("hyp_pair_count(v2)");
+      if (rc) return rc;
+    }
+    return HYP_OK;
   }
   const size_t smem = 128 * 128 * sizeof(uint32_t) + kChunk + 2 * kHalo;
   if (cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

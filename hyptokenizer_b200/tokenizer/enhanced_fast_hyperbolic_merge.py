@@ -329,6 +329,8 @@ class EnhancedFastHyperbolicTokenizer(CurvatureStepMixin, FastHyperbolicTokenize
         """reference :903-990."""
         return self._score_arrays([candidate.token_i], [candidate.token_j], [candidate.distance])[0]
 
+    _refill_needs_full_list = True      # every candidate of a refill is scored and re-ranked (reference :992-1013)
+
     def _basic_candidate_arrays(self):
         if self.cache_semantics == "snapshot":
             return self._find_merge_candidates_fast_arrays()

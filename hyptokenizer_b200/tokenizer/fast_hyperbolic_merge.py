@@ -117,16 +117,79 @@ class FastHyperbolicTokenizer(HyperbolicTokenizer):
         self.use_approximate_search = False
 
     # ---- candidate search ------------------------------------------------------------------------
+    # _candidate_arrays: lists up to this many candidates are materialised and sorted whole; longer ones go through the
+    # device radix select, which materialises at most _SELECT_EMIT_LIMIT + n of them
+    _EMIT_ALL_LIMIT = 1 << 21
+    _SELECT_EMIT_LIMIT = 1 << 20
+    # subclasses that re-rank the WHOLE list of a refill by something else than distance (the enhanced tokenizer's
+    # combined score, reference enhanced_fast_hyperbolic_merge.py:992-1013) cannot take the distance-ordered head of it
+    _refill_needs_full_list = False
+
+    def _sorted_candidates(self, oi, oj, od, n, keep=None):
+        """(d, i, j) lexicographic == stable sort on d of the row-major list; first `keep` entries as numpy arrays."""
+        order = torch.argsort(oi.to(torch.int64) * n + oj.to(torch.int64))
+        od = od[order]
+        o2 = torch.sort(od, stable=True).indices
+        if keep is not None:
+            o2 = o2[:keep]
+        order = order[o2]
+        return oi[order].cpu().numpy().astype(np.int64), oj[order].cpu().numpy().astype(np.int64), od[o2].cpu().numpy()
+
+    def _candidate_topk(self, keep: int, thr: float):
+        """The first `keep` candidates in (d, i, j) order of a list too long to materialise -- all AdaptiveMergeCache
+        .add_batch keeps of it (reference :91-95) -- by a radix select on the device (include/hyptok_b200.h,
+        hyp_allpairs_hist / _row_ties / _emit_cut): <= 3 histogram sweeps over the 31 bits of d narrow down the
+        keep-th distance, a per-row count of the pairs AT that distance finds the row where the keep-th pair sits
+        (ties are row-major), one sweep emits the <= keep + n survivors."""
+        E, ws = self._table(), self._workspace()
+        n, D = self.current_vocab_size, E.shape[1]
+        L, c, sem = _lib.lib(), LM._curv(self.curvature), SEM[self.semantics]
+        hist = torch.empty(1 << 12, dtype=torch.int64, device=E.device)
+        prefix, plen, below = 0, 0, 0
+        cut_bits, cut_row, n_emit = None, -1, 0
+        with torch.cuda.device(E.device):
+            for bin_bits in (12, 12, 7):
+                check(L.hyp_allpairs_hist(ptr(E), E.stride(0), n, D, c, sem, thr, prefix, plen, bin_bits, ptr(hist),
+                                          stream_ptr()))
+                h = hist[: 1 << bin_bits].cpu().numpy()
+                cum = below + np.cumsum(h)
+                b = min(int(np.searchsorted(cum, keep, side="left")), len(h) - 1)
+                below = int(cum[b - 1]) if b > 0 else below
+                prefix, plen = (prefix << bin_bits) | b, plen + bin_bits
+                if int(cum[b]) <= self._SELECT_EMIT_LIMIT:      # everything up to the end of this bin: few enough to sort
+                    cut_bits, n_emit = (prefix + 1) << (31 - plen), int(cum[b])
+                    break
+            else:
+                # `prefix` is the bit pattern of the keep-th distance: `below` pairs are strictly closer, the rest of
+                # the list is decided among the pairs exactly AT it, in row-major order
+                ties = torch.empty(n, dtype=torch.int32, device=E.device)
+                check(L.hyp_allpairs_row_ties(ptr(E), E.stride(0), n, D, c, sem, thr, prefix, ptr(ties), stream_ptr()))
+                cs = np.cumsum(ties.cpu().numpy().astype(np.int64))
+                cut_row = min(int(np.searchsorted(cs, keep - below, side="left")), n - 1)
+                cut_bits, n_emit = prefix, below + int(cs[cut_row])
+            oi = torch.empty(n_emit, dtype=torch.int32, device=E.device)
+            oj = torch.empty(n_emit, dtype=torch.int32, device=E.device)
+            od = torch.empty(n_emit, dtype=torch.float32, device=E.device)
+            check(L.hyp_allpairs_emit_cut(ptr(E), E.stride(0), n, D, c, sem, thr, cut_bits, cut_row, ptr(oi), ptr(oj),
+                                          ptr(od), n_emit, ptr(ws["count"]), stream_ptr()))
+            assert int(ws["count"].item()) == n_emit, "radix select: emitted count differs from the histogram's"
+        return self._sorted_candidates(oi, oj, od, n, keep)
+
     def _candidate_arrays(self):
-        """All (i, j, d) below the threshold, sorted by distance (stable over row-major order)."""
+        """All (i, j, d) below the threshold, sorted by distance (stable over row-major order) -- or, when that list
+        would not fit (`_last_candidate_total` > _EMIT_ALL_LIMIT), its first cache.max_size entries, which is all
+        the cache keeps of it."""
         E, ws = self._table(), self._workspace()
         n, D = self.current_vocab_size, E.shape[1]
         thr = _threshold_f32(self.merge_threshold, n)
         head = self._global_best(thr)
         total = head.count_lo | (head.count_hi << 32)
+        self._last_candidate_total = total
+        if total > self._EMIT_ALL_LIMIT and total > self.cache.max_size and not self._refill_needs_full_list:
+            return self._candidate_topk(self.cache.max_size, thr)
         if total > 200_000_000:
-            raise NotImplementedError(
-                f"cache_semantics='snapshot' would materialise {total} candidates; use cache_semantics='fresh'")
+            raise NotImplementedError(f"this tokenizer scores every candidate of a refill and {total} of them would be "
+                                      "materialised; lower merge_threshold")
         oi = torch.empty(total, dtype=torch.int32, device=E.device)
         oj = torch.empty(total, dtype=torch.int32, device=E.device)
         od = torch.empty(total, dtype=torch.float32, device=E.device)
@@ -135,17 +198,13 @@ class FastHyperbolicTokenizer(HyperbolicTokenizer):
                 check(_lib.lib().hyp_allpairs_emit(ptr(E), E.stride(0), n, D, LM._curv(self.curvature),
                                                    SEM[self.semantics], thr, ptr(oi), ptr(oj), ptr(od), total,
                                                    ptr(ws["count"]), stream_ptr()))
-        # (d, i, j) lexicographic == stable sort on d of the row-major list
-        order = torch.argsort(oi.to(torch.int64) * n + oj.to(torch.int64))
-        od = od[order]
-        o2 = torch.sort(od, stable=True).indices
-        order = order[o2]
-        return oi[order].cpu().numpy().astype(np.int64), oj[order].cpu().numpy().astype(np.int64), od[o2].cpu().numpy()
+        return self._sorted_candidates(oi, oj, od, n)
 
     def _find_merge_candidates_fast_arrays(self):
         """reference :253-376 (cache first, else full search + cache.add_batch)."""
         got = self.cache.pop_arrays(100)
         if got is not None:
+            self._last_candidate_total = len(got[2])
             return got
         ii, jj, dd = self._candidate_arrays()
         self.cache.add_arrays(ii, jj, dd)
@@ -255,7 +314,7 @@ class FastHyperbolicTokenizer(HyperbolicTokenizer):
         for step in range(steps):
             ii, jj, dd = self._find_merge_candidates_fast_arrays()
             if step % log_every == 0 or len(dd) == 0:
-                self._log_stats(step, len(dd))
+                self._log_stats(step, self._last_candidate_total)      # the reference logs the length of the FULL list
             if len(dd) == 0:
                 misses += 1
                 if misses > 5 and adaptive_threshold:

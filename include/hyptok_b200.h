@@ -125,6 +125,26 @@ int hyp_allpairs_emit(const float *E, int64_t ldE, int64_t n, int D, float c, in
                       float threshold, int32_t *out_i, int32_t *out_j, float *out_d,
                       int64_t capacity, unsigned long long *count, void *stream);
 
+/* ---- the first K candidates in (d, i, j) order without materialising the list: what
+ * AdaptiveMergeCache.add_batch keeps (fast_hyperbolic_merge.py:91-95: concat, stable sort on d, truncate to
+ * max_size = 10 000) when the list has 5*10^7 entries.  A radix select over the 31 significant bits of d >= 0,
+ * driven by the host: histogram passes narrow the K-th distance down to its bit pattern, a per-row count of the
+ * pairs AT that distance finds the row where the K-th pair (row-major ties) sits, and one emit with a cut writes
+ * the <= K + n survivors, which the host sorts.  Every pass is one sweep of the exact all-pairs kernel.
+ *   hyp_allpairs_hist      hist[1 << 12] (uint64, zeroed by the callee): candidates (i < j, d < threshold) whose
+ *                          distance bits 30 .. 31 - prefix_len equal `prefix`, binned on the next `bin_bits` bits
+ *   hyp_allpairs_row_ties  row_ties[n] (zeroed by the callee): per row i, candidates (i, j) with bits(d) == d_bits
+ *   hyp_allpairs_emit_cut  hyp_allpairs_emit restricted to bits(d) < cut_bits, or == cut_bits in rows <= cut_row */
+int hyp_allpairs_hist(const float *E, int64_t ldE, int64_t n, int D, float c, int semantics,
+                      float threshold, uint32_t prefix, int prefix_len, int bin_bits,
+                      unsigned long long *hist, void *stream);
+int hyp_allpairs_row_ties(const float *E, int64_t ldE, int64_t n, int D, float c, int semantics,
+                          float threshold, uint32_t d_bits, unsigned int *row_ties, void *stream);
+int hyp_allpairs_emit_cut(const float *E, int64_t ldE, int64_t n, int D, float c, int semantics,
+                          float threshold, uint32_t cut_bits, int64_t cut_row, int32_t *out_i,
+                          int32_t *out_j, float *out_d, int64_t capacity, unsigned long long *count,
+                          void *stream);
+
 /* Exact per-row nearest neighbours (what the reference asks FAISS for, fast_hyperbolic_merge.py:
  * 301-304, hyperbolic_merge.py:217, but in the true Lorentz distance instead of Klein-L2 and
  * without sampling): for every row i of the shard [row0, row0+nrows) the k smallest (d(i,j), j)
@@ -252,7 +272,9 @@ int hyp_coherence_distances(const float *E, int64_t ldE, const int32_t *idx_i, c
  * other pairs in an open-addressing table: hash_keys[h] = (cp_a << 32 | cp_b), 0xFFFF.. = empty,
  * hash_vals[h] = count; hash_capacity must be a power of two.  The callee zeroes/initialises all
  * outputs.  *overflow (device int) != 0 if the table filled up.  Input must be valid UTF-8 (the
- * reference would raise UnicodeDecodeError otherwise). */
+ * reference would raise UnicodeDecodeError otherwise).  Two kernels with identical results serve the
+ * call, chosen on the device by the stream's alphabet (no host round trip); the verdict lives in a
+ * 256-byte per-GPU scratch the library allocates on first use -- the one hidden allocation of this ABI. */
 int hyp_pair_count(const uint8_t *text, int64_t n_bytes, unsigned long long *ascii_counts,
                    unsigned long long *hash_keys, unsigned long long *hash_vals,
                    int64_t hash_capacity, int *overflow, void *stream);

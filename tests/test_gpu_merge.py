@@ -537,3 +537,30 @@ def test_degenerate_sizes():
     with pytest.raises(ValueError):
         tok.optimize_merges(steps=1)
     assert tok.current_vocab_size == 4 and tok.vocab == list("abcd")
+
+
+@pytest.mark.parametrize("sem,scale,thr,dups", [("reference", 0.05, 0.1, 0), ("lorentz", 0.3, 1.5, 0),
+                                                ("lorentz", 0.05, 0.5, 400), ("lorentz", 0.3, 9.0, 0)])
+def test_device_topk_select_equals_sorted_list(sem, scale, thr, dups):
+    """The device radix select behind cache_semantics="snapshot" (hyp_allpairs_hist / _row_ties / _emit_cut): the first
+    K candidates in (d, i, j) order without materialising the list must be exactly the head of the fully sorted list --
+    in the shipped arithmetic (every distance 0.0: the cut is decided by row-major ties alone), in the corrected
+    geometry, with 400 duplicated rows (a block of exact ties at 0 inside a spread of distinct distances), and with the
+    early exit (a whole histogram bin emitted) disabled and enabled."""
+    from hyptokenizer_b200.synth import synthetic_embeddings, synthetic_vocab
+    from hyptokenizer_b200.tokenizer.fast_hyperbolic_merge import FastHyperbolicTokenizer
+    n = 3000
+    emb = synthetic_embeddings(n, 60, scale=scale, seed=13)
+    if dups:
+        emb[500:500 + dups] = emb[7]
+    tok = FastHyperbolicTokenizer(synthetic_vocab(n), torch.nn.Parameter(emb), merge_threshold=thr, max_vocab_size=n + 8,
+                                  semantics=sem, cache_semantics="snapshot", cache_size=2500)
+    wi, wj, wd = tok._candidate_arrays()                       # the whole list, sorted
+    total = tok._last_candidate_total
+    assert total == len(wd) and total > 10 * 2500
+    for all_limit, emit_limit in ((0, 0), (0, 1 << 14)):
+        tok._EMIT_ALL_LIMIT, tok._SELECT_EMIT_LIMIT = all_limit, emit_limit
+        gi, gj, gdd = tok._candidate_arrays()
+        assert tok._last_candidate_total == total
+        assert len(gdd) == 2500
+        assert np.array_equal(gi, wi[:2500]) and np.array_equal(gj, wj[:2500]) and same_bits(gdd, wd[:2500])

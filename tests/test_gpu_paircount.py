@@ -7,11 +7,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["v3", "v2"])
+@pytest.fixture(autouse=True, params=["auto", "v3", "v2"])
 def kernel_variant(request, monkeypatch):
-    """Every test of this file runs against the default kernel (v3: count first, correct later) and against v2 (decide
-    first); HYP_PAIR_COUNT is read at every call.  v1 has its own test below."""
-    monkeypatch.setenv("HYP_PAIR_COUNT", request.param)
+    """Every test of this file runs with the default dispatch (the device picks v3 -- count first, correct later -- or
+    v2 -- decide first -- by the stream's alphabet) and with each of the two forced; HYP_PAIR_COUNT is read at every
+    call.  v1 has its own test below."""
+    if request.param == "auto":
+        monkeypatch.delenv("HYP_PAIR_COUNT", raising=False)
+    else:
+        monkeypatch.setenv("HYP_PAIR_COUNT", request.param)
     return request.param
 
 
@@ -102,6 +106,27 @@ def test_strip_corrections_dense():
             parts.append("Q~#")                      # rare symbols: outside the 27 private ranks
     data = np.frombuffer("".join(parts).encode("ascii"), np.uint8)
     assert count_pairs(data) == count_pairs_c(data)
+
+
+def test_counter_wraps_with_repeated_symbols():
+    """One-byte private counters that wrap many times per lane, on runs of one symbol -- so that two consecutive pairs
+    keep hitting the SAME bin (the case where the second store carries both increments and a wrap must be carried
+    exactly once) -- and on a Zipf-skewed wide alphabet at a size where the hottest bins wrap in every lane."""
+    import numpy as np
+    from hyptokenizer_b200.pair_count import count_pairs
+    from oracle.pair_count import count_pairs_c
+    rng = np.random.default_rng(3)
+    n = 48 << 20
+    data = np.full(n, ord("x"), np.uint8)
+    pos = rng.integers(0, n, n // 40)
+    data[pos] = rng.choice(np.frombuffer(b"yz \n", np.uint8), size=pos.size, p=[0.4, 0.3, 0.2, 0.1])
+    assert count_pairs(data) == count_pairs_c(data)
+    alphabet = np.frombuffer((" etaoinshrdlcumwfgypbvkjxqz" "ETAOINSHRDLCUMWFGYPBVKJXQZ" "0123456789"
+                              ".,;:!?'\"()-\t").encode(), np.uint8)
+    w = 1.0 / (np.arange(len(alphabet)) + 1.5) ** 2
+    wide = rng.choice(alphabet, size=96 << 20, p=w / w.sum())
+    wide[rng.integers(0, wide.size, wide.size // 80)] = 10
+    assert count_pairs(wide) == count_pairs_c(wide)
 
 
 def test_v1_kernel_matches_too():
