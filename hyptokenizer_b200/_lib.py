@@ -82,6 +82,8 @@ _SIGNATURES = {
     "hyp_coherence_distances": ([_p, _i64, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _f, _i32, _p], C.c_int),
     "hyp_apply_merges": ([_p, _p, _i64, _p, _p, _p, _i32, _p, _p, _i64, _p, _p, _p], C.c_int),
     "hyp_pair_count": ([_p, _i64, _p, _p, _p, _i64, _p, _p], C.c_int),
+    "hyp_pair_count_sorted_workspace_bytes": ([_i64], _i64),
+    "hyp_pair_count_sorted": ([_p, _p, _p, _i64, _i64, _p, _p, _i64, _p, _p, _i64, _p], C.c_int),
 }
 
 _lib: Optional[C.CDLL] = None

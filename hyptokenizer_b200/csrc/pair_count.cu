@@ -932,13 +932,13 @@ done:
 
 // ---------------------------------------------------------------------------------------------------------------
 // Which kernel for this stream?  v3 counts every pair of the 27 most frequent symbols unconditionally and repairs the
-// rest in a cold path; that pays while the cold path is rare.  One CTA looks at 16 windows of 4 KiB spread over the
+// rest in a cold path; that pays while the cold path is rare.  One CTA looks at 8 windows of 2 KiB spread over the
 // stream: the share of bytes outside the 27 most frequent symbols of the sample (line breaks aside) and of adjacent
 // white-space bytes.  Above 0.4 % of the positions v2 -- which decides every pair before it counts, at a fixed cost --
 // is the faster one (wide alphabets, indented text).  The verdict is a device word both kernels read: the one that is
 // not chosen returns at once, so there is no host round trip.  Results are identical either way.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kSelWindows = 16, kSelWindow = 4096, kSelThreads = 1024;
+constexpr int kSelWindows = 8, kSelWindow = 2048, kSelThreads = 1024;
 __global__ void __launch_bounds__(kSelThreads)
 pair_count_select_kernel(const uint8_t *__restrict__ text, int64_t n, int *__restrict__ select) {
   __shared__ unsigned int hist[256];

@@ -86,6 +86,53 @@ def _rules_of(tok) -> Dict[Tuple[str, str], str]:
 
 def apply_rules(tok, texts: Sequence[str]):
     """Run the kernel.  Returns (table, tokens int32 numpy (flat), starts, counts)."""
+    table, d_tok, d_off, d_cnt, offsets, n = apply_rules_device(tok, texts)
+    return table, d_tok.cpu().numpy(), offsets[:-1], d_cnt.cpu().numpy()[:n]
+
+
+def count_token_pairs(tok, lines: Sequence[str]) -> Dict[Tuple[str, str], int]:
+    """`_compute_pair_frequencies` (reference frequency_aware_hyperbolic_merge.py:92-112) for a tokenizer WITH merge
+    rules: adjacent pairs of `tok.tokenize(line.strip())` over all lines, counted on the device -- batched rule
+    application (hyp_apply_merges), then 64-bit pair keys, radix sort and run-length encode (hyp_pair_count_sorted).
+    With empty rules this is the character-bigram count of pair_count.count_pairs."""
+    texts = [ln.strip() for ln in lines]
+    table, d_tok, d_off, d_cnt, offsets, n = apply_rules_device(tok, texts)
+    n_slots = int(offsets[-1])
+    if n == 0 or n_slots == 0:
+        return {}
+    dev = d_tok.device
+    L = _lib.lib()
+    nbytes = L.hyp_pair_count_sorted_workspace_bytes(n_slots)
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    wsp = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+    cap = 1 << 16
+    while True:
+        keys = torch.empty(cap, dtype=torch.int64, device=dev)
+        cnts = torch.empty(cap, dtype=torch.int64, device=dev)
+        nu = torch.zeros(1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            check(L.hyp_pair_count_sorted(ptr(d_tok), ptr(d_off), ptr(d_cnt), n, n_slots, ptr(keys), ptr(cnts), cap,
+                                          ptr(nu), wsp, nbytes, stream_ptr()))
+        m = int(nu.item())
+        if m <= cap:
+            break
+        cap = 1 << (m - 1).bit_length()
+    k = keys[:m].cpu().numpy()
+    c = cnts[:m].cpu().numpy()
+    a = (k >> 32).astype(np.int32)
+    b = (k & 0xFFFFFFFF).astype(np.uint32).view(np.int32) if m else np.empty(0, np.int32)
+    strings = table.strings
+    name = lambda v: strings[v] if v >= 0 else chr(-v - 1)
+    out: Dict[Tuple[str, str], int] = {}
+    for x, y, cnt in zip(a.tolist(), b.tolist(), c.tolist()):
+        key = (name(x), name(y))
+        out[key] = out.get(key, 0) + int(cnt)          # two ids never share a string; kept additive for safety
+    return out
+
+
+def apply_rules_device(tok, texts: Sequence[str]):
+    """Run the kernel, results stay on the device: (table, tokens int32 [n_slots], offsets int64 [n+1], counts int32
+    [n], host offsets, n)."""
     dev = tok.device
     rules = _rules_of(tok)
     cache = getattr(tok, "_rule_table", None)
@@ -107,7 +154,7 @@ def apply_rules(tok, texts: Sequence[str]):
         check(_lib.lib().hyp_apply_merges(ptr(d_text), ptr(d_off), len(blobs), ptr(table.d_ascii), ptr(table.d_cp),
                                           ptr(table.d_cp_sym), table.n_cp, ptr(table.d_keys), ptr(table.d_vals),
                                           table.capacity, ptr(d_tok), ptr(d_cnt), stream_ptr()))
-    return table, d_tok.cpu().numpy(), offsets[:-1], d_cnt.cpu().numpy()[: len(blobs)]
+    return table, d_tok, d_off, d_cnt, offsets, len(blobs)
 
 
 def tokenize_batch(tok, texts: Sequence[str]) -> List[List[str]]:

@@ -279,6 +279,19 @@ int hyp_pair_count(const uint8_t *text, int64_t n_bytes, unsigned long long *asc
                    unsigned long long *hash_keys, unsigned long long *hash_vals,
                    int64_t hash_capacity, int *overflow, void *stream);
 
+/* General path of the same count (frequency_aware_hyperbolic_merge.py:92-112 over the output of a tokenize()
+ * WITH merge rules, hyperbolic_merge.py:414-446): adjacent token-id pairs within each text, over the
+ * [offsets[t], offsets[t] + n_tokens[t]) layout hyp_apply_merges writes (`tokens` has n_slots = offsets[n_texts]
+ * int32 slots).  64-bit keys (first << 32 | second, ids as uint32), device radix sort, run-length encode:
+ * out_keys[i] ascending (by the ids biased with 2^31, i.e. negative "character without id" tokens first),
+ * out_counts[i]; *n_unique (device int64) = number of distinct pairs, which may exceed `capacity` (then only
+ * the first `capacity` were written: call again with more room).  workspace 256-byte aligned. */
+int64_t hyp_pair_count_sorted_workspace_bytes(int64_t n_slots);
+int hyp_pair_count_sorted(const int32_t *tokens, const int64_t *offsets, const int32_t *n_tokens,
+                          int64_t n_texts, int64_t n_slots, unsigned long long *out_keys,
+                          unsigned long long *out_counts, int64_t capacity, int64_t *n_unique,
+                          void *workspace, int64_t workspace_bytes, void *stream);
+
 /* ---- batched tokenize (tokenizer/hyperbolic_merge.py:414-446; what scripts/benchmark_efficiency.py
  * :58-94 measures) -------------------------------------------------------------------------------
  * n_texts UTF-8 texts, text t = bytes [offsets[t], offsets[t+1]).  Tokens are host-assigned symbol ids

@@ -43,7 +43,7 @@ def run_golden(cls, gd, r, corpus_path, device=None, inject_reference_rows=False
         from helpers import RowInjector
         assert not r["flags"]["use_adaptive_curvature"]
         fin = r["final"]
-        tok._row_injector = RowInjector(tok, from_bits(fin["embeddings"], fin["n"], d + 1).numpy(), len(vocab), max_ulp=64)
+        tok._row_injector = RowInjector(tok, from_bits(fin["embeddings"], fin["n"], d + 1).numpy(), len(vocab), max_ulp=16.0)
     merges, heads, curv = [], [], []
     merge, find = tok._merge_tokens, tok._find_merge_candidates_fast
 

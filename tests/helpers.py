@@ -48,11 +48,12 @@ class RowInjector:
     every APPENDED row.  In tie-heavy regimes (duplicated midpoint rows whose mutual product is 1 or 1 + 2^-23
     depending on one bit of x0) that can flip a later choice.  To PROVE that a divergence has this cause and no
     other, the injector wraps `_merge_tokens`: after every merge it checks that the row the device appended is
-    within `max_ulp` units in the last place of the reference's row (NaN pattern identical) and then REPLACES it by
-    the reference's bits.  If the merge sequence, candidate counts and distances are then identical to the golden
+    within `max_ulp` units in the last place OF THE ROW'S LARGEST ELEMENT of the reference's row (NaN pattern
+    identical; the small spatial elements come out of a cancellation y - <x,y> x, so their own ulp is not the measure)
+    and then REPLACES it by the reference's bits.  If the merge sequence, candidate counts and distances are then identical to the golden
     trace from the first step to the last, the only thing that separated the two runs was those last bits."""
 
-    def __init__(self, tok, ref_rows: np.ndarray, n0: int, max_ulp: int = 64):
+    def __init__(self, tok, ref_rows: np.ndarray, n0: int, max_ulp: float = 16.0):
         self.max_seen = 0
         self.rows = 0
         self.max_ulp = max_ulp
@@ -66,9 +67,12 @@ class RowInjector:
                 got = tok.embeddings.data[r].detach().cpu().numpy()
                 want = ref[r]
                 assert np.array_equal(np.isnan(got), np.isnan(want)), f"row {r}: NaN pattern differs from the reference"
-                u = int(ulp_diff(got, want).max())
-                self.max_seen = max(self.max_seen, u)
-                assert u <= self.max_ulp, f"row {r} is {u} ulp from the reference's row (> {self.max_ulp})"
+                ok = ~np.isnan(want)
+                if ok.any():
+                    scale = float(np.abs(want[ok]).max())
+                    u = float(np.abs(got[ok].astype(np.float64) - want[ok]).max() / (scale * 2.0 ** -23))
+                    self.max_seen = max(self.max_seen, u)
+                    assert u <= self.max_ulp, f"row {r} is {u:.1f} ulp (of its scale) from the reference's row (> {self.max_ulp})"
                 tok.embeddings.data[r] = torch.from_numpy(want.copy()).to(tok.embeddings.device)
                 self.rows += 1
             return out

@@ -151,7 +151,7 @@ def test_fast_snapshot_trace_strict_parity(golden):
         tok = FastHyperbolicTokenizer([f"w{k}" for k in range(300)], torch.nn.Parameter(emb),
                                       merge_threshold=run["threshold0"], max_vocab_size=1024,
                                       use_approximate_search=False, semantics="lorentz", cache_semantics="snapshot")
-        inj = RowInjector(tok, ref_rows, 300, max_ulp=64)
+        inj = RowInjector(tok, ref_rows, 300, max_ulp=16.0)
         tok.optimize_merges(steps=250, log_every=1000)
         assert [[a, b] for a, b, _ in tok.last_trace] == run["merges_ij"]
         assert tok.vocab == fin["vocab"] and [list(m) for m in tok.merge_history] == fin["merges"]

@@ -87,3 +87,39 @@ def test_after_training_roundtrip():
     assert got == [ora.tokenize(t) for t in texts]
     for t, ids in zip(texts[:200], tok.encode_batch(texts[:200])):
         assert tok.decode(ids) == t
+
+
+def test_token_pair_counts_vs_oracle():
+    """General pair counting (hyp_pair_count_sorted): adjacent pairs of tokenize(line.strip()) WITH merge rules --
+    multi-character tokens, a vocabulary-sized alphabet, characters without an id -- against the oracle's tokenize loop
+    and a Python dict, the way _compute_pair_frequencies counts (frequency_aware_hyperbolic_merge.py:92-112)."""
+    from hyptokenizer_b200.tokenizer.batch_tokenize import count_token_pairs
+    rng = random.Random(11)
+    alphabet = list("abcdefgh é中")
+    vocab = ["<pad>", "<bos>", "<eos>", "<unk>"] + alphabet
+    pool, history = list(alphabet[:8]), []
+    for _ in range(300):
+        x, y = rng.choice(pool), rng.choice(pool)
+        if len(x + y) <= 5:
+            history.append((x, y, x + y))
+            pool.append(x + y)
+    tok = make_tok(vocab + [h[2] for h in history], history)
+    ora = oracle_tok(vocab + [h[2] for h in history], history)
+    lines = []
+    for k in range(4000):
+        ln = "".join(rng.choice(alphabet + ["Z", "\U0001F600"]) for _ in range(rng.randint(0, 60)))
+        lines.append(("  " if k % 7 == 0 else "") + ln + (" \t" if k % 5 == 0 else "") + "\n")
+    lines += ["", "\n", "a\n", "   \n"]
+    want = {}
+    for ln in lines:
+        toks = ora.tokenize(ln.strip())
+        for a, b in zip(toks, toks[1:]):
+            want[(a, b)] = want.get((a, b), 0) + 1
+    got = count_token_pairs(tok, lines)
+    assert got == want
+    assert max(len(a) for a, _ in got) > 1              # multi-character tokens took part
+    # empty rules: the character-bigram count of the dense kernel
+    from hyptokenizer_b200.pair_count import count_pairs
+    plain = make_tok(vocab, [])
+    text = "".join(lines)
+    assert count_token_pairs(plain, lines) == count_pairs(text.encode("utf-8"))
