@@ -67,7 +67,9 @@ def parse():
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--ref-v0", type=int, default=REF_V0, help="vocabulary size the reference arm runs")
     ap.add_argument("--c4-bytes", type=int, default=1 << 30)
-    ap.add_argument("--c5-steps", type=int, default=300)
+    ap.add_argument("--c5-steps", type=int, default=150)
+    ap.add_argument("--c5-v0", type=int, default=2000)
+    ap.add_argument("--c5-budget-s", type=int, default=240)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-tf32-peak", action="store_true")

@@ -57,8 +57,9 @@ def run(a, env) -> dict:
     from .synth import synthetic_corpus, synthetic_embeddings
     from .tokenizer.enhanced_fast_hyperbolic_merge import EnhancedFastHyperbolicTokenizer
     import random
+    import signal
     rank, dev = env.rank, env.dev
-    v0, d, steps = a.v0, a.dim, a.c5_steps
+    v0, d, steps = a.c5_v0, a.dim, a.c5_steps
     rng = random.Random(0)
     words = set()
     while len(words) < v0 - 31:
@@ -85,13 +86,26 @@ def run(a, env) -> dict:
                  ("hyp_abi_version", "hyp_last_error", "hyp_check_device") and "workspace_bytes" not in n]
         torch.manual_seed(123)
         random.seed(5)
+        class _Budget(Exception):
+            pass
+
+        def _alarm(signum, frame):
+            raise _Budget()
+
+        old_handler = signal.signal(signal.SIGALRM, _alarm)
         with _DeviceTimer(L, names) as timer:
             t0 = time.perf_counter()
             err = None
+            signal.alarm(int(a.c5_budget_s))          # one refill scores every candidate in Python: bound the run
             try:
                 tok.optimize_merges(steps=steps, log_every=10 ** 9, adaptive_threshold=True)
             except RuntimeError as e:                 # semantics="reference": the shipped curvature step raises, as in the reference
                 err = str(e)
+            except _Budget:
+                err = f"wall budget of {a.c5_budget_s} s reached"
+            finally:
+                signal.alarm(0)
+                signal.signal(signal.SIGALRM, old_handler)
             torch.cuda.synchronize()
             wall = time.perf_counter() - t0
     finally:
@@ -110,6 +124,9 @@ def run(a, env) -> dict:
                        "device_s": dev_s, "host_s": wall - dev_s, "device_share": dev_s / wall if wall > 0 else None,
                        "device_calls": int(sum(timer.calls.values())),
                        "device_top": [{"entry": k, "s": v, "calls": timer.calls[k]} for k, v in top],
-                       "note": "host-bound by construction: Python string scoring of every candidate the cache hands out; "
-                               "device time includes the synchronisation around each call"},
+                       "candidates_last_refill": int(getattr(tok, "_last_candidate_total", -1)),
+                       "note": "host-bound by construction: Python string scoring of every candidate of a cache refill (the "
+                               "compression score re-tokenises the corpus sample per candidate, ~ms each), which is why the "
+                               "default size is V0=2000: at V0=10 000 one refill holds ~10^5 candidates and takes minutes of "
+                               "Python; device time includes the synchronisation around each call"},
             "gpu_launches": int(sum(timer.calls.values()))}

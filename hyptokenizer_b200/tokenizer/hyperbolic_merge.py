@@ -202,9 +202,7 @@ class HyperbolicTokenizer:
         if best is None:
             best = self._initial_best(_threshold_f32(self.merge_threshold, n0))
         cap = min(self.max_vocab_size, E.shape[0])   # callers may have swapped `embeddings` for a smaller tensor
-        lens = torch.zeros(cap, dtype=torch.int32)
-        lens[:n0] = torch.tensor([len(t) for t in self.vocab[:n0]], dtype=torch.int32)
-        lens = lens.to(E.device, non_blocking=True)
+        lens = self._token_lengths(cap, n0, E.device)
         st = HypMergeState(threshold=float(self.merge_threshold), n=n0, capacity=cap,
                            best_d=best.d, best_i=best.i, best_j=best.j, steps_done=0, stop=0, pad=0)
         state = ws["state"]
@@ -249,10 +247,25 @@ class HyperbolicTokenizer:
         torch.cuda.current_stream(E.device).synchronize()   # the queued no-op segments behind a stop
         rec = np.concatenate(recs) if len(recs) > 1 else recs[0]
         self._last_state = out
+        self._lens_valid = out.n          # the kernel kept len[n] = len[i] + len[j] for every row it appended
         self.merge_threshold = out.threshold if threshold_every > 0 else self.merge_threshold
         self.current_vocab_size = n
         assert self.current_vocab_size == out.n
         return rec, out.stop
+
+    def _token_lengths(self, cap: int, n: int, device) -> torch.Tensor:
+        """Device array of len(token) per row (the midpoint weights, reference :323-324).  Built from the host
+        strings once and then maintained by the loop kernel; rebuilt only when the vocabulary changed behind its back
+        (a host-side _merge_tokens, a caller editing `vocab`)."""
+        cached = getattr(self, "_lens_dev", None)
+        if (cached is not None and cached.shape[0] == cap and cached.device == device and
+                getattr(self, "_lens_valid", -1) == n and len(self.vocab) == n):
+            return cached
+        lens = torch.zeros(cap, dtype=torch.int32)
+        lens[:n] = torch.tensor([len(t) for t in self.vocab[:n]], dtype=torch.int32)
+        self._lens_dev = lens.to(device, non_blocking=True)
+        self._lens_valid = n
+        return self._lens_dev
 
     def _pinned(self, max_steps: int, nseg: int):
         """Pinned landing buffers for the merge log and the per-segment state snapshots (grown on demand)."""

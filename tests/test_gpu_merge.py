@@ -555,7 +555,8 @@ def test_device_topk_select_equals_sorted_list(sem, scale, thr, dups):
         emb[500:500 + dups] = emb[7]
     tok = FastHyperbolicTokenizer(synthetic_vocab(n), torch.nn.Parameter(emb), merge_threshold=thr, max_vocab_size=n + 8,
                                   semantics=sem, cache_semantics="snapshot", cache_size=2500)
-    wi, wj, wd = tok._candidate_arrays()                       # the whole list, sorted
+    tok._EMIT_ALL_LIMIT = 1 << 40
+    wi, wj, wd = tok._candidate_arrays()                       # the whole list, materialised and sorted
     total = tok._last_candidate_total
     assert total == len(wd) and total > 10 * 2500
     for all_limit, emit_limit in ((0, 0), (0, 1 << 14)):
