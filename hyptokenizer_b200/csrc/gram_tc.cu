@@ -548,55 +548,72 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 // One WARP per row: the row's <= 1024 tile minima sit in registers (32 per lane), and the k-th smallest is found by a
 // radix descent over the bit patterns (all values >= 1.0, so the bits order like the values), one REDUX per bit,
 // starting at the highest bit in which the row's minimum and maximum differ (the minima of one row span ~2 % of
-// their value: ~18 bits instead of 31).  The panel is read with a stride (one 32-byte sector per value), but it is
-// L2-resident (20-160 MB).  Replaces a thread-per-row insertion select whose data-dependent inserts diverged and whose
-// 100 blocks per 12 500-row shard left most SMs idle (0.13 ms of a 0.87 ms call at 8 GPUs; now ~0.02).
+// their value: ~18 bits instead of 31).  A block takes 32 rows: their slice of the [tile][row] panel is read once,
+// line by line, and transposed through shared memory.  Replaces a thread-per-row insertion select whose data-dependent
+// inserts diverged and whose 100 blocks per 12 500-row shard left most SMs idle (0.13 ms of a 0.87 ms call at 8 GPUs).
 constexpr int KS_PER_LANE = 32;
+constexpr int KS_ROWS = 32;                // rows per block: one coalesced 128-byte line of the panel per tile
+
+// k-th smallest (1-based rank k) of the warp's values v[q] = value number lane + 32 q, as a bit pattern
+__device__ __forceinline__ unsigned int warp_kth_smallest(const unsigned int (&v)[KS_PER_LANE], int64_t n_vals, int k,
+                                                          int lane) {
+  const unsigned int kInf = 0x7f800000u;
+  unsigned int lo = kInf, hi = 0;
+#pragma unroll
+  for (int q = 0; q < KS_PER_LANE; ++q) {
+    lo = min(lo, v[q]);
+    if (lane + 32 * q < n_vals) hi = max(hi, v[q]);            // (the +inf padding does not widen the span)
+  }
+  lo = __reduce_min_sync(HYP_FULL_MASK, lo);
+  hi = __reduce_max_sync(HYP_FULL_MASK, hi);
+  // bits above `top` are common to every value of the row
+  const int top = lo == hi ? -1 : 31 - __clz(lo ^ hi);
+  unsigned int prefix = top >= 31 ? 0u : (lo >> (top + 1)) << (top + 1);
+  int want = k;                                       // rank still to find among the values matching `prefix`
+  for (int bit = top; bit >= 0; --bit) {
+    unsigned int c0 = 0;
+#pragma unroll
+    for (int q = 0; q < KS_PER_LANE; ++q)
+      c0 += (((v[q] ^ prefix) >> bit) == 0u) ? 1u : 0u;          // matches the prefix above `bit` and has bit == 0
+    c0 = __reduce_add_sync(HYP_FULL_MASK, c0);
+    if ((unsigned int)want > c0) {
+      want -= (int)c0;
+      prefix |= 1u << bit;
+    }
+  }
+  // (fewer than k finite minima: the descent ends on +inf, thr = +inf, every column is a candidate and the row
+  //  overflows into the exact redo)
+  return n_vals < k ? kInf : prefix;
+}
+
 __global__ void __launch_bounds__(256)
 kth_select_warp_kernel(const float *__restrict__ tilemin, int64_t ld_tm, int64_t col_tiles, int64_t nrows,
                        int64_t row0, int k, const float *__restrict__ nrm,
                        const unsigned int *__restrict__ max_nrm_bits, float *__restrict__ thr) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  extern __shared__ float panel[];                    // [col_tiles][KS_ROWS + 1]: the block's rows, transposed on the way in
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned int kInf = 0x7f800000u;
-  for (int64_t r = warp; r < nrows; r += nwarps) {
-    unsigned int v[KS_PER_LANE];
+  for (int64_t r0 = (int64_t)blockIdx.x * KS_ROWS; r0 < nrows; r0 += (int64_t)gridDim.x * KS_ROWS) {
+    __syncthreads();
+    // tile t of the panel = 32 consecutive rows = one 128-byte line: every byte of the panel is read once, coalesced
+    for (int64_t t = warp; t < col_tiles; t += 8)
+      panel[t * (KS_ROWS + 1) + lane] = (r0 + lane < nrows) ? __ldcs(tilemin + t * ld_tm + r0 + lane) : __uint_as_float(kInf);
+    __syncthreads();
+    for (int rr = warp; rr < KS_ROWS; rr += 8) {
+      const int64_t r = r0 + rr;
+      if (r >= nrows) break;
+      unsigned int v[KS_PER_LANE];
 #pragma unroll
-    for (int q = 0; q < KS_PER_LANE; ++q) {
-      const int64_t t = lane + 32 * q;
-      v[q] = t < col_tiles ? __float_as_uint(__ldcs(tilemin + t * ld_tm + r)) : kInf;
-    }
-    unsigned int lo = kInf, hi = 0;
-#pragma unroll
-    for (int q = 0; q < KS_PER_LANE; ++q) {
-      lo = min(lo, v[q]);
-      if (lane + 32 * q < col_tiles) hi = max(hi, v[q]);        // (the +inf padding does not widen the span)
-    }
-    lo = __reduce_min_sync(HYP_FULL_MASK, lo);
-    hi = __reduce_max_sync(HYP_FULL_MASK, hi);
-    // bits above `top` are common to every value of the row
-    const int top = lo == hi ? -1 : 31 - __clz(lo ^ hi);
-    unsigned int prefix = top >= 31 ? 0u : (lo >> (top + 1)) << (top + 1);
-    int want = k;                                     // rank (1-based) still to find among the values matching `prefix`
-    for (int bit = top; bit >= 0; --bit) {
-      unsigned int c0 = 0;
-#pragma unroll
-      for (int q = 0; q < KS_PER_LANE; ++q)
-        c0 += (((v[q] ^ prefix) >> bit) == 0u) ? 1u : 0u;          // matches the prefix above `bit` and has bit == 0
-      c0 = __reduce_add_sync(HYP_FULL_MASK, c0);
-      if ((unsigned int)want > c0) {
-        want -= (int)c0;
-        prefix |= 1u << bit;
+      for (int q = 0; q < KS_PER_LANE; ++q) {
+        const int64_t t = lane + 32 * q;
+        v[q] = t < col_tiles ? __float_as_uint(panel[t * (KS_ROWS + 1) + rr]) : kInf;   // bank (t + rr) mod 32: no conflicts
       }
-    }
-    // (fewer than k finite minima: the descent ends on +inf, thr = +inf, every column is a candidate and the row
-    //  overflows into the exact redo -- the same outcome as before)
-    if (lane == 0) {
-      const float tau = col_tiles < k ? __uint_as_float(kInf) : __uint_as_float(prefix);
-      // spatial TF32 rounding (2^-9 |xs_i| |xs_j|, 5 % margin) + fp32 accumulation and the split time-like term
-      const float eps = 0.001953125f * 1.05f * nrm[row0 + r] * __uint_as_float(*max_nrm_bits) + 8e-6f * fmaxf(1.f, tau);
-      thr[r] = tau + 2.f * eps;
+      const float tau = __uint_as_float(warp_kth_smallest(v, col_tiles, k, lane));
+      if (lane == 0) {
+        // spatial TF32 rounding (2^-9 |xs_i| |xs_j|, 5 % margin) + fp32 accumulation and the split time-like term
+        const float eps = 0.001953125f * 1.05f * nrm[row0 + r] * __uint_as_float(*max_nrm_bits) + 8e-6f * fmaxf(1.f, tau);
+        thr[r] = tau + 2.f * eps;
+      }
     }
   }
 }
@@ -960,9 +977,11 @@ int gram_topk_run(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t 
   if (rc) return rc;
   if (timing) cudaEventRecord(tev[2], st);
   if (p.n_ct <= 32 * KS_PER_LANE) {
-    int64_t sb = (nrows + 7) / 8;
+    const size_t psm = (size_t)p.n_ct * (KS_ROWS + 1) * sizeof(float);
+    cudaFuncSetAttribute(kth_select_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+    int64_t sb = (nrows + KS_ROWS - 1) / KS_ROWS;
     if (sb > (int64_t)sms * 8) sb = (int64_t)sms * 8;
-    kth_select_warp_kernel<<<(int)sb, 256, 0, st>>>(tilemin, L.ld_tm, p.n_ct, nrows, row0, k, nrm, maxn, thr);
+    kth_select_warp_kernel<<<(int)sb, 256, psm, st>>>(tilemin, L.ld_tm, p.n_ct, nrows, row0, k, nrm, maxn, thr);
   } else {
     kth_select_kernel<<<(int)((nrows + 127) / 128), 128, 0, st>>>(tilemin, L.ld_tm, p.n_ct, nrows, row0, k, nrm, maxn,
                                                                   thr);
