@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--engine", default="tc", choices=["tc", "exact"])
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--ref-v0", type=int, default=REF_V0, help="vocabulary size the reference arm runs")
+    ap.add_argument("--c3-min-steps", type=int, default=40)
     ap.add_argument("--c4-bytes", type=int, default=1 << 30)
     ap.add_argument("--c5-steps", type=int, default=150)
     ap.add_argument("--c5-v0", type=int, default=2000)
@@ -400,7 +401,7 @@ def bench_c3(a, env: Env, tf32: dict | None) -> dict:
         else:
             result["rec"] = rec_local
 
-    n_steps = max(a.steps, 40)      # a step is a few ms: enough of them for the clock sampler to see the region
+    n_steps = max(a.steps, a.c3_min_steps)   # a step is a few ms: enough of them for the clock sampler to see the region
 
     def timed(fn, with_clocks=False):
         for _ in range(a.warmup):

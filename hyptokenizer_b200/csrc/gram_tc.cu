@@ -551,12 +551,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 // their value: ~18 bits instead of 31).  A block takes 32 rows: their slice of the [tile][row] panel is read once,
 // line by line, and transposed through shared memory.  Replaces a thread-per-row insertion select whose data-dependent
 // inserts diverged and whose 100 blocks per 12 500-row shard left most SMs idle (0.13 ms of a 0.87 ms call at 8 GPUs).
-constexpr int KS_PER_LANE = 32;
+constexpr int KS_PER_LANE = 32;            // most values per lane (n_ct <= 1024); the kernel is instantiated for 8 / 16 / 32
 constexpr int KS_ROWS = 32;                // rows per block: one coalesced 128-byte line of the panel per tile
 
 // k-th smallest (1-based rank k) of the warp's values v[q] = value number lane + 32 q, as a bit pattern
-__device__ __forceinline__ unsigned int warp_kth_smallest(const unsigned int (&v)[KS_PER_LANE], int64_t n_vals, int k,
-                                                          int lane) {
+template <int Q>
+__device__ __forceinline__ unsigned int warp_kth_smallest(const unsigned int (&v)[Q], int64_t n_vals, int k, int lane) {
+  constexpr int KS_PER_LANE = Q;
   const unsigned int kInf = 0x7f800000u;
   unsigned int lo = kInf, hi = 0;
 #pragma unroll
@@ -586,6 +587,7 @@ __device__ __forceinline__ unsigned int warp_kth_smallest(const unsigned int (&v
   return n_vals < k ? kInf : prefix;
 }
 
+template <int Q>
 __global__ void __launch_bounds__(256)
 kth_select_warp_kernel(const float *__restrict__ tilemin, int64_t ld_tm, int64_t col_tiles, int64_t nrows,
                        int64_t row0, int k, const float *__restrict__ nrm,
@@ -602,13 +604,13 @@ kth_select_warp_kernel(const float *__restrict__ tilemin, int64_t ld_tm, int64_t
     for (int rr = warp; rr < KS_ROWS; rr += 8) {
       const int64_t r = r0 + rr;
       if (r >= nrows) break;
-      unsigned int v[KS_PER_LANE];
+      unsigned int v[Q];
 #pragma unroll
-      for (int q = 0; q < KS_PER_LANE; ++q) {
+      for (int q = 0; q < Q; ++q) {
         const int64_t t = lane + 32 * q;
         v[q] = t < col_tiles ? __float_as_uint(panel[t * (KS_ROWS + 1) + rr]) : kInf;   // bank (t + rr) mod 32: no conflicts
       }
-      const float tau = __uint_as_float(warp_kth_smallest(v, col_tiles, k, lane));
+      const float tau = __uint_as_float(warp_kth_smallest<Q>(v, col_tiles, k, lane));
       if (lane == 0) {
         // spatial TF32 rounding (2^-9 |xs_i| |xs_j|, 5 % margin) + fp32 accumulation and the split time-like term
         const float eps = 0.001953125f * 1.05f * nrm[row0 + r] * __uint_as_float(*max_nrm_bits) + 8e-6f * fmaxf(1.f, tau);
@@ -978,10 +980,15 @@ int gram_topk_run(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t 
   if (timing) cudaEventRecord(tev[2], st);
   if (p.n_ct <= 32 * KS_PER_LANE) {
     const size_t psm = (size_t)p.n_ct * (KS_ROWS + 1) * sizeof(float);
-    cudaFuncSetAttribute(kth_select_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
     int64_t sb = (nrows + KS_ROWS - 1) / KS_ROWS;
     if (sb > (int64_t)sms * 8) sb = (int64_t)sms * 8;
-    kth_select_warp_kernel<<<(int)sb, 256, psm, st>>>(tilemin, L.ld_tm, p.n_ct, nrows, row0, k, nrm, maxn, thr);
+    auto launch_select = [&](auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+      kern<<<(int)sb, 256, psm, st>>>(tilemin, L.ld_tm, p.n_ct, nrows, row0, k, nrm, maxn, thr);
+    };
+    if (p.n_ct <= 32 * 8) launch_select(kth_select_warp_kernel<8>);
+    else if (p.n_ct <= 32 * 16) launch_select(kth_select_warp_kernel<16>);
+    else launch_select(kth_select_warp_kernel<32>);
   } else {
     kth_select_kernel<<<(int)((nrows + 127) / 128), 128, 0, st>>>(tilemin, L.ld_tm, p.n_ct, nrows, row0, k, nrm, maxn,
                                                                   thr);
