@@ -54,6 +54,7 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS + 32;   // TMA, MMA issuer 0, 
 constexpr int TC_CAND_ROW = 512;   // candidate slots per row in the workspace, split evenly over the column segments
 constexpr int TC_CAP = 384;        // most candidates of one row the finish kernel re-scores (more: exact redo)
 constexpr int TC_MAX_SEG = 16;     // column segments per row block pair
+constexpr bool kDefaultTs = false; // engine when HYP_TC_ENGINE is unset: false = both operands in shared memory
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -113,6 +114,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
+}
+// One lane of a CONVERGED warp.  The MMA warps run their loops with all 32 lanes (every operand of tcgen05.mma is then
+// provably warp-uniform and lives in uniform registers) and only the instruction itself is issued by the elected lane.
+// With the whole loop inside `if (lane == 0)` the compiler wrapped EVERY tcgen05.mma in an ELECT / 4 x R2UR.BROADCAST /
+// BRA.U.ANY waterfall: ~84 cycles per MMA from one thread, above the tensor pipe's 64.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -296,9 +306,15 @@ struct TcParams {
   int32_t *cand;      // [nrows][TC_CAND_ROW]: segment s of a row owns slots [s * seg_cap, (s + 1) * seg_cap)
   int32_t *cand_cnt;  // [nrows][TC_MAX_SEG]: hits per segment (> seg_cap == overflow)
   int seg_cap;
+  // TS engine (A operands in tensor memory): the packed A table of the shard and its row pitch in floats
+  const float *xa;
+  int kp;
 };
 
-template <int PASS>
+// NS / TB: the operand layout (full slabs, tail row bytes) as compile-time constants for the common dimensions
+// (d = 100: 3 slabs + 32-byte tail; d = 50: 2 slabs), -1 = read it from the parameters.  With constants the k-step
+// offsets of the descriptors are immediates of the uniform datapath and the MMA loop has no predicates.
+template <int PASS, int NS = -1, int TB = -1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapA_tail,
                const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapB_tail,
@@ -382,23 +398,22 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     // One thread issues every tcgen05.mma of the CTA, so its own instruction stream is the limit: the
     // descriptors of all k-steps are prepared once (low word = (address >> 4) + per-k-step offset, high word
     // constant per slab kind) and the tile loop only adds a base and issues.
-    if (lane == 0) {
+    {
       constexpr int kMaxK = TC_MAX_SLABS * 4;
-      uint32_t koff[kMaxK], khi[kMaxK];
+      const int n_slabs = NS >= 0 ? NS : p.n_slabs;
+      const int tail_b = TB >= 0 ? TB : p.tail_row_bytes;
       const uint32_t hi128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-      const uint32_t hitail = (uint32_t)((8 * p.tail_row_bytes) >> 4) | (1u << 14) |
-                              ((p.tail_row_bytes == 32 ? 6u : 4u) << 29);
-#pragma unroll
-      for (int ks = 0; ks < kMaxK; ++ks) {
+      const uint32_t hitail = (uint32_t)((8 * tail_b) >> 4) | (1u << 14) | ((tail_b == 32 ? 6u : 4u) << 29);
+      auto koff = [&](int ks) -> uint32_t {
         const int slab = ks >> 2, within = ks & 3;
-        const bool tail = slab >= p.n_slabs;
-        koff[ks] = (uint32_t)(((tail ? p.n_slabs : slab) * TC_SLAB_BYTES + within * 32) >> 4);
-        khi[ks] = tail ? hitail : hi128;
-      }
+        return (uint32_t)((((slab >= n_slabs) ? n_slabs : slab) * TC_SLAB_BYTES + within * 32) >> 4);
+      };
+      auto khi = [&](int ks) -> uint32_t { return (ks >> 2) >= n_slabs ? hitail : hi128; };
       const int h = warp == 1 ? 0 : 1;
       const uint32_t a_lo = ((smem_u32(sA + (size_t)h * p.stage_bytes) >> 4) & 0x3fff) | (1u << 16);
       const bool idle = h >= p.rb_per_cta;              // single-block mode: the second issuer only keeps the barriers moving
-      const int nk = (p.debug & 2) ? 0 : p.n_ksteps;
+      const int nk_rt = (p.debug & 2) ? 0 : p.n_ksteps;
+      const int nk = (NS >= 0 && TB >= 0) ? (p.debug & 2 ? 0 : (NS * TC_KSLAB + TB / 4) / 8) : nk_rt;
       uint32_t bstage = 0, bphase = 0, aphase = 0;
       uint32_t tt = 0;                      // tiles issued by this CTA: accumulators 2*(tt&1)+h, use number tt>>1
       for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
@@ -414,20 +429,24 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             mbar_wait(acc_empty + abuf, ((tt >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_addr = tmem_base + abuf * TC_N;
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < kMaxK; ++ks) {
-              if (ks < nk) {
-                const uint64_t ad = ((uint64_t)khi[ks] << 32) | (uint64_t)(a_lo + koff[ks]);
-                const uint64_t bd = ((uint64_t)khi[ks] << 32) | (uint64_t)(b_lo + koff[ks]);
-                umma_tf32(d_addr, ad, bd, kIdescTf32, ks > 0 ? 1u : 0u);
+              for (int ks = 0; ks < kMaxK; ++ks) {
+                if (ks < nk) {
+                  const uint64_t ad = ((uint64_t)khi(ks) << 32) | (uint64_t)(a_lo + koff(ks));
+                  const uint64_t bd = ((uint64_t)khi(ks) << 32) | (uint64_t)(b_lo + koff(ks));
+                  umma_tf32(d_addr, ad, bd, kIdescTf32, ks > 0 ? 1u : 0u);
+                }
               }
+              umma_commit(acc_full + abuf);    // this row block's accumulator is ready for its epilogue group
             }
-            umma_commit(acc_full + abuf);    // this row block's accumulator is ready for its epilogue group
           }
-          umma_commit(b_empty + bstage);     // B stage reusable once both issuers' MMAs have read it
+          if (elect_one()) umma_commit(b_empty + bstage);     // B stage reusable once both issuers' MMAs have read it
+          __syncwarp();
           if (++bstage == (uint32_t)p.n_stages) { bstage = 0; bphase ^= 1; }
         }
-        umma_commit(a_empty);                // this issuer is done with its A tile
+        if (elect_one()) umma_commit(a_empty);                // this issuer is done with its A tile
+        __syncwarp();
       }
     }
   } else {
@@ -540,6 +559,285 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, TC_ACC * TC_N);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TS engine (HYP_TC_ENGINE=ts; an alternative, not the default): the same two passes with the A operands in TENSOR MEMORY.
+//
+// The kernel above is bound by shared-memory bandwidth: every M128 x N128 x K8 MMA reads 4 KB of A and 4 KB of B from
+// shared memory, two chains per B tile, plus the TMA writes: with the epilogue switched off a full pass takes 2.18 ms =
+// 2076 cycles per B tile against 1664 at the tensor pipe's own pace and ~2040 at 128 B/clk.
+// tcgen05.mma can take A from tensor memory instead (the form
+// `[d_tmem], [a_tmem], b_desc`: row m of A on lane m, element k in column a_col + k; checked on B200 by
+// tools/ts_probe.cu): the A rows of a work item are written there ONCE per item, and an MMA then reads only B from
+// shared memory -- half the bytes.  Tensor memory has 512 columns: two row blocks' A operands take 2 x 128 (K <= 128),
+// which leaves 256 for the accumulators, so the column tile shrinks to N = 64 to keep them double-buffered for both
+// row blocks (2 blocks x 2 buffers x 64 columns).  Shared memory now holds nothing but the B ring (64 x 416 B tiles).
+// Roles as above, except that the epilogue warps of a row block also LOAD its A operand at the start of an item:
+// thread <-> row reads its packed row from global memory (26 16-byte loads, once per ~260 tiles) and stores it with
+// tcgen05.st; a_full / a_empty barriers order that against the block's MMA chain.
+// Measured (B200, V = 100 k, d = 100): results bit-identical to the SS engine on every test; a full pass takes 2.77 ms
+// against 2.57 ms -- 43 cycles per M128 x N64 x K8 MMA where the pipe's pace is 32: with half-width tiles every MMA
+// still fetches its whole 4 KB A operand, now from tensor memory, and that read rate is the new bound.  N = 128 would
+// halve it but needs all 512 columns for the accumulators alone.  Kept as a tested alternative and as the evidence for
+// that bound; the way past BOTH limits is cta_group::2 (one B tile feeding two SMs).
+// ---------------------------------------------------------------------------------------------
+constexpr int TS_N = 64;
+constexpr int TS_SLAB_BYTES = TS_N * 128;          // 8 KiB: 64 rows x 128 B
+constexpr int TS_A_BASE = 256;                     // accumulator (parity, block h) at column (2 parity + h) * 64
+constexpr int TS_A_COLS = 128;                     // columns reserved per row block's A operand
+constexpr int TS_MAX_STAGES = 6;
+constexpr uint32_t kIdescTf32N64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TS_N >> 3) << 17) |
+                                   ((uint32_t)(TC_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+template <int PASS, int NS = -1, int TB = -1>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gram_ts_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapB_tail,
+               const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *sB = base;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)p.n_stages * p.stage_bytes);
+  uint64_t *a_full = bars + 0, *a_empty = bars + 2;                                      // [2] each: per row block
+  uint64_t *acc_full = bars + 4, *acc_empty = bars + 4 + TC_ACC;                         // [TC_ACC] each
+  uint64_t *b_full = bars + 4 + 2 * TC_ACC, *b_empty = bars + 4 + 2 * TC_ACC + TS_MAX_STAGES;   // [n_stages] each
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 4 + 2 * TC_ACC + 2 * TS_MAX_STAGES);
+  const uint32_t tile_tx = p.n_slabs * TS_SLAB_BYTES + TS_N * p.tail_row_bytes;
+  const int tail_elem0 = p.n_slabs * TC_KSLAB;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row_blocks = (p.nrows + TC_M - 1) / TC_M;
+  const int64_t row_pairs = (row_blocks + p.rb_per_cta - 1) / p.rb_per_cta;
+  const int64_t items = row_pairs * p.n_seg;
+
+  if (threadIdx.x == 0) {
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(a_full + h, TC_EPI_WARPS / 2);      // one arrival per warp of the block's epilogue group
+      mbar_init(a_empty + h, 1);                    // the block's MMA issuer
+    }
+    for (int s = 0; s < TC_ACC; ++s) {
+      mbar_init(acc_full + s, 1);
+      mbar_init(acc_empty + s, TC_EPI_WARPS / 2);
+    }
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_empty + s, 2);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer: the column tiles of the item's segment, nothing else =================
+    if (lane == 0) {
+      uint32_t bstage = 0, bphase = 0;
+      for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
+        const int64_t t0 = (w % p.n_seg) * p.seg_tiles;
+        const int64_t t1 = t0 + p.seg_tiles < p.n_ct ? t0 + p.seg_tiles : p.n_ct;
+        for (int64_t t = t0; t < t1; ++t) {
+          const int64_t ct = t * p.ct_step;
+          mbar_wait(b_empty + bstage, bphase ^ 1);
+          mbar_expect_tx(b_full + bstage, tile_tx);
+          uint8_t *dst = sB + (size_t)bstage * p.stage_bytes;
+          for (int s = 0; s < p.n_slabs; ++s)
+            tma_load_2d(&tmapB, b_full + bstage, dst + s * TS_SLAB_BYTES, s * TC_KSLAB, (int)(ct * TS_N));
+          if (p.tail_row_bytes)
+            tma_load_2d(&tmapB_tail, b_full + bstage, dst + p.n_slabs * TS_SLAB_BYTES, tail_elem0, (int)(ct * TS_N));
+          if (++bstage == (uint32_t)p.n_stages) { bstage = 0; bphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2 + TC_EPI_WARPS) {
+    // ================= MMA issuers: warp 1 for row block 2rp, the last warp for row block 2rp + 1 =================
+    {
+      constexpr int kMaxK = TC_MAX_SLABS * 4;
+      const int n_slabs = NS >= 0 ? NS : p.n_slabs;
+      const int tail_b = TB >= 0 ? TB : p.tail_row_bytes;
+      const uint32_t hi128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t hitail = (uint32_t)((8 * tail_b) >> 4) | (1u << 14) | ((tail_b == 32 ? 6u : 4u) << 29);
+      auto koff = [&](int ks) -> uint32_t {
+        const int slab = ks >> 2, within = ks & 3;
+        return (uint32_t)((((slab >= n_slabs) ? n_slabs : slab) * TS_SLAB_BYTES + within * 32) >> 4);
+      };
+      auto khi = [&](int ks) -> uint32_t { return (ks >> 2) >= n_slabs ? hitail : hi128; };
+      const int h = warp == 1 ? 0 : 1;
+      const bool idle = h >= p.rb_per_cta;              // single-block mode: the second issuer only keeps the B ring moving
+      const uint32_t a_addr = tmem_base + TS_A_BASE + h * TS_A_COLS;
+      const int nk = (NS >= 0 && TB >= 0) ? (NS * TC_KSLAB + TB / 4) / 8 : p.n_ksteps;
+      uint32_t bstage = 0, bphase = 0, aphase = 0;
+      uint32_t tt = 0;                      // tiles issued by this CTA: accumulator 2*(tt&1)+h, use number tt>>1
+      for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
+        const int64_t t0 = (w % p.n_seg) * p.seg_tiles;
+        const int64_t t1 = t0 + p.seg_tiles < p.n_ct ? t0 + p.seg_tiles : p.n_ct;
+        if (!idle) {
+          mbar_wait(a_full + h, aphase);     // the block's A operand is in tensor memory
+          aphase ^= 1;
+          tc_fence_after();
+        }
+        for (int64_t t = t0; t < t1; ++t, ++tt) {
+          mbar_wait(b_full + bstage, bphase);
+          const uint32_t b_lo = ((smem_u32(sB + (size_t)bstage * p.stage_bytes) >> 4) & 0x3fff) | (1u << 16);
+          if (!idle) {
+            const uint32_t abuf = 2 * (tt & 1) + h;
+            mbar_wait(acc_empty + abuf, ((tt >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_addr = tmem_base + abuf * TS_N;
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < kMaxK; ++ks) {
+                if (ks < nk) {
+                  const uint64_t bd = ((uint64_t)khi(ks) << 32) | (uint64_t)(b_lo + koff(ks));
+                  umma_tf32_ts(d_addr, a_addr + 8 * ks, bd, kIdescTf32N64, ks > 0 ? 1u : 0u);
+                }
+              }
+              umma_commit(acc_full + abuf);
+            }
+          }
+          if (elect_one()) umma_commit(b_empty + bstage);
+          __syncwarp();
+          if (++bstage == (uint32_t)p.n_stages) { bstage = 0; bphase ^= 1; }
+        }
+        if (!idle) {
+          if (elect_one()) umma_commit(a_empty + h);  // every MMA that reads this A operand has completed
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ================= epilogue (+ A loader): warps 2..9 = two groups of four warps, one per row block =================
+    const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int lane_base = 32 * quad;
+    const int r_in_block = lane_base + lane;
+    const float inf = __int_as_float(0x7f800000);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)lane_base << 16);
+    const int a_chunks = (p.n_ksteps * 8 + 31) / 32;
+    uint32_t T = 0, ephase = 0;
+    for (int64_t w = blockIdx.x; w < items && grp < p.rb_per_cta; w += gridDim.x) {
+      const int64_t rp = w / p.n_seg;
+      const int seg = (int)(w - rp * p.n_seg);
+      const int64_t t0 = seg * p.seg_tiles;
+      const int64_t t1 = t0 + p.seg_tiles < p.n_ct ? t0 + p.seg_tiles : p.n_ct;
+      const int64_t rel = (rp * p.rb_per_cta + grp) * TC_M + r_in_block;      // row within the shard
+      const int64_t blk0 = p.row0 + (rp * p.rb_per_cta + grp) * TC_M;
+      const int64_t gi = p.row0 + rel;
+      const bool row_ok = rel < p.nrows;
+      // ---- this thread's row of the A operand -> tensor memory (the previous item's MMAs must be done with it)
+      mbar_wait(a_empty + grp, ephase ^ 1);
+      ephase ^= 1;
+      tc_fence_after();
+      {
+        const float4 *src = reinterpret_cast<const float4 *>(p.xa + (row_ok ? rel : 0) * p.kp);
+        for (int c = 0; c < a_chunks; ++c) {
+          uint32_t r[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 v = row_ok ? __ldg(src + c * 8 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            r[4 * q] = __float_as_uint(v.x); r[4 * q + 1] = __float_as_uint(v.y);
+            r[4 * q + 2] = __float_as_uint(v.z); r[4 * q + 3] = __float_as_uint(v.w);
+          }
+          tmem_st32(lane_addr + TS_A_BASE + grp * TS_A_COLS + c * 32, r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + grp);
+      }
+      const float thr = (PASS == 2 && row_ok) ? __ldg(p.thr + rel) : -inf;
+      int cnt = 0;
+      int32_t *const my_cand = p.cand + rel * TC_CAND_ROW + (int64_t)seg * p.seg_cap;
+      for (int64_t tix = t0; tix < t1; ++tix, ++T) {
+        const int64_t ct = tix * p.ct_step;
+        const uint32_t abuf = 2 * (uint32_t)(T & 1) + grp, accphase = (uint32_t)((T >> 1) & 1);
+        const int64_t j0 = ct * TS_N;
+        mbar_wait(acc_full + abuf, accphase);
+        tc_fence_after();
+        const bool checked = (j0 + TS_N > p.n) || (j0 < blk0 + TC_M && j0 + TS_N > blk0);
+        float tmin = inf;
+        const uint32_t taddr = lane_addr + abuf * TS_N;
+        auto consume = [&](int chunk, const float (&v)[32]) {
+          if (PASS == 1) {
+            if (!checked) {
+              float m4[4] = {inf, inf, inf, inf};
+#pragma unroll
+              for (int c = 0; c < 32; ++c) m4[c & 3] = fminf(m4[c & 3], v[c]);
+              tmin = fminf(tmin, fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const int64_t gj = j0 + chunk * 32 + c;
+                if (gj < p.n && gj != gi) tmin = fminf(tmin, v[c]);
+              }
+            }
+          } else {
+            uint32_t bit[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) bit[c] = v[c] <= thr ? (1u << c) : 0u;
+#pragma unroll
+            for (int wd = 16; wd >= 1; wd >>= 1)
+#pragma unroll
+              for (int c = 0; c < wd; ++c) bit[c] |= bit[c + wd];
+            uint32_t hits = bit[0];
+            while (hits) {
+              const int c = __ffs(hits) - 1;
+              hits &= hits - 1;
+              const int64_t gj = j0 + chunk * 32 + c;
+              if (!checked || (gj < p.n && gj != gi)) {
+                if (cnt < p.seg_cap) my_cand[cnt] = (int32_t)gj;
+                ++cnt;
+              }
+            }
+          }
+        };
+        {
+          float va[32], vb[32];
+          tmem_ld32_nowait(taddr, va);
+          tmem_ld32_nowait(taddr + 32, vb);
+          tmem_ld_wait();
+          tmem_pin(va);
+          tmem_pin(vb);
+          consume(0, va);
+          consume(1, vb);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + abuf);
+        if (PASS == 1 && row_ok) p.tilemin[tix * p.ld_tm + rel] = fmaxf(tmin, 1.0f);
+      }
+      if (PASS == 2 && row_ok) p.cand_cnt[rel * TC_MAX_SEG + seg] = cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -804,7 +1102,8 @@ static EncodeTiledFn get_encode() {
 
 struct TcLayout {
   int Kp, n_slabs, n_ksteps, tail_row_bytes, stage_bytes, n_stages;
-  int64_t ld_tm, col_tiles;
+  int stage_bytes_ts, n_stages_ts;     // TS engine: 64-column B tiles, nothing else in shared memory
+  int64_t ld_tm, col_tiles, col_tiles_ts;
   size_t off_xa, off_xb, off_nrm, off_max, off_tilemin, off_thr, off_cand, off_cnt, off_flist, total;
 };
 
@@ -830,6 +1129,15 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
   }
   if (L.n_stages < 1) L.n_stages = 1;
   L.col_tiles = (n + TC_N - 1) / TC_N;
+  L.col_tiles_ts = (n + TS_N - 1) / TS_N;
+  L.stage_bytes_ts = ((L.n_slabs * TS_SLAB_BYTES + TS_N * L.tail_row_bytes + 1023) / 1024) * 1024;
+  L.n_stages_ts = budget / L.stage_bytes_ts;
+  if (L.n_stages_ts > 4) L.n_stages_ts = 4;
+  if (const char *e = getenv("HYP_TC_STAGES")) {
+    const int want = atoi(e);
+    if (want >= 1 && want <= TS_MAX_STAGES && want * L.stage_bytes_ts <= budget) L.n_stages_ts = want;
+  }
+  if (L.n_stages_ts < 1) L.n_stages_ts = 1;
   L.ld_tm = ((nrows + 31) / 32) * 32;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
@@ -837,7 +1145,7 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
   L.off_xb = take((size_t)n * L.Kp * 4);       // XB: every row as a B operand
   L.off_nrm = take((size_t)n * 4);
   L.off_max = take(256);                       // [0] max norm bits, [1] number of flagged rows
-  L.off_tilemin = take((size_t)L.col_tiles * L.ld_tm * 4);
+  L.off_tilemin = take((size_t)L.col_tiles_ts * L.ld_tm * 4);      // (the TS engine's 64-column tiles: the larger panel)
   L.off_thr = take((size_t)nrows * 4);
   L.off_cand = take((size_t)nrows * TC_CAND_ROW * 4);
   L.off_cnt = take((size_t)nrows * TC_MAX_SEG * 4);
@@ -849,7 +1157,7 @@ static TcLayout tc_layout(int64_t n, int64_t nrows, int D) {
 // Work decomposition of one pass: `pairs` row block pairs (or single blocks) x n_seg column segments over `sms`
 // persistent CTAs.  Cost model in tile-times: waves * (tiles per segment + 2 for the A tiles of the item); the
 // smallest segment count that reaches the minimum wins (fewer A loads, longer candidate lists per segment).
-static void tc_segments(int64_t pairs, int64_t n_ct, int sms, int &n_seg, int64_t &seg_tiles) {
+static void tc_segments(int64_t pairs, int64_t n_ct, int sms, int &n_seg, int64_t &seg_tiles, int a_cost = 2) {
   if (n_ct < 1) n_ct = 1;
   int lo = 1, hi = TC_MAX_SEG;
   if (const char *e = getenv("HYP_TC_SEG")) {          // force a segment count (tests, tuning)
@@ -861,10 +1169,10 @@ static void tc_segments(int64_t pairs, int64_t n_ct, int sms, int &n_seg, int64_
   seg_tiles = n_ct;
   for (int S = lo; S <= hi; ++S) {
     const int64_t st = (n_ct + S - 1) / S;
-    if (lo != hi && S > 1 && st < 12) break;           // segments too short to amortise their A tiles
+    if (lo != hi && S > 1 && st < 6 * a_cost) break;   // segments too short to amortise their A operands
     const int64_t seff = (n_ct + st - 1) / st;         // no empty segments
     const int64_t waves = (pairs * seff + sms - 1) / sms;
-    const double cost = (double)waves * (double)(st + 2);
+    const double cost = (double)waves * (double)(st + a_cost);
     if (cost < best * 0.995) {
       best = cost;
       n_seg = (int)seff;
@@ -944,16 +1252,55 @@ int gram_topk_run(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t 
     }
   }
 
+  // HYP_TC_ENGINE=ts: A operands in tensor memory, 64-column tiles (gram_ts_kernel); ss: both operands in shared memory
+  const char *eng = getenv("HYP_TC_ENGINE");
+  const bool ts = eng ? (eng[0] == 't') : kDefaultTs;
+  CUtensorMap tsmaps[2];                     // TS engine: B, B tail with 64-row boxes
+  if (ts) {
+    const cuuint32_t box64[2] = {(cuuint32_t)TC_KSLAB, (cuuint32_t)TS_N};
+    const cuuint32_t tbox64[2] = {(cuuint32_t)(L.tail_row_bytes ? L.tail_row_bytes / 4 : TC_KSLAB), (cuuint32_t)TS_N};
+    for (int m = 0; m < 2; ++m) {
+      const bool tail = m == 1;
+      const CUtensorMapSwizzle sw = !tail || !L.tail_row_bytes ? CU_TENSOR_MAP_SWIZZLE_128B
+                                    : L.tail_row_bytes == 32   ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                               : CU_TENSOR_MAP_SWIZZLE_64B;
+      CUresult cr = encode(&tsmaps[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)XB, gdimB, gstride,
+                           tail ? tbox64 : box64, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) {
+        set_error("hyp_gram_topk: cuTensorMapEncodeTiled failed (%d) for TS map %d", (int)cr, m);
+        return HYP_ERR_CUDA;
+      }
+    }
+  }
+
   TcParams p{};
   p.n = n; p.row0 = row0; p.nrows = nrows; p.n_slabs = L.n_slabs; p.n_ksteps = L.n_ksteps;
-  p.tail_row_bytes = L.tail_row_bytes; p.stage_bytes = L.stage_bytes; p.n_stages = L.n_stages;
+  p.tail_row_bytes = L.tail_row_bytes; p.stage_bytes = ts ? L.stage_bytes_ts : L.stage_bytes;
+  p.n_stages = ts ? L.n_stages_ts : L.n_stages;
+  p.xa = XA; p.kp = L.Kp;
   p.debug = getenv("HYP_TC_DEBUG") ? atoi(getenv("HYP_TC_DEBUG")) : 0;
   p.tilemin = tilemin; p.ld_tm = L.ld_tm; p.thr = thr; p.cand = cand; p.cand_cnt = cnt;
-  const size_t smem = 1024 + (size_t)(2 + L.n_stages) * L.stage_bytes + (4 + 2 * TC_ACC + 2 * TC_MAX_STAGES) * 8;
+  const size_t smem = ts ? 1024 + (size_t)L.n_stages_ts * L.stage_bytes_ts + (6 + 2 * TC_ACC + 2 * TS_MAX_STAGES) * 8
+                         : 1024 + (size_t)(2 + L.n_stages) * L.stage_bytes + (4 + 2 * TC_ACC + 2 * TC_MAX_STAGES) * 8;
   auto k1 = gram_tc_kernel<1>;
   auto k2 = gram_tc_kernel<2>;
-  cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto t1 = gram_ts_kernel<1>;
+  auto t2 = gram_ts_kernel<2>;
+  if (L.n_slabs == 3 && L.tail_row_bytes == 32) {          // d in 93 .. 100
+    k1 = gram_tc_kernel<1, 3, 32>; k2 = gram_tc_kernel<2, 3, 32>; t1 = gram_ts_kernel<1, 3, 32>; t2 = gram_ts_kernel<2, 3, 32>;
+  } else if (L.n_slabs == 2 && L.tail_row_bytes == 0) {    // d in 45 .. 60
+    k1 = gram_tc_kernel<1, 2, 0>; k2 = gram_tc_kernel<2, 2, 0>; t1 = gram_ts_kernel<1, 2, 0>; t2 = gram_ts_kernel<2, 2, 0>;
+  }
+  if (ts) {
+    cudaFuncSetAttribute(t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(t2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  } else {
+    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  const int64_t col_tiles = ts ? L.col_tiles_ts : L.col_tiles;
+  const int a_cost = ts ? 8 : 2;             // an item's A operands, in tile times
   const int64_t row_blocks = (nrows + TC_M - 1) / TC_M;
   // Two row blocks per item halve the L2 -> SM traffic of the column stream (the first bound this kernel hit); the
   // column segments provide the parallelism a small shard lacks, so pairing needs only two row blocks.
@@ -965,16 +1312,17 @@ int gram_topk_run(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t 
   // column tiles does that: it visits every `step`-th tile.  The bound sits near rank k*step instead of k, so pass 2
   // collects ~step times as many candidates for the exact re-score; the two costs balance at step 2-3 at V=100k
   // (HYP_TC_SUB overrides).  Small tables keep every tile (at least 4k sampled tiles are required).
-  int step = 2;
+  int step = ts ? 4 : 2;                     // (64-column tiles: every 4th keeps the panel at the same number of minima)
   if (const char *e = getenv("HYP_TC_SUB")) step = atoi(e);
   if (step < 1) step = 1;
-  while (step > 1 && (L.col_tiles + step - 1) / step < 4 * (int64_t)k) --step;
+  while (step > 1 && (col_tiles + step - 1) / step < 4 * (int64_t)k) --step;
   p.ct_step = step;
-  p.n_ct = (L.col_tiles + step - 1) / step;
-  tc_segments(row_pairs, p.n_ct, sms, p.n_seg, p.seg_tiles);
+  p.n_ct = (col_tiles + step - 1) / step;
+  tc_segments(row_pairs, p.n_ct, sms, p.n_seg, p.seg_tiles, a_cost);
   p.seg_cap = 0;
   int64_t items = row_pairs * p.n_seg;
-  k1<<<(int)(items < sms ? items : sms), TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  if (ts) t1<<<(int)(items < sms ? items : sms), TC_THREADS, smem, st>>>(tsmaps[0], tsmaps[1], p);
+  else k1<<<(int)(items < sms ? items : sms), TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   rc = check_launch("hyp_gram_topk(pass 1)");
   if (rc) return rc;
   if (timing) cudaEventRecord(tev[2], st);
@@ -997,12 +1345,13 @@ int gram_topk_run(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t 
   if (rc) return rc;
   if (timing) cudaEventRecord(tev[3], st);
   p.ct_step = 1;
-  p.n_ct = L.col_tiles;
-  tc_segments(row_pairs, p.n_ct, sms, p.n_seg, p.seg_tiles);
+  p.n_ct = col_tiles;
+  tc_segments(row_pairs, p.n_ct, sms, p.n_seg, p.seg_tiles, a_cost);
   p.seg_cap = (TC_CAND_ROW / p.n_seg) & ~7;
   if (p.seg_cap > TC_CAP) p.seg_cap = TC_CAP;
   items = row_pairs * p.n_seg;
-  k2<<<(int)(items < sms ? items : sms), TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+  if (ts) t2<<<(int)(items < sms ? items : sms), TC_THREADS, smem, st>>>(tsmaps[0], tsmaps[1], p);
+  else k2<<<(int)(items < sms ? items : sms), TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
   rc = check_launch("hyp_gram_topk(pass 2)");
   if (rc) return rc;
   int64_t fb = (nrows + 3) / 4;
@@ -1021,8 +1370,8 @@ int gram_topk_run(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t 
     cudaEventSynchronize(tev[6]);
     float ms[6];
     for (int q = 0; q < 6; ++q) cudaEventElapsedTime(&ms[q], tev[q], tev[q + 1]);
-    fprintf(stderr, "[hyp_gram_topk] step=%d seg=%d/%d rb=%d pack %.3f  pass1 %.3f  select %.3f  pass2 %.3f  finish %.3f  "
-                    "redo %.3f ms\n", step, p.n_seg, (int)p.seg_tiles, p.rb_per_cta, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5]);
+    fprintf(stderr, "[hyp_gram_topk] %s step=%d seg=%d/%d rb=%d pack %.3f  pass1 %.3f  select %.3f  pass2 %.3f  finish %.3f  "
+                    "redo %.3f ms\n", ts ? "ts" : "ss", step, p.n_seg, (int)p.seg_tiles, p.rb_per_cta, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5]);
     for (auto &e : tev) cudaEventDestroy(e);
   }
   return rc;

@@ -8,6 +8,14 @@ from helpers import same_bits
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["ss", "ts"])
+def tc_engine(request, monkeypatch):
+    """Every test of this file runs on both tensor-core engines: "ss" (both MMA operands in shared memory, 128-column
+    tiles) and "ts" (A operands in tensor memory, 64-column tiles); HYP_TC_ENGINE is read at every call."""
+    monkeypatch.setenv("HYP_TC_ENGINE", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("n,d,k,scale,nrows,row0", [(1024, 100, 32, 0.05, None, 0), (4500, 100, 32, 0.01, None, 0),
                                                     (4500, 50, 16, 0.3, 1000, 777), (9000, 100, 32, 0.01, 3000, 6000),
                                                     (2100, 124, 8, 0.1, None, 0), (1500, 7, 4, 0.2, None, 0),
