@@ -86,25 +86,34 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line).  nvidia-smi needs a few hundred ms
+    before its first sample, longer than some timed regions: the process is started ahead of the warm-up (which runs
+    the same kernels), `mark()` is called when the timed region begins, and only samples from then on are reported
+    (all of them, flagged, if the region was too short to catch one)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.t_mark = time.time()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=self.tmp,
+                                          "-lms", "50", "-i", str(gpu_index)], stdout=self.tmp,
                                          stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
+    def mark(self):
+        self.t_mark = time.time()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        import datetime
+        t_end = time.time()
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -112,25 +121,29 @@ class ClockSampler:
             self.proc.kill()
         self.tmp.flush()
         self.tmp.seek(0)
-        sm, smax, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.tmp.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[1]))
-                smax.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]),
+                             {n for n, v in zip(names, parts[5:9]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
         os.unlink(self.tmp.name)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        inside = [r for r in rows if self.t_mark - 0.05 <= r[0] <= t_end + 0.05]
+        use = inside or rows[-3:]
+        reasons = set().union(*[r[3] for r in use])
+        out = {"sm_mhz": statistics.median(r[1] for r in use), "sm_max_mhz": max(r[2] for r in use),
+               "reasons": sorted(reasons), "samples": len(use)}
+        if not inside:
+            out["note"] = "timed region shorter than the sampling interval: the last samples of the warm-up (same kernels)"
+        return out
 
 
 class Env:
@@ -258,10 +271,12 @@ def bench_c2(a, env: Env) -> dict:
         torch.cuda.synchronize()
         return ev[0].elapsed_time(ev[2]), ev[1].elapsed_time(ev[2])
 
+    sampler = ClockSampler(env.local) if rank == 0 else None
     for _ in range(a.warmup):
         one_step(False)
     env.barrier()
-    sampler = ClockSampler(env.local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     t_total, t_loop = [], []
     for _ in range(a.steps):
         tt, tl = one_step(True)
@@ -404,10 +419,12 @@ def bench_c3(a, env: Env, tf32: dict | None) -> dict:
     n_steps = max(a.steps, a.c3_min_steps)   # a step is a few ms: enough of them for the clock sampler to see the region
 
     def timed(fn, with_clocks=False):
+        sampler = ClockSampler(env.local) if (rank == 0 and with_clocks) else None
         for _ in range(a.warmup):
             fn()
         env.barrier()
-        sampler = ClockSampler(env.local) if (rank == 0 and with_clocks) else None
+        if sampler:
+            sampler.mark()
         ts = []
         for _ in range(n_steps):
             env.flush.fill_(1)
@@ -485,7 +502,7 @@ def bench_c3(a, env: Env, tf32: dict | None) -> dict:
                                     if world > 1 else "none (1 GPU)"),
                        "rows_redone_exactly": flagged, "barrier_status": status, "l2": "flushed between timed steps",
                        "ms_local_only": ms_local, "ms_with_nccl_allgather": ms_nccl,
-                       "allgather_ms": ms_fused - ms_local},
+                       "allgather_ms": (ms_fused - ms_local) if world > 1 else 0.0},
             "gpu_launches": launches * n_steps,
             "launches_note": "per step: tc_pack, gram_tc<1>, kth_select, gram_tc<2>, tc_finish, allpairs_topk (redo, "
                              "returns at once when no row is flagged)" + (", ctx_barrier" if ctx is not None and world > 1 else ""),
@@ -524,11 +541,12 @@ def bench_c4(a, env: Env) -> dict:
     stream = torch.cuda.current_stream()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     ts, tk = [], []
-    sampler = None
+    sampler = ClockSampler(env.local) if rank == 0 else None
     for it in range(a.warmup + a.steps):
         if it == a.warmup:
             env.barrier()
-            sampler = ClockSampler(env.local) if rank == 0 else None
+            if sampler:
+                sampler.mark()
         e0.record(stream)
         check(L.hyp_pair_count(ptr(text), nbytes, ptr(asc), ptr(keys), ptr(vals), cap, ptr(ovf), stream.cuda_stream))
         e1.record(stream)

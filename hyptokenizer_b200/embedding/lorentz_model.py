@@ -59,6 +59,16 @@ def _rows(t: torch.Tensor, bshape: torch.Size, D: int) -> Tuple[torch.Tensor, in
     return te.reshape(-1, D).contiguous(), D
 
 
+def _no_grad_path(name: str, *tensors) -> None:
+    """The reference computes these functions with torch ops, so autograd flows through them.  Here only `distance`
+    and `batch_distance` carry a backward kernel (the merge loop never differentiates anything else); the others return
+    detached results.  Failing loudly beats a training loop that silently stops learning."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise RuntimeError(f"hyptokenizer_b200.embedding.lorentz_model.{name} has no backward pass: its result is detached. "
+                           "Call it under torch.no_grad() / on .detach()ed inputs, or differentiate through `distance` / "
+                           "`batch_distance`, which do carry gradients.")
+
+
 def _pair(x: torch.Tensor, y: torch.Tensor):
     dev = require_cuda(x, y)
     _lib.check_device(dev)
@@ -71,6 +81,7 @@ def _pair(x: torch.Tensor, y: torch.Tensor):
 
 def minkowski_dot(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """reference embedding/lorentz_model.py:14-25."""
+    _no_grad_path("minkowski_dot", x, y)
     dev, D, bshape, n, xr, ldx, yr, ldy = _pair(x, y)
     out = torch.empty(n, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
@@ -85,6 +96,7 @@ def minkowski_norm(x: torch.Tensor) -> torch.Tensor:
 
 def project_to_hyperboloid(x: torch.Tensor, c: float = 1.0) -> torch.Tensor:
     """reference embedding/lorentz_model.py:41-56."""
+    _no_grad_path("project_to_hyperboloid", x, c)
     dev = require_cuda(x)
     _lib.check_device(dev)
     D = x.shape[-1]
@@ -103,6 +115,7 @@ def lorentz_to_klein(x: torch.Tensor, c: float = 1.0) -> torch.Tensor:
 
 def exp_map(x: torch.Tensor, v: torch.Tensor, c: float = 1.0) -> torch.Tensor:
     """reference embedding/lorentz_model.py:73-93."""
+    _no_grad_path("exp_map", x, v)
     dev, D, bshape, n, xr, ldx, vr, ldv = _pair(x, v)
     out = torch.empty((n, D), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
@@ -112,6 +125,7 @@ def exp_map(x: torch.Tensor, v: torch.Tensor, c: float = 1.0) -> torch.Tensor:
 
 def log_map(x: torch.Tensor, y: torch.Tensor, c: float = 1.0, semantics: Optional[str] = None) -> torch.Tensor:
     """reference embedding/lorentz_model.py:96-119."""
+    _no_grad_path("log_map", x, y)
     dev, D, bshape, n, xr, ldx, yr, ldy = _pair(x, y)
     out = torch.empty((n, D), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):

@@ -135,3 +135,20 @@ def test_distortion_ratios_match_per_pair_loop():
     assert stats["num_pairs"] == 300 and abs(stats["mean"] - float(np.mean(want))) <= 1e-5 * abs(float(np.mean(want)))
     with pytest.raises(IndexError):
         distortion_ratios(E.cuda(), [(0, 500, 1.0)])
+
+
+def test_non_differentiable_ops_fail_loudly():
+    """The reference computes every Lorentz function with torch ops; here only distance / batch_distance have a
+    backward kernel.  The others must refuse inputs that require grad instead of silently returning detached results."""
+    from hyptokenizer_b200.embedding import lorentz_model as LM
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    x = synthetic_embeddings(4, 6, scale=0.3, seed=1, device="cuda").requires_grad_(True)
+    y = synthetic_embeddings(4, 6, scale=0.3, seed=2, device="cuda")
+    for fn, args in ((LM.minkowski_dot, (x, y)), (LM.exp_map, (y, x)), (LM.log_map, (x, y)), (LM.project_to_hyperboloid, (x,))):
+        with pytest.raises(RuntimeError, match="no backward pass"):
+            fn(*args)
+        with torch.no_grad():
+            fn(*args)                                   # fine when no graph is being recorded
+        fn(*[a.detach() for a in args])
+    LM.distance(x, y, semantics="lorentz").sum().backward()    # the differentiable ones still are
+    assert x.grad is not None
