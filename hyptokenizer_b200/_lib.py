@@ -79,6 +79,10 @@ _SIGNATURES = {
     "hyp_merge_steps": ([_p, _i64, _p, _i32, _f, _i32, _p, _p, _i32, _i32, _i32, C.c_double, _i32, _p, _i64, _p],
                         C.c_int),
     "hyp_row_min": ([_p, _i64, _i64, _i64, _i32, _f, _i32, _f, _p, _p, _i64, _p], C.c_int),
+    "hyp_gemv_topk_workspace_bytes": ([_i64], _i64),
+    "hyp_gemv_topk": ([_p, _i64, _i64, _p, _i64, _i32, _f, _i32, _i32, _p, _p, _p, _i64, _p], C.c_int),
+    "hyp_score_candidates": ([_p, _i64, _p, _p, _p, _p, _p, _i32, _p, _p, C.c_double, C.c_double, C.c_double, C.c_double,
+                              _p, _p, _i64, _i32, _f, _i32, _p], C.c_int),
     "hyp_coherence_distances": ([_p, _i64, _p, _p, _p, _p, _p, _i32, _p, _i64, _i32, _f, _i32, _p], C.c_int),
     "hyp_apply_merges": ([_p, _p, _i64, _p, _p, _p, _i32, _p, _p, _i64, _p, _p, _p], C.c_int),
     "hyp_pair_count": ([_p, _i64, _p, _p, _p, _i64, _p, _p], C.c_int),

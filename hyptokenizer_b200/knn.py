@@ -55,6 +55,23 @@ def lorentz_topk(E: torch.Tensor, k: int = 32, c: float = 1.0, semantics: Option
     return idx, d
 
 
+def row_topk(E: torch.Tensor, row: int, k: int = 32, c: float = 1.0, semantics: Optional[str] = None,
+             n: Optional[int] = None, q: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The k nearest rows of ONE row (or of an external query `q` of D floats; then nothing is excluded unless `row`
+    >= 0) among rows [0, n): the per-merge incremental query (hyp_gemv_topk, K4).  Returns (idx int32 [k], d fp32 [k]),
+    bit-identical to the corresponding row of lorentz_topk."""
+    E, n, _, sem = _check_table(E, n, 0, None, semantics)
+    qv = E[row] if q is None else q.detach().to(torch.float32).contiguous()
+    idx = torch.empty(k, dtype=torch.int32, device=E.device)
+    d = torch.empty(k, dtype=torch.float32, device=E.device)
+    L = _lib.lib()
+    ws = torch.empty(max(L.hyp_gemv_topk_workspace_bytes(n), 8), dtype=torch.uint8, device=E.device)
+    with torch.cuda.device(E.device):
+        check(L.hyp_gemv_topk(ptr(E), E.stride(0), n, ptr(qv), int(row), E.shape[1], float(c), sem, k, ptr(idx), ptr(d),
+                              ptr(ws), ws.numel(), stream_ptr()))
+    return idx, d
+
+
 def _check_table(E, n, row0, nrows, semantics):
     if not E.is_cuda or E.dtype != torch.float32 or E.dim() != 2:
         raise RuntimeError("lorentz_topk needs a 2-D float32 CUDA tensor (no CPU fallback)")

@@ -134,6 +134,40 @@ class FrequencyAwareHyperbolicTokenizer(HyperbolicTokenizer):
             scores.append(self.alpha * dist_score + self.beta * freq_score + self.gamma * semantic_score)
         return scores
 
+    def _score_batch_device(self, cands: List[Tuple[int, int, float]]) -> List[float]:
+        """`_score_batch` with the float64 part on the device too (hyp_score_candidates): one launch computes the
+        coherence distances, their numpy-order mean, the sigmoid and the weighted score.  Same RNG consumption; the
+        scores agree with the host path to the last bits of `exp` (not used by default: the host path IS numpy)."""
+        n = self.current_vocab_size
+        C = len(cands)
+        if C == 0:
+            return []
+        S = min(50, n)
+        E = self._table()
+        samples = torch.empty((C, S), dtype=torch.int64)
+        for c in range(C):
+            samples[c] = torch.randperm(n)[:S]
+        max_freq = max(self.pair_frequencies.values()) if self.pair_frequencies else 1
+        fs = np.empty(C, dtype=np.float64)
+        for c, (i, j, _) in enumerate(cands):
+            f = np.log1p(self.pair_frequencies.get((self.vocab[i], self.vocab[j]), 0))
+            fs[c] = f / np.log1p(max_freq) if max_freq > 0 else 0
+        dev = E.device
+        as_i32 = lambda v: torch.tensor(v, dtype=torch.int32).to(dev)
+        d_ii, d_jj = as_i32([c[0] for c in cands]), as_i32([c[1] for c in cands])
+        d_li, d_lj = as_i32([len(self.vocab[c[0]]) for c in cands]), as_i32([len(self.vocab[c[1]]) for c in cands])
+        d_dist = torch.tensor([c[2] for c in cands], dtype=torch.float32).to(dev)
+        d_fs = torch.from_numpy(fs).to(dev)
+        d_samples = samples.to(torch.int32).to(dev)
+        out = torch.empty(C, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().hyp_score_candidates(ptr(E), E.stride(0), ptr(d_ii), ptr(d_jj), ptr(d_li), ptr(d_lj),
+                                                  ptr(d_samples), S, ptr(d_dist), ptr(d_fs), float(self.alpha),
+                                                  float(self.beta), float(self.gamma), float(self.merge_threshold),
+                                                  ptr(out), None, C, E.shape[1], LM._curv(self.curvature),
+                                                  SEM[self.semantics], stream_ptr()))
+        return out.cpu().tolist()
+
     def _find_merge_candidates(self) -> List[Tuple[int, int, float]]:
         """reference :201-234: (i, j, -score), ascending (stable)."""
         candidates = super()._find_merge_candidates()

@@ -251,6 +251,14 @@ int hyp_merge_steps(float *E, int64_t ldE, int32_t *len, int D, float c, int sem
                     hyp_merge_state *state, hyp_merge_record *log, int32_t max_steps,
                     int32_t step0, int32_t threshold_every, double threshold_mul,
                     int32_t capacity_hint, void *workspace, int64_t workspace_bytes, void *stream);
+/* One row against the table, top-k form (K4): the k smallest (d(E[i], q), i) over i < n, i != exclude_row (-1: none),
+ * ascending, ties on i; q = D floats in device memory (e.g. E + row * ldE).  What one query of the reference's FAISS
+ * index returns (fast_hyperbolic_merge.py:301-304), in the true Lorentz distance; bit-identical to the row of
+ * hyp_allpairs_topk.  out_idx / out_d [k], (-1, +inf) padded.  k <= 64.  workspace: 8 n bytes. */
+int64_t hyp_gemv_topk_workspace_bytes(int64_t n);
+int hyp_gemv_topk(const float *E, int64_t ldE, int64_t n, const float *q, int64_t exclude_row, int D, float c,
+                  int semantics, int k, int32_t *out_idx, float *out_d, void *workspace,
+                  int64_t workspace_bytes, void *stream);
 /* One row against the table: argmin over i<n of (d(E[i], E[row]), i) and count below
  * threshold; the single-step building block (K4). */
 int hyp_row_min(const float *E, int64_t ldE, int64_t n, int64_t row, int D, float c, int semantics,
@@ -264,6 +272,18 @@ int hyp_row_min(const float *E, int64_t ldE, int64_t n, int64_t row, int D, floa
 int hyp_coherence_distances(const float *E, int64_t ldE, const int32_t *idx_i, const int32_t *idx_j,
                             const int32_t *len_i, const int32_t *len_j, const int32_t *sample, int S,
                             float *out, int64_t C, int D, float c, int semantics, void *stream);
+
+/* The whole candidate score of frequency_aware_hyperbolic_merge.py:114-199 on the device, float64 in the reference's
+ * operation order (numpy's pairwise mean; exp from CUDA's libm, <= 1 ulp from numpy's):
+ *   coherence[c] = 1 / (1 + exp(mean_s d(mid_c, E[sample[c][s]]) - threshold)) over the samples != i, j (0 if none),
+ *   score[c]     = alpha / (1 + dist[c]) + beta * freq_score[c] + gamma * coherence[c].
+ * dist[C]: the candidates' distances (fp32, as hyp_allpairs_emit / hyp_rescore_pairs give them); freq_score[C]:
+ * log1p(f) / log1p(f_max) from the host (a lookup by token strings).  coherence may be NULL.  S <= 64. */
+int hyp_score_candidates(const float *E, int64_t ldE, const int32_t *idx_i, const int32_t *idx_j,
+                         const int32_t *len_i, const int32_t *len_j, const int32_t *sample, int S,
+                         const float *dist, const double *freq_score, double alpha, double beta,
+                         double gamma, double threshold, double *score, double *coherence, int64_t C,
+                         int D, float c, int semantics, void *stream);
 
 /* ---- K6: pair counting (frequency_aware_hyperbolic_merge.py:92-112) ----------------------- */
 /* Adjacent code-point pairs inside each `line.strip()` of a UTF-8 byte stream (16-byte aligned),

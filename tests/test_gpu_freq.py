@@ -51,3 +51,32 @@ def test_pair_frequencies_from_file(golden, tmp_path):
     ok = {k: v for k, v in tok.pair_frequencies.items() if "|" not in k[0] + k[1]}
     assert {k: back.pair_frequencies[k] for k in ok} == ok
     assert (back.alpha, back.beta, back.gamma) == (0.4, 0.4, 0.2)
+
+
+def test_device_scoring_matches_host_scoring(tmp_path):
+    """hyp_score_candidates (coherence mean in numpy's pairwise order, sigmoid and weighted score in float64 on the
+    device) against the host path the class uses (numpy), same RNG draws: equal to the last bits of exp()."""
+    import numpy as np
+    import torch
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    from hyptokenizer_b200.tokenizer.frequency_aware_hyperbolic_merge import FrequencyAwareHyperbolicTokenizer
+    chars = list("abcdefghijklmnopqrstuvwxyz ")
+    vocab = ["<pad>", "<bos>", "<eos>", "<unk>"] + chars + [a + b for a in "abcdef" for b in "xyz"]
+    corpus = tmp_path / "c.txt"
+    corpus.write_text("the quick brown fox jumps over the lazy dog\n" * 50 + "ax by cz ax ax\n" * 20)
+    for sem, scale, thr in (("lorentz", 0.3, 2.5), ("lorentz", 0.05, 0.5), ("reference", 0.05, 0.5)):
+        emb = synthetic_embeddings(len(vocab), 24, scale=scale, seed=4)
+        tok = FrequencyAwareHyperbolicTokenizer(vocab, torch.nn.Parameter(emb), corpus_path=str(corpus),
+                                                merge_threshold=thr, max_vocab_size=len(vocab) + 8, semantics=sem)
+        cands = [(i, j, float(np.float32(0.01 * (i + j)))) for i in range(4, 40, 3) for j in range(i + 1, 49, 7)]
+        cands += [(5, 6, 0.0), (7, 48, 1.5)]
+        torch.manual_seed(77)
+        host = tok._score_batch(cands)
+        torch.manual_seed(77)
+        dev = tok._score_batch_device(cands)
+        assert len(host) == len(dev) == len(cands)
+        for h, g in zip(host, dev):
+            if h != h:
+                assert g != g                                  # the shipped arithmetic: NaN scores stay NaN
+            else:
+                assert abs(h - g) <= 1e-13 * max(abs(h), 1.0), (sem, h, g)

@@ -173,3 +173,27 @@ def test_sharded_topk_multi_gpu(tmp_path, n, k):
             gi, gd, best = r[key]
             assert torch.equal(gi, wi.cpu()) and same_bits(gd, wd.cpu()), key
             assert best == res[0]["exact/nccl"][2]
+
+
+@pytest.mark.parametrize("n,d,k,sem,scale", [(5000, 100, 32, "lorentz", 0.05), (3000, 50, 8, "lorentz", 0.3),
+                                             (700, 7, 64, "lorentz", 0.5), (2000, 100, 32, "reference", 0.05),
+                                             (20, 5, 32, "lorentz", 0.3)])
+def test_row_topk_equals_allpairs_row(n, d, k, sem, scale):
+    """hyp_gemv_topk (one row against the table, the per-merge incremental query) is bit-identical to the
+    corresponding row of the exact all-pairs top-k: same keys (d, index), NaN rows skipped, (-1, inf) padding."""
+    from hyptokenizer_b200.knn import lorentz_topk, row_topk
+    from hyptokenizer_b200.synth import synthetic_embeddings
+    E = synthetic_embeddings(n, d, scale=scale, seed=n + 1, device="cuda")
+    if n > 100:
+        E[n // 2] = float("nan")
+        E[10:14] = E[3]                                   # exact ties: index order decides
+    for row in (0, 3, n // 3, n - 1):
+        wi, wd = lorentz_topk(E, k, 1.0, sem, n, row, 1)
+        gi, gd = row_topk(E, row, k, 1.0, sem)
+        assert torch.equal(gi, wi[0]) and same_bits(gd, wd[0]), row
+    # an external query vector: nothing excluded
+    q = synthetic_embeddings(1, d, scale=scale, seed=99, device="cuda")[0]
+    gi, gd = row_topk(E, -1, k, 1.0, sem, q=q)
+    F = torch.cat([E, q[None]], 0)
+    wi, wd = lorentz_topk(F, k, 1.0, sem, n + 1, n, 1)
+    assert torch.equal(gi, wi[0]) and same_bits(gd, wd[0])
