@@ -955,6 +955,9 @@ __global__ void kth_select_kernel(const float *__restrict__ tilemin, int64_t ld_
 // exact fp32 re-score of each row's candidates (ATen order), sort by (d, j), write the first k into `sink`.
 // One warp per row.  A row whose candidate buffers overflowed (massive ties) is not written: flags[r] = 1 and the
 // row is appended to flist for the exact redo that follows on the same stream.
+// NS > 0: the spatial dimension d as a compile-time constant (100, 50): the ATen-order loops unroll without predicates
+// (the kernel is instruction-bound: 0.85e9 warp instructions per call at V = 100 k with the generic loops).
+template <int NS>
 __global__ void __launch_bounds__(128)
 tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, int64_t nrows, float sqrt_c, float sgn,
                  int k, const int32_t *__restrict__ cand, const int32_t *__restrict__ cand_cnt, int n_seg, int seg_cap,
@@ -989,15 +992,22 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
     // exact re-score, four candidates per warp pass: a group of 8 lanes IS ATen's 8 summation lanes
     // (lane l owns elements 8k+l, partial k mod 4), so the order is reproduced with 4 registers per lane
     const float *xi = E + (row0 + r) * ldE;
-    const int N = D - 1, vs = N >> 3, full = vs >> 2;
+    const int N = NS > 0 ? NS : D - 1, vs = N >> 3, full = vs >> 2;
+    constexpr int KV = NS > 0 ? (NS >> 3) : 16;      // lane vectors held in registers (d <= 128)
     const int grp = lane >> 3, l8 = lane & 7;
     if (N >= 8) {
-      // the query row's elements of this lane stay in registers for all candidates (up to 16 lane vectors: d <= 128)
-      constexpr int kInFlight = 2;   // 4 in flight was slower (128 registers, lower occupancy)
-      float xr[16];
+      // the query row's elements of this lane stay in registers for all candidates
+#ifndef HYP_FIN_INFLIGHT
+#define HYP_FIN_INFLIGHT 2
+#endif
+      constexpr int kInFlight = HYP_FIN_INFLIGHT;   // (generic loops: 4 in flight was slower -- 128 registers, lower occupancy)
+      float xr[KV];
 #pragma unroll
-      for (int kk = 0; kk < 16; ++kk) xr[kk] = kk < vs ? __ldg(xi + 1 + 8 * kk + l8) : 0.f;
+      for (int kk = 0; kk < KV; ++kk) xr[kk] = kk < vs ? __ldg(xi + 1 + 8 * kk + l8) : 0.f;
       const float xi0 = __ldg(xi);
+      float xt[7];                    // the <= 7 tail elements of the query row (N mod 8), loaded once
+#pragma unroll
+      for (int e = 0; e < 7; ++e) xt[e] = (8 * vs + e < N) ? __ldg(xi + 1 + 8 * vs + e) : 0.f;
       for (int q0 = 0; q0 < mtot; q0 += 4 * kInFlight) {
         // kInFlight candidates per 8-lane group and pass: their loads are issued together
         float Ll[kInFlight], tailv[kInFlight], xj0[kInFlight];
@@ -1009,26 +1019,29 @@ tc_finish_kernel(const float *__restrict__ E, int64_t ldE, int D, int64_t row0, 
           livev[h] = q < mtot;
           jv[h] = cj[w][livev[h] ? q : 0];
         }
-        float yv[kInFlight][16];
+        float yv[kInFlight][KV], yt[kInFlight][7];
 #pragma unroll
         for (int h = 0; h < kInFlight; ++h) {
           const float *xj = E + (int64_t)jv[h] * ldE;
 #pragma unroll
-          for (int kk = 0; kk < 16; ++kk) yv[h][kk] = kk < vs ? __ldg(xj + 1 + 8 * kk + l8) : 0.f;
+          for (int kk = 0; kk < KV; ++kk) yv[h][kk] = kk < vs ? __ldg(xj + 1 + 8 * kk + l8) : 0.f;
+#pragma unroll
+          for (int e = 0; e < 7; ++e) yt[h][e] = (8 * vs + e < N) ? __ldg(xj + 1 + 8 * vs + e) : 0.f;
           xj0[h] = __ldg(xj);
         }
 #pragma unroll
         for (int h = 0; h < kInFlight; ++h) {
-          const float *xj = E + (int64_t)jv[h] * ldE;
           float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int kk = 0; kk < 16; ++kk) {
+          for (int kk = 0; kk < KV; ++kk) {
             if (kk < 4 * full) part[kk & 3] = __fadd_rn(part[kk & 3], __fmul_rn(xr[kk], yv[h][kk]));
             else if (kk < vs) part[0] = __fadd_rn(part[0], __fmul_rn(xr[kk], yv[h][kk]));
           }
           Ll[h] = __fadd_rn(__fadd_rn(__fadd_rn(part[0], part[1]), part[2]), part[3]);
           float acc = 0.f;
-          for (int e = 8 * vs; e < N; ++e) acc = __fadd_rn(acc, __fmul_rn(__ldg(xi + 1 + e), __ldg(xj + 1 + e)));
+#pragma unroll
+          for (int e = 0; e < 7; ++e)
+            if (8 * vs + e < N) acc = __fadd_rn(acc, __fmul_rn(xt[e], yt[h][e]));
           tailv[h] = acc;
         }
 #pragma unroll
@@ -1357,8 +1370,11 @@ int gram_topk_run(const float *E, int64_t ldE, int64_t n, int64_t row0, int64_t 
   int64_t fb = (nrows + 3) / 4;
   if (fb > sms * 16) fb = sms * 16;
   if (timing) cudaEventRecord(tev[4], st);
-  tc_finish_kernel<<<(int)fb, 128, 0, st>>>(E, ldE, D, row0, nrows, sqrtf(c), sgn, k, cand, cnt, p.n_seg, p.seg_cap,
-                                           sink, row_flags, flist, nflag);
+  auto fin = tc_finish_kernel<0>;
+  if (D - 1 == 100) fin = tc_finish_kernel<100>;
+  else if (D - 1 == 50) fin = tc_finish_kernel<50>;
+  fin<<<(int)fb, 128, 0, st>>>(E, ldE, D, row0, nrows, sqrtf(c), sgn, k, cand, cnt, p.n_seg, p.seg_cap, sink, row_flags,
+                              flist, nflag);
   rc = check_launch("hyp_gram_topk(finish)");
   if (rc) return rc;
   if (timing) cudaEventRecord(tev[5], st);
