@@ -360,6 +360,40 @@ def bench_c2(a, env: Env) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
+# c2 in the SHIPPED control flow: FastHyperbolicTokenizer(cache_semantics="snapshot"), the pop-100 cache of the reference
+# ------------------------------------------------------------------------------------------------
+def bench_snapshot(a, env: Env, steps: int = 505) -> dict:
+    """The reference's FastHyperbolicTokenizer merges from a stale cache: one all-pairs candidate search per ~101
+    merges, 10 000 candidates kept (fast_hyperbolic_merge.py:63-133, :253-376).  `cache_semantics="snapshot"` replays
+    exactly that over the device kernels; this is the like-for-like of what `--impl reference` times.  Five cache cycles
+    at the benchmark's V0, both arithmetics: in the shipped one every distance is 0.0, all n (n - 1) / 2 pairs are
+    candidates and a refill is the device radix select over 5e7 ties (hyp_allpairs_hist / _row_ties / _emit_cut)."""
+    import random
+    from hyptokenizer_b200.synth import synthetic_embeddings, synthetic_vocab
+    from hyptokenizer_b200.tokenizer.fast_hyperbolic_merge import FastHyperbolicTokenizer
+    out = {}
+    for sem in ("lorentz", "reference"):
+        emb = synthetic_embeddings(a.v0, a.dim, scale=SCALE, seed=42)
+        random.seed(42)
+        tok = FastHyperbolicTokenizer(synthetic_vocab(a.v0), torch.nn.Parameter(emb), merge_threshold=THRESHOLD,
+                                      max_vocab_size=a.v0 + steps + 8, device=env.dev, semantics=sem,
+                                      cache_semantics="snapshot")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tok.optimize_merges(steps=steps, log_every=10 ** 9)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        ii, jj, dd = tok._candidate_arrays()
+        torch.cuda.synchronize()
+        refill = time.perf_counter() - t1
+        out[sem] = {"merges": len(tok.last_trace), "merges_per_s": len(tok.last_trace) / dt,
+                    "candidates_of_a_refill": int(tok._last_candidate_total), "kept": int(len(dd)),
+                    "refill_ms": 1e3 * refill}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # c3: all-pairs Lorentz distance + top-k over V=100k, row-sharded, lists all-gathered inside the timed region
 # ------------------------------------------------------------------------------------------------
 def bench_c3(a, env: Env, tf32: dict | None) -> dict:
@@ -876,6 +910,8 @@ def run_ours(a):
         line = bench_c2(a, env)
         if env.rank == 0 and not a.no_cpu_baseline and env.world == 1:
             line["cpu_baseline"] = cpu_baseline(a)
+        if env.rank == 0 and a.workload in ("all", "c2") and not a.no_e2e:
+            line["config"]["snapshot_cache_semantics"] = bench_snapshot(a, env)
         if a.workload == "all":
             # the other driver-visible figures of the path ride in the same line: numeric fields under config, full
             # lines under `secondary`

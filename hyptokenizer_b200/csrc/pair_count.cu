@@ -822,7 +822,10 @@ pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
   const int64_t interior_hi = (n - 20) / kV3Chunk;         // chunk c is interior iff 1 <= c < interior_hi
   // (Tried: two 16-byte groups per thread and step, to give the scheduler two independent streams -- 970 GB/s against
   //  1061 for this form on the config-4 stream; 16 warps racing on 8 warps' counters, as an upper bound for "more
-  //  warps": 1335.  The kernel is bound by dependent-issue latency at 2 warps per scheduler, see DESIGN.md.)
+  //  warps": 1335.  Carrying a wrapped counter where it happens -- a branch per two-pair step, the carry bin taken from
+  //  the counter's own address, no positions collected: 790 GB/s with a divergent detour, 768 with a warp vote and
+  //  predicated atomics; a branch between the steps stops ptxas from overlapping one step's loads with the previous
+  //  step's stores.  The kernel is bound by dependent-issue latency at 2 warps per scheduler, see DESIGN.md.)
 
   for (;;) {
 #pragma unroll
