@@ -825,7 +825,10 @@ pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
   //  warps": 1335.  Carrying a wrapped counter where it happens -- a branch per two-pair step, the carry bin taken from
   //  the counter's own address, no positions collected: 790 GB/s with a divergent detour, 768 with a warp vote and
   //  predicated atomics; a branch between the steps stops ptxas from overlapping one step's loads with the previous
-  //  step's stores.  The kernel is bound by dependent-issue latency at 2 warps per scheduler, see DESIGN.md.)
+  //  step's stores.  Software-pipelining the table lookups of group g + 1 in front of the updates of group g (ptxas
+  //  cannot hoist a table load over a counter store, same array): 929.  Cheaper wrap bookkeeping (the form below against
+  //  one PRMT per pair and a position loop): +1 %.  What is left is the chain of eight LDS -> +1 -> STS steps per group at
+  //  2 warps per scheduler, see DESIGN.md.)
 
   for (;;) {
 #pragma unroll
@@ -863,7 +866,9 @@ pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
         adj |= t[j + 1] & t[j + 2];
         any |= t[j] | t[j + 1];
       }
-      uint32_t wacc[4] = {0, 0, 0, 0};         // byte 3 - (i & 3) of wacc[i >> 2]: bit 0 set if the counter of pair i passed 255
+      // Which counters passed 255?  Per two-pair step one IMAD (c1 << 16 | c0: bits 8 and 24 are the wrap flags; the
+      // FMA pipe, not the ALU the rest of the loop saturates) and a four-instruction OR tree at the end of the group.
+      uint32_t e[8];
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
         const uint32_t a0 = (t[i] >> 16) + ((t[i + 1] & 0x383u) | lane4);
@@ -877,24 +882,19 @@ pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
         c1 += same ? 2u : 1u;
         col[a0] = (uint8_t)c0;
         col[a1] = (uint8_t)c1;
-        wacc[i >> 2] = __byte_perm(wacc[i >> 2], c0, 0x2105);
-        wacc[i >> 2] = __byte_perm(wacc[i >> 2], c1, 0x2105);
+        e[i >> 1] = c1 * 65536u + c0;
       }
-      // A one-byte counter passed 255: +1 in the CTA's carry table, whose bins are worth 256 at the flush.  The bin is
-      // recomputed from the text bytes; no global access, no call.
-      if ((wacc[0] | wacc[1] | wacc[2] | wacc[3]) & 0x01010101u) {
-        uint32_t wrap = 0;
+      // A one-byte counter passed 255 (some lane of the warp in 87 % of the groups): +1 in the CTA's carry table, whose
+      // bins are worth 256 at the flush.  The step index is static here, so the bin row * 28 + column comes straight
+      // from the step's table entries (the counter's address without the lane bits: (a >> 7) << 2 | a & 3).
+      if (((e[0] | e[1] | e[2]) | (e[3] | e[4] | e[5]) | (e[6] | e[7])) & 0x01000100u) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) wrap |= ((wacc[i >> 2] >> (8 * (3 - (i & 3)))) & 1u) << i;
-        while (wrap) {
-          const int i = __ffs(wrap) - 1;
-          wrap &= wrap - 1;
-          // bytes i and i + 1 of the hot view (H[4] holds byte 16)
-          const uint32_t lo = (i >> 2) == 0 ? H[0] : (i >> 2) == 1 ? H[1] : (i >> 2) == 2 ? H[2] : H[3];
-          const uint32_t hi = (i >> 2) == 0 ? H[1] : (i >> 2) == 1 ? H[2] : (i >> 2) == 2 ? H[3] : H[4];
-          const uint32_t two = __funnelshift_r(lo, hi, 8 * (i & 3));
-          const uint32_t ra = sym[two & 0xffu], rb = sym[(two >> 8) & 0xffu];
-          if (ra < kV3Junk && rb < kV3Junk) atomicAdd(&carry[ra * kV3Syms + rb], 1u);    // (junk bins wrap too)
+        for (int k = 0; k < 8; ++k) {
+          if (e[k] & 0x01000100u) {
+            const uint32_t r0 = (t[2 * k] >> 16) + (t[2 * k + 1] & 0x383u), r1 = (t[2 * k + 1] >> 16) + (t[2 * k + 2] & 0x383u);
+            if (e[k] & 0x00000100u) atomicAdd(&carry[((r0 >> 7) << 2) | (r0 & 3u)], 1u);
+            if (e[k] & 0x01000000u) atomicAdd(&carry[((r1 >> 7) << 2) | (r1 & 3u)], 1u);
+          }
         }
       }
       // white space next to white space or a line break (positions -1 .. 17), a byte outside the private alphabet
@@ -927,7 +927,7 @@ done:
     if (v) atomicAdd(ascii_counts + (uint32_t)inv[q >> 6] * 128u + inv[q & 63], (unsigned long long)v);
   }
   for (int q = tid; q < kV3Bins; q += kV3Threads) {
-    const uint32_t v = carry[q];
+    const uint32_t v = (q / kV3Syms == (int)kV3Junk || q % kV3Syms == (int)kV3Junk) ? 0u : carry[q];   // (junk bins wrap too)
     if (v) atomicAdd(ascii_counts + (uint32_t)inv[q / kV3Syms] * 128u + inv[q % kV3Syms], 256ULL * v);
   }
 }
