@@ -636,6 +636,24 @@ def bench_c4(a, env: Env) -> dict:
         # parity at the benchmark's own size (not timed): the dict of the WHOLE stream against the C restatement
         full = ref if sample.size == nbytes else count_pairs_c(host.numpy())
         line["config"]["dict_equals_oracle"] = bool(full == counts)
+    # The same call on English letter frequencies (same size): rare letters and counters that wrap, which the uniform
+    # stream of configs[3] never produces.  Reported beside the headline, dict checked against the oracle.
+    from hyptokenizer_b200.synth import english_corpus
+    eb = nbytes
+    ehost = english_corpus(eb, seed=7)
+    etext = torch.from_numpy(ehost).to(dev)
+    tz = []
+    for it in range(a.warmup + a.steps):
+        e0.record(stream)
+        check(L.hyp_pair_count(ptr(etext), eb, ptr(asc), ptr(keys), ptr(vals), cap, ptr(ovf), stream.cuda_stream))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if it >= a.warmup:
+            tz.append(e0.elapsed_time(e1))
+    line["config"]["english_letters_gbs"] = eb / (float(np.mean(tz)) * 1e-3) / 1e9
+    line["config"]["english_letters_bytes"] = eb
+    if not a.no_cpu_baseline:
+        line["config"]["english_letters_dict_equals_oracle"] = bool(count_pairs_c(ehost) == pairs_to_dict(asc, keys, vals))
     return line
 
 
@@ -930,7 +948,8 @@ def run_ours(a):
                             "c3_tf32_peak_tflops": c3["roofline"]["peak"],
                             "c4_gbs": c4["value"], "c4_kernel_gbs": c4["roofline"]["achieved"],
                             "c4_frac": c4["roofline"]["frac"],
-                            "c4_dict_equals_oracle": c4["config"].get("dict_equals_oracle")})
+                            "c4_dict_equals_oracle": c4["config"].get("dict_equals_oracle"),
+                            "c4_english_letters_gbs": c4["config"].get("english_letters_gbs")})
                 line["secondary"] = {"c3": c3, "c4": c4}
                 line["gpu_launches"] += c3["gpu_launches"] + c4["gpu_launches"]
     if env.rank == 0:

@@ -757,7 +757,7 @@ pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
                      unsigned long long *hkeys, unsigned long long *hvals, uint32_t cap_mask, int *overflow,
                      const int *__restrict__ select) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  if (select && *select != 3) return;          // the stream's alphabet chose the other kernel (pair_count_select_kernel)
+  if (*select != 3) return;                    // the stream's alphabet chose the other kernel (pair_count_select_kernel)
   uint8_t *priv = smem_raw;                                                     // [warps][28 rows][7 words][32 lanes][4]
   uint32_t *hist64 = reinterpret_cast<uint32_t *>(smem_raw + kV3Warps * kV3PrivPerWarp);   // [64*64]
   uint32_t *carry = hist64 + 64 * 64;                                           // [28*28]: wraps of the one-byte counters
@@ -770,23 +770,8 @@ pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
 
   int64_t ch = blockIdx.x;
   if (ch >= n_chunks) return;
-  for (int q = tid; q < 256; q += kV3Threads) hist64[q] = 0;
-  __syncthreads();
-  {  // frequency ranks of the ASCII bytes of this CTA's first chunk
-    const int64_t c0 = ch * kV3Chunk, c1 = (c0 + kV3Chunk < n) ? c0 + kV3Chunk : n;
-    for (int64_t b = c0 + tid; b < c1; b += kV3Threads) atomicAdd(&hist64[__ldg(text + b)], 1u);
-    __syncthreads();
-    uint32_t rank = 0xffu;
-    if (tid < 128 && tid != 0x0a && tid != 0x0d) {
-      const uint32_t mine = hist64[tid];
-      rank = 0;
-      for (int w = 0; w < 128; ++w) {
-        const uint32_t c = hist64[w];
-        rank += (w != 0x0a && w != 0x0d && (c > mine || (c == mine && w < tid))) ? 1u : 0u;
-      }
-      if (rank >= 64u) rank = 0xffu;
-    }
-    __syncthreads();
+  {  // frequency ranks of the ASCII bytes: one ranking for the whole stream (pair_count_select_kernel)
+    const uint32_t rank = tid < 128 ? reinterpret_cast<const uint8_t *>(select + 1)[tid] : 0xffu;
     if (tid < 128) {
       const uint32_t pr = rank < kV3Junk ? rank : kV3Junk;
       const uint32_t t = tid;
@@ -942,8 +927,9 @@ done:
 // not chosen returns at once, so there is no host round trip.  Results are identical either way.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSelWindows = 8, kSelWindow = 2048, kSelThreads = 1024;
+constexpr int kSelSlotInts = 64;               // one verdict slot: [0] = 2 | 3, bytes 4 .. 131 = frequency rank of ASCII byte c
 __global__ void __launch_bounds__(kSelThreads)
-pair_count_select_kernel(const uint8_t *__restrict__ text, int64_t n, int *__restrict__ select) {
+pair_count_select_kernel(const uint8_t *__restrict__ text, int64_t n, int *__restrict__ select, int force) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned int member[4];           // bit c: ASCII byte c is one of the 27 most frequent (or a line break)
   __shared__ unsigned int bad;
@@ -957,22 +943,31 @@ pair_count_select_kernel(const uint8_t *__restrict__ text, int64_t n, int *__res
   auto pos_of = [&](int64_t q) -> int64_t {    // q-th sampled byte -> position in the text
     return n > span ? (q / kSelWindow) * stride + (q % kSelWindow) : q;
   };
-  // frequency ranks from the first window only (what a counting CTA does with its first chunk)
-  const int64_t first = span < kSelWindow ? span : kSelWindow;
-  for (int64_t q = tid; q < first; q += kSelThreads) atomicAdd(&hist[__ldg(text + q)], 1u);
+  // Frequency ranks of the ASCII bytes over the whole sample, ONE ranking for every counting CTA.  (Round 2 ranked per
+  // CTA from its first 4 KiB: a letter of 0.1 % of the text is absent from a third of such chunks, loses its private
+  // bin there, and every 16-byte group that holds it takes the cold path -- half the throughput on English letter
+  // frequencies.)  Ties, absent bytes above all: lower-case letters and the space first, then by byte value.
+  for (int64_t q = tid; q < span; q += kSelThreads) atomicAdd(&hist[__ldg(text + pos_of(q))], 1u);
   __syncthreads();
   if (tid < 128) {
     bool in = tid == 0x0a || tid == 0x0d;
+    unsigned int rank = 0xffu;
     if (!in) {
-      const unsigned int mine = hist[tid];
-      unsigned int rank = 0;
+      auto key = [&](int c) -> unsigned int {
+        const unsigned int likely = ((c >= 'a' && c <= 'z') || c == ' ') ? 1u : 0u;
+        return hist[c] * 2u + likely;
+      };
+      const unsigned int mine = key(tid);
+      rank = 0;
       for (int w = 0; w < 128; ++w) {
-        const unsigned int c = hist[w];
+        const unsigned int c = key(w);
         rank += (w != 0x0a && w != 0x0d && (c > mine || (c == mine && w < tid))) ? 1u : 0u;
       }
       in = rank < 27u;
+      if (rank >= 64u) rank = 0xffu;
     }
     if (in) atomicOr(&member[tid >> 5], 1u << (tid & 31));
+    reinterpret_cast<uint8_t *>(select + 1)[tid] = (uint8_t)rank;
   }
   __syncthreads();
   unsigned int mine_bad = 0;
@@ -987,10 +982,10 @@ pair_count_select_kernel(const uint8_t *__restrict__ text, int64_t n, int *__res
   mine_bad = __reduce_add_sync(HYP_FULL_MASK, mine_bad);
   if ((tid & 31) == 0 && mine_bad) atomicAdd(&bad, mine_bad);
   __syncthreads();
-  if (tid == 0) *select = ((unsigned long long)bad * 250ull > (unsigned long long)span) ? 2 : 3;   // > 0.4 %
+  if (tid == 0) *select = force ? force : ((unsigned long long)bad * 250ull > (unsigned long long)span) ? 2 : 3;   // > 0.4 %
 }
 
-// a few device words per GPU for the selection verdicts of calls in flight (allocated on first use)
+// 16 KiB per GPU for the selection verdicts (and rank tables) of calls in flight (allocated on first use)
 static int *select_slot() {
   constexpr int kDevs = 64, kSlots = 64;
   static int *base[kDevs] = {nullptr};
@@ -998,12 +993,12 @@ static int *select_slot() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= kDevs) return nullptr;
-  if (!base[dev] && cudaMalloc((void **)&base[dev], kSlots * sizeof(int)) != cudaSuccess) {
+  if (!base[dev] && cudaMalloc((void **)&base[dev], kSlots * kSelSlotInts * sizeof(int)) != cudaSuccess) {
     cudaGetLastError();
     base[dev] = nullptr;
     return nullptr;
   }
-  return base[dev] + (next[dev]++ % kSlots);
+  return base[dev] + (size_t)(next[dev]++ % kSlots) * kSelSlotInts;
 }
 
 }  // namespace hyp
@@ -1036,14 +1031,13 @@ extern "C" int hyp_pair_count(const uint8_t *text, int64_t n_bytes, unsigned lon
   const char *ev = getenv("HYP_PAIR_COUNT");
   const int variant = (ev && ev[0] == 'v' && ev[1] >= '1' && ev[1] <= '3') ? ev[1] - '0' : 0;
   if (variant != 1) {
-    int *select = nullptr;
-    if (variant == 0) {
-      select = select_slot();
-      if (!select) {
-        set_error("hyp_pair_count: no device memory for the kernel selection word");
-        return HYP_ERR_CUDA;
-      }
-      pair_count_select_kernel<<<1, kSelThreads, 0, st>>>(text, n_bytes, select);
+    int *select = select_slot();
+    if (!select) {
+      set_error("hyp_pair_count: no device memory for the kernel selection slot");
+      return HYP_ERR_CUDA;
+    }
+    pair_count_select_kernel<<<1, kSelThreads, 0, st>>>(text, n_bytes, select, variant);
+    {
       int rc = check_launch("hyp_pair_count(select)");
       if (rc) return rc;
     }

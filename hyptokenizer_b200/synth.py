@@ -42,3 +42,26 @@ def synthetic_corpus(n_bytes: int, seed: int = 0, words_per_line: int = 20) -> n
         out[pos:pos + m] = blk
         pos += m
     return out
+
+
+_ENGLISH_LETTERS = b"etaoinshrdlcumwfgypbvkjxqz"
+_ENGLISH_FREQ = (12.7, 9.06, 8.17, 7.51, 6.97, 6.75, 6.33, 6.09, 5.99, 4.25, 4.03, 2.78, 2.76, 2.41, 2.36, 2.23, 2.02,
+                 1.97, 1.93, 1.49, 0.98, 0.77, 0.15, 0.15, 0.10, 0.07)
+
+
+def english_corpus(n_bytes: int, seed: int = 0, words_per_line: int = 20) -> np.ndarray:
+    """Like `synthetic_corpus`, but the letters follow English letter frequencies (first-order model): the same 27
+    symbols + line break, with a Zipf-like bigram distribution instead of a flat one -- rare letters (0.1 % of the
+    text) and counters that pass 255, which the uniform stream never produces."""
+    rng = np.random.default_rng(seed)
+    letters = np.frombuffer(_ENGLISH_LETTERS, np.uint8)
+    p = np.asarray(_ENGLISH_FREQ, np.float64)
+    # inverse CDF through a 65 536-entry table: frequencies quantised to 2^-16, one gather per byte
+    table = letters[np.searchsorted(np.cumsum(p / p.sum()), (np.arange(65536) + 0.5) / 65536.0).clip(0, len(letters) - 1)]
+    out = table[rng.integers(0, 65536, size=n_bytes, dtype=np.uint16)]
+    lens = rng.integers(2, 9, size=n_bytes // 3 + 8)
+    ends = np.cumsum(lens + 1) - 1
+    ends = ends[ends < n_bytes]
+    out[ends] = 32
+    out[ends[words_per_line - 1::words_per_line]] = 10
+    return out

@@ -167,6 +167,21 @@ def test_large_ascii_vs_oracle():
     assert count_pairs(("\n".join(sample)).encode("ascii")) == count_pairs_py(sample)
 
 
+def test_english_letter_frequencies_vs_oracle():
+    """48 MB with English letter frequencies: rare letters (0.07 % of the text) that a small sample may not contain, and
+    hot bigrams whose one-byte counters pass 255 many times per lane -- the full dict against the C oracle.  A stream
+    that starts with 64 KB of a different alphabet must not change the counts either (the rank table is a sample)."""
+    import numpy as np
+    from hyptokenizer_b200.pair_count import count_pairs
+    from hyptokenizer_b200.synth import english_corpus, synthetic_corpus
+    from oracle.pair_count import count_pairs_c
+    data = english_corpus(48 << 20, seed=3)
+    assert count_pairs(data) == count_pairs_c(data)
+    mixed = np.concatenate([np.frombuffer(b"0123456789 ABCDEF\n" * 3641, np.uint8)[:65536], synthetic_corpus(8 << 20, seed=1),
+                            english_corpus(8 << 20, seed=4)])
+    assert count_pairs(mixed) == count_pairs_c(mixed)
+
+
 def test_sharded_single_process_equals_plain():
     """Without a process group the sharded entry point is the plain one (one shard = the whole corpus)."""
     from hyptokenizer_b200.pair_count import count_pairs, count_pairs_sharded

@@ -10,7 +10,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from hyptokenizer_b200 import _lib  # noqa: E402
 from hyptokenizer_b200._lib import check, ptr  # noqa: E402
-from hyptokenizer_b200.synth import synthetic_corpus  # noqa: E402
+from hyptokenizer_b200.synth import english_corpus, synthetic_corpus  # noqa: E402
 
 
 def wide_corpus(nbytes, seed=0):
@@ -52,4 +52,5 @@ def run(name, host, iters=5):
 if __name__ == "__main__":
     mb = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     run("c4-stream", synthetic_corpus(mb << 20, seed=0))
+    run("english-letters", english_corpus(mb << 20))
     run("wide-alphabet", wide_corpus(mb << 20))
