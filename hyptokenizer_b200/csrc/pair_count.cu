@@ -260,7 +260,12 @@ constexpr int kV2Threads = HYP_PC_SYMS <= 28 ? 512 : 384;
 constexpr int kV2Warps = kV2Threads / 32;
 constexpr int kV2Chunk = kV2Threads * 16;                 // bytes of text per CTA step (8 KiB), one 16-byte group per thread
 constexpr int kPrivPerWarp = kPrivRows * 64;              // rows x 16 lane pairs x 4 bytes
-constexpr size_t kV2Smem = (size_t)kV2Warps * kPrivPerWarp + 64 * 64 * 4 + 512 + 512 + 1024 + 256 + 64;
+// CTA histogram (shared-memory atomics) for the pairs outside the private alphabet: the 80 most frequent symbols.  It
+// was 64 x 64 until late round 2; a 75-symbol stream then sent 7 % of its pairs to the GLOBAL table, where the atomics
+// of all SMs on a few hundred hot addresses serialise in L2 (most of the 6.1 ms per GiB of that stream).
+constexpr int kV2Hist = HYP_PC_SYMS <= 28 ? 80 : 64;
+constexpr size_t kV2Smem = (size_t)kV2Warps * kPrivPerWarp + kV2Hist * kV2Hist * 4 + 512 + 512 + 1024 + 256 + 128;
+static_assert(kV2Smem <= 232448, "v2 shared memory");
 
 // byte offset of private bin (ra, rb) inside a lane pair's column: word row (ra % kPrivDiv) * kPrivSyms + rb (16 words
 // per row), byte ra / kPrivDiv of the word
@@ -268,14 +273,14 @@ __device__ __forceinline__ uint32_t priv_off_a(uint32_t ra) { return (ra % kPriv
 __device__ __forceinline__ uint32_t priv_off_b(uint32_t rb) { return rb * 64u; }
 
 struct V2Ctx {
-  uint32_t *hist64;
-  const uint8_t *sym;            // byte -> frequency rank 0..63, 0xff = none
+  uint32_t *hist;                // [kV2Hist * kV2Hist]
+  const uint8_t *sym;            // byte -> frequency rank 0 .. kV2Hist - 1, 0xff = none
   unsigned long long *ascii_counts;
   // cold path: pairs resolved by the general scans, pairs outside the private alphabet.  It never touches the private
   // counters (a column is shared by two lanes and only the converged hot loop keeps them apart).
   __device__ __forceinline__ void add(uint32_t a, uint32_t b) const {
     const uint32_t ra = sym[a], rb = sym[b];
-    if ((ra | rb) < 64u) atomicAdd(&hist64[ra * 64u + rb], 1u);
+    if (ra < (uint32_t)kV2Hist && rb < (uint32_t)kV2Hist) atomicAdd(&hist[ra * kV2Hist + rb], 1u);
     else atomicAdd(ascii_counts + a * 128u + b, 1ULL);
   }
 };
@@ -344,10 +349,10 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
                      unsigned long long *hkeys, unsigned long long *hvals, uint32_t cap_mask, int *overflow,
                      const int *__restrict__ select) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  if (select && *select != 2) return;          // the stream's alphabet chose the other kernel (pair_count_select_kernel)
+  if (*select != 2) return;                    // the stream's alphabet chose the other kernel (pair_count_select_kernel)
   uint8_t *priv = smem_raw;                                                    // [warps][256 word rows][32 lanes][4]
-  uint32_t *hist64 = reinterpret_cast<uint32_t *>(smem_raw + kV2Warps * kPrivPerWarp);   // [64*64]
-  uint16_t *tabA = reinterpret_cast<uint16_t *>(hist64 + 64 * 64);              // byte -> priv_off_a(private rank)
+  uint32_t *hist64 = reinterpret_cast<uint32_t *>(smem_raw + kV2Warps * kPrivPerWarp);   // [kV2Hist * kV2Hist]
+  uint16_t *tabA = reinterpret_cast<uint16_t *>(hist64 + kV2Hist * kV2Hist);    // byte -> priv_off_a(private rank)
   uint16_t *tabB = tabA + 256;                                                  // byte -> priv_off_b(private rank)
   uint32_t *tabC = reinterpret_cast<uint32_t *>(tabB + 256);                    // byte -> class bits, see v2_prepare
   uint8_t *sym = reinterpret_cast<uint8_t *>(tabC + 256);                                                    // byte -> frequency rank, 0xff = none
@@ -357,23 +362,9 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
 
   int64_t ch = blockIdx.x;
   if (ch >= n_chunks) return;
-  for (int k = tid; k < 256; k += kV2Threads) hist64[k] = 0;
-  __syncthreads();
-  {  // frequency ranks of the ASCII bytes of this CTA's first chunk
-    const int64_t c0 = ch * kV2Chunk, c1 = (c0 + kV2Chunk < n) ? c0 + kV2Chunk : n;
-    for (int64_t b = c0 + tid; b < c1; b += kV2Threads) atomicAdd(&hist64[__ldg(text + b)], 1u);
-    __syncthreads();
-    uint32_t rank = 0xffu;
-    if (tid < 128 && tid != 0x0a && tid != 0x0d) {
-      const uint32_t mine = hist64[tid];
-      rank = 0;
-      for (int w = 0; w < 128; ++w) {
-        const uint32_t c = hist64[w];
-        rank += (w != 0x0a && w != 0x0d && (c > mine || (c == mine && w < tid))) ? 1u : 0u;
-      }
-      if (rank >= 64u) rank = 0xffu;
-    }
-    __syncthreads();
+  {  // frequency ranks of the ASCII bytes: one ranking for the whole stream (pair_count_select_kernel)
+    uint32_t rank = tid < 128 ? reinterpret_cast<const uint8_t *>(select + 1)[tid] : 0xffu;
+    if (rank >= (uint32_t)kV2Hist) rank = 0xffu;
     if (tid < 128) {
       const uint32_t pr = rank < kJunkRank ? rank : kJunkRank;
       sym[tid] = (uint8_t)rank;
@@ -389,7 +380,7 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
       if (rank != 0xffu) inv[rank] = (uint8_t)tid;
     }
     uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
-    const int nz = (kV2Warps * kPrivPerWarp + 64 * 64 * 4) / 16;
+    const int nz = (kV2Warps * kPrivPerWarp + kV2Hist * kV2Hist * 4) / 16;
     for (int k = tid; k < nz; k += kV2Threads) z[k] = make_uint4(0, 0, 0, 0);
     __syncthreads();
   }
@@ -418,7 +409,6 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
     // add in a phase issues nothing: the RMW is predicated.  __syncwarp orders the phases for the compiler too.
     const uint32_t mine_e = odd ? 0u : g.counted, mine_o = odd ? g.counted : 0u;
     uint32_t wacc[4] = {0, 0, 0, 0};           // byte 3 - (i & 3) of wacc[i >> 2]: 1 if the counter of pair i passed 255
-#ifndef HYP_PC_ONEPHASE
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       uint8_t *p = priv_col + (g.A[i] + g.B[i + 1]);
@@ -429,25 +419,6 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
       __syncwarp();
       wacc[i >> 2] = __byte_perm(wacc[i >> 2], l + 1u, 0x2105);
     }
-#else
-    // EXPERIMENT for round 2 (not measured, not the default; A/B with tools/ab_pair.sh and EXTRA=-DHYP_PC_ONEPHASE):
-    // one phase per update.  The two lanes of a column exchange their target offsets; when both are active on the
-    // SAME bin the even lane adds 2 and the odd lane nothing, otherwise both update (different bytes) at once.
-    (void)mine_e; (void)mine_o;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const uint32_t act = (g.counted >> i) & 1u;
-      const uint32_t o = g.A[i] + g.B[i + 1];
-      const uint32_t key = act ? o : (0x10000u | (uint32_t)lane);      // an idle lane matches nobody
-      const bool coll = __shfl_xor_sync(HYP_FULL_MASK, key, 1) == key;
-      const uint32_t inc = coll ? 2u : 1u;
-      uint8_t *p = priv_col + o;
-      uint32_t l = 0;
-      if (act && !(coll && odd)) { l = *p; *p = (uint8_t)(l + inc); }
-      __syncwarp();
-      wacc[i >> 2] = __byte_perm(wacc[i >> 2], l + inc, 0x2105);       // byte 1 of l + inc: the counter passed 255
-    }
-#endif
     uint32_t wrap = 0;                         // bit i: the counter of pair i passed 255
     if (wacc[0] | wacc[1] | wacc[2] | wacc[3]) {
 #pragma unroll
@@ -562,9 +533,9 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
         atomicAdd(ascii_counts + (uint32_t)inv[ra] * 128u + inv[rb], (unsigned long long)s);
     }
   }
-  for (int k = tid; k < 64 * 64; k += kV2Threads) {
+  for (int k = tid; k < kV2Hist * kV2Hist; k += kV2Threads) {
     const uint32_t v = hist64[k];
-    if (v) atomicAdd(ascii_counts + (uint32_t)inv[k >> 6] * 128u + inv[k & 63], (unsigned long long)v);
+    if (v) atomicAdd(ascii_counts + (uint32_t)inv[k / kV2Hist] * 128u + inv[k % kV2Hist], (unsigned long long)v);
   }
 }
 
@@ -771,7 +742,8 @@ pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
   int64_t ch = blockIdx.x;
   if (ch >= n_chunks) return;
   {  // frequency ranks of the ASCII bytes: one ranking for the whole stream (pair_count_select_kernel)
-    const uint32_t rank = tid < 128 ? reinterpret_cast<const uint8_t *>(select + 1)[tid] : 0xffu;
+    uint32_t rank = tid < 128 ? reinterpret_cast<const uint8_t *>(select + 1)[tid] : 0xffu;
+    if (rank >= 64u) rank = 0xffu;
     if (tid < 128) {
       const uint32_t pr = rank < kV3Junk ? rank : kV3Junk;
       const uint32_t t = tid;
@@ -963,8 +935,7 @@ pair_count_select_kernel(const uint8_t *__restrict__ text, int64_t n, int *__res
         const unsigned int c = key(w);
         rank += (w != 0x0a && w != 0x0d && (c > mine || (c == mine && w < tid))) ? 1u : 0u;
       }
-      in = rank < 27u;
-      if (rank >= 64u) rank = 0xffu;
+      in = rank < 27u;                         // (published as it is, 0 .. 125: each kernel keeps the ranks it has bins for)
     }
     if (in) atomicOr(&member[tid >> 5], 1u << (tid & 31));
     reinterpret_cast<uint8_t *>(select + 1)[tid] = (uint8_t)rank;
