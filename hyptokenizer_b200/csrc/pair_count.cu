@@ -561,11 +561,7 @@ pair_count_v2_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
 // Result bits are identical to v1 / v2 for any input (tests/test_gpu_paircount.py runs all three).
 constexpr int kV3Syms = 28;                                // 27 private symbols + the junk rank
 constexpr uint32_t kV3Junk = kV3Syms - 1;
-#ifdef HYP_V3_RACY16        // TIMING EXPERIMENT ONLY (wrong counts): 16 warps, warps w and w + 8 race on one block of columns
-constexpr int kV3Threads = 512, kV3Warps = 8;
-#else
 constexpr int kV3Threads = 256, kV3Warps = kV3Threads / 32;
-#endif
 constexpr int kV3Chunk = kV3Threads * 16;                  // 4 KiB of text per CTA step, one 16-byte group per thread
 constexpr int kV3RowBytes = (kV3Syms / 4) * 128;           // a row of 28 bins = 7 words per lane x 32 lanes
 constexpr int kV3PrivPerWarp = 25600;                      // 28 rows = 25 088 bytes, padded so that the low 10 bits of a
@@ -767,7 +763,7 @@ pair_count_v3_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long 
   // bits 0-1 and 7-9, 4 * lane bits 2-6: `(t & 0x383) | lane4` is one LOP3, the row is added by one LEA.HI, and the warp's
   // base rides in the address mode of LDS / STS.  volatile: the read-modify-writes of one thread stay in program order.
   volatile uint8_t *const col = priv;
-  const uint32_t lane4 = 4u * lane | (uint32_t)(warp % kV3Warps) * kV3PrivPerWarp;   // (+ the warp's block: bits 10 and up)
+  const uint32_t lane4 = 4u * lane | (uint32_t)warp * kV3PrivPerWarp;   // (+ the warp's block: bits 10 and up)
   const V3Cold cold{hist64, sym, tabC, ascii_counts, hkeys, hvals, cap_mask, overflow, text, n};
 
   const int64_t step = (int64_t)gridDim.x * kV3Chunk;
@@ -868,7 +864,7 @@ done:
   __syncthreads();
 
   // flush: private counters (sum over the warp's 32 columns per bin), then the CTA histogram
-  const uint32_t *cols = reinterpret_cast<const uint32_t *>(priv + (warp % kV3Warps) * kV3PrivPerWarp);
+  const uint32_t *cols = reinterpret_cast<const uint32_t *>(priv + warp * kV3PrivPerWarp);
   for (int g = 0; g < (int)kV3Junk * (kV3Syms / 4); ++g) {      // word rows of ranks 0 .. 26 (the junk row is dropped)
     const uint32_t w = cols[g * 32 + lane];
     const uint32_t s0 = __reduce_add_sync(HYP_FULL_MASK, w & 0xffu), s1 = __reduce_add_sync(HYP_FULL_MASK, (w >> 8) & 0xffu);
