@@ -293,8 +293,10 @@ int hyp_score_candidates(const float *E, int64_t ldE, const int32_t *idx_i, cons
  * hash_vals[h] = count; hash_capacity must be a power of two.  The callee zeroes/initialises all
  * outputs.  *overflow (device int) != 0 if the table filled up.  Input must be valid UTF-8 (the
  * reference would raise UnicodeDecodeError otherwise).  Two kernels with identical results serve the
- * call, chosen on the device by the stream's alphabet (no host round trip); the verdict lives in a
- * 256-byte per-GPU scratch the library allocates on first use -- the one hidden allocation of this ABI. */
+ * call, chosen on the device by the stream's alphabet (no host round trip): a one-CTA kernel samples 16 KiB of the
+ * stream, ranks the ASCII bytes by frequency (the counting kernels keep private counters for the 27 most frequent) and
+ * writes its verdict and the rank table into a 16 KiB per-GPU scratch (64 slots for calls in flight) the library
+ * allocates on first use -- the one hidden allocation of this ABI. */
 int hyp_pair_count(const uint8_t *text, int64_t n_bytes, unsigned long long *ascii_counts,
                    unsigned long long *hash_keys, unsigned long long *hash_vals,
                    int64_t hash_capacity, int *overflow, void *stream);
