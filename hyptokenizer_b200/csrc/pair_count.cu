@@ -228,11 +228,12 @@ pair_count_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long lon
 // v1 above retires one shared-memory atomic per input byte, and ATOMS runs at ~1 lane per clock per SM on this part:
 // 148 SMs x 1.97 GHz = the ~310 GB/s it measures, with 80 thread instructions per byte of per-position branching on top.
 // v2 removes both (680 GB/s on the same stream):
-//  * each CTA ranks the ASCII bytes of its first chunk by frequency.  Pairs of the 27 most frequent symbols are
+//  * the ASCII bytes are ranked by frequency (one ranking per stream, from the sample pair_count_select_kernel takes;
+//    until late round 2 every CTA ranked its own first chunk).  Pairs of the 27 most frequent symbols are
 //    counted in PRIVATE one-byte counters, one column of 28 x 28 bins per PAIR of lanes, word-interleaved so that column
 //    c of a warp lives in bank c (+16 in odd rows): an update is a plain LDS.U8 / +1 / STS.U8, no atomics and no bank conflicts, in two
 //    predicated phases (even lanes, then odd lanes) because two lanes share a column.  A counter that wraps carries
-//    256 into the global table.  Pairs within the 64 most frequent symbols go to a CTA histogram with ATOMS, anything
+//    256 into the global table.  Pairs within the 80 most frequent symbols go to a CTA histogram with ATOMS, anything
 //    rarer straight to the global table.  Counts stay exact for any input; the alphabet only decides how fast.
 //  * the hot loop has no data-dependent branch: a byte outside the private alphabet has the last private rank, whose row
 //    and column of the table are junk bins; the byte offset of a bin is one add of two table entries,
@@ -892,7 +893,9 @@ done:
 // stream: the share of bytes outside the 27 most frequent symbols of the sample (line breaks aside) and of adjacent
 // white-space bytes.  Above 0.4 % of the positions v2 -- which decides every pair before it counts, at a fixed cost --
 // is the faster one (wide alphabets, indented text).  The verdict is a device word both kernels read: the one that is
-// not chosen returns at once, so there is no host round trip.  Results are identical either way.
+// not chosen returns at once, so there is no host round trip.  The same kernel ranks the ASCII bytes of its sample by
+// frequency and publishes the ranks behind the verdict: both counting kernels build their lookup tables from them.
+// Results are identical either way (and for any rank table: the ranks decide how fast, never what is counted).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSelWindows = 8, kSelWindow = 2048, kSelThreads = 1024;
 constexpr int kSelSlotInts = 64;               // one verdict slot: [0] = 2 | 3, bytes 4 .. 131 = frequency rank of ASCII byte c
