@@ -9,5 +9,5 @@ for v in "$@"; do
   export HYPTOK_B200_LIB=$PWD/hyptokenizer_b200/lib/libhyptok_$v.so
   echo "== $v"
   python -m pytest tests/test_gpu_paircount.py -x -q -m gpu 2>&1 | tail -1
-  python tools/bench_pair.py "$MB" 2>&1 | tail -2
+  python tools/bench_pair.py "$MB" 2>&1 | tail -3
 done
